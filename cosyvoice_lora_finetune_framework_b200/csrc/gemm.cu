@@ -1,0 +1,357 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine for sm_100a (see gemm.h for the contraction it runs).
+//
+// One CTA computes a 128 x BN output tile. Warp 0 (one lane) streams A/B k-blocks through a
+// ring of shared-memory stages with TMA (128B-swizzled, K-major, 64 columns = one swizzle atom
+// per row); warp 1 allocates BN TMEM columns and one lane issues tcgen05.mma (M=128, N=BN, K=16,
+// fp32 accumulate in TMEM); tcgen05.commit hands stages back to the producer and finally the
+// accumulator to warps 2-5, which read it with tcgen05.ld (thread = output row) and apply the
+// fused epilogue (bias / GELU / GELU' / row mask / fp32 residual / channel-major store).
+//
+// Replaces the library calls the reference makes through torch: F.linear (lora.py:66-74,
+// modules.py:138,266-268,291,218), nn.Conv1d / ConvTranspose1d (modules.py:65,87,101,112,943,981).
+#include "gemm.h"
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+
+namespace cvflow {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, (BN == 128) ? 2 : 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barriers: full[s] at +8*s, empty[s] at +8*(kStages+s), tmem_full at +8*2*kStages, tmem ptr after
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int b = mt / p.tiles_per_batch;
+  const int i0 = (mt - b * p.tiles_per_batch) * BM;
+  const int n0 = nt * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb_global = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg sg = p.seg[s];
+        const CUtensorMap* tm = &p.tmA[sg.a_map];
+        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
+          tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.bf16, BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.nkb_total; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+        const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom
+          umma_f16_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;
+    const int orow = i * p.rmul + p.roff;
+    const bool valid = (i < p.R) && (orow < p.out_rows);
+    const long frow = (long)b * p.out_rows + orow;
+    const float rm = (valid && p.rowmask) ? p.rowmask[frow] : 1.f;
+    const int bf = p.bf16;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nn = n0 + c * 32;
+      if (nn >= p.n_valid) break;  // warp-uniform
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
+      }
+      if (p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF) {
+        if (p.aux_out) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) +
+                                                frow * p.ld_aux + nn);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack2_h16(x[8 * j + 0], x[8 * j + 1], bf);
+            v.y = pack2_h16(x[8 * j + 2], x[8 * j + 3], bf);
+            v.z = pack2_h16(x[8 * j + 4], x[8 * j + 5], bf);
+            v.w = pack2_h16(x[8 * j + 6], x[8 * j + 7], bf);
+            dst[j] = v;
+          }
+        }
+        if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
+        }
+      } else if (p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD) {
+        const uint4* src = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const uint16_t*>(p.mul_src) + frow * p.ld_aux + nn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v = __ldg(src + j);
+          float pre[8];
+          unpack2_h16(v.x, bf, pre[0], pre[1]);
+          unpack2_h16(v.y, bf, pre[2], pre[3]);
+          unpack2_h16(v.z, bf, pre[4], pre[5]);
+          unpack2_h16(v.w, bf, pre[6], pre[7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e])
+                                                               : gelu_erf_grad_f(pre[e]);
+        }
+      }
+      if (p.rowmask) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= rm;
+      }
+      if (p.resid) {
+        const float4* rs = reinterpret_cast<const float4*>(p.resid + frow * p.ldr + p.col_off + nn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = rs[j];
+          x[4 * j + 0] += v.x; x[4 * j + 1] += v.y; x[4 * j + 2] += v.z; x[4 * j + 3] += v.w;
+        }
+      }
+      if (p.transposed_out) {
+        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
+      } else if (p.out_f32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc +
+                                                p.col_off + nn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + frow * p.ldc +
+                                              p.col_off + nn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack2_h16(x[8 * j + 0], x[8 * j + 1], bf);
+          v.y = pack2_h16(x[8 * j + 2], x[8 * j + 3], bf);
+          v.z = pack2_h16(x[8 * j + 4], x[8 * j + 5], bf);
+          v.w = pack2_h16(x[8 * j + 6], x[8 * j + 7], bf);
+          dst[j] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1, uint64_t d2,
+                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                  uint32_t b2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -100;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+static int encode_2d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1,
+                     uint64_t stride1_bytes, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -100;
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+#define GEMM_FAIL(...)                          \
+  do {                                          \
+    if (err) snprintf(err, errlen, __VA_ARGS__); \
+    return -1;                                  \
+  } while (0)
+
+int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
+  memset(p, 0, sizeof(*p));
+  if (a.nseg < 1 || a.nseg > 8) GEMM_FAIL("gemm: nseg %d out of range", a.nseg);
+  if (a.Ktot % BK) GEMM_FAIL("gemm: Ktot %d not a multiple of %d", a.Ktot, BK);
+  if (!a.out || !a.W || !a.A[0]) GEMM_FAIL("gemm: null operand");
+  int nkb = 0;
+  bool use1 = false;
+  for (int s = 0; s < a.nseg; ++s) {
+    const GemmSeg& sg = a.seg[s];
+    if (sg.a_map < 0 || sg.a_map > 1 || !a.A[sg.a_map]) GEMM_FAIL("gemm: segment %d bad source", s);
+    if (sg.a_col0 % 8 || sg.a_col0 + sg.nkb * BK > a.a_cols[sg.a_map])
+      GEMM_FAIL("gemm: segment %d columns [%d,+%d) outside source (%d cols)", s, sg.a_col0,
+                sg.nkb * BK, a.a_cols[sg.a_map]);
+    use1 |= sg.a_map == 1;
+    nkb += sg.nkb;
+    p->seg[s] = sg;
+  }
+  if (nkb * BK != a.Ktot) GEMM_FAIL("gemm: segments cover %d columns, Ktot %d", nkb * BK, a.Ktot);
+  if (!a.transposed_out) {
+    if (a.n_valid % 32) GEMM_FAIL("gemm: n_valid %d must be a multiple of 32", a.n_valid);
+    if ((a.ldc % 8) || (a.col_off % 8)) GEMM_FAIL("gemm: ldc/col_off must be multiples of 8");
+  }
+  if (a.n_valid > a.N && !a.transposed_out) GEMM_FAIL("gemm: n_valid > N");
+  p->nseg = a.nseg;
+  p->nkb_total = nkb;
+  p->bf16 = a.bf16;
+  p->R = a.R; p->rmul = a.rmul; p->roff = a.roff; p->out_rows = a.out_rows; p->nbatch = a.nbatch;
+  p->tiles_per_batch = (a.R + BM - 1) / BM;
+  p->out = a.out; p->out_f32 = a.out_f32 || a.transposed_out; p->ldc = a.ldc; p->col_off = a.col_off;
+  p->n_valid = a.n_valid; p->transposed_out = a.transposed_out;
+  p->alpha = a.alpha; p->bias = a.bias; p->act = a.act; p->aux_out = a.aux_out;
+  p->mul_src = a.mul_src; p->ld_aux = a.ld_aux; p->rowmask = a.rowmask; p->resid = a.resid;
+  p->ldr = a.ldr;
+  // tile shape: 256-wide tiles only when N divides evenly and there is more than a wave of them
+  const long mtiles = (long)p->tiles_per_batch * a.nbatch;
+  int bn = 128;
+  if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= 2 * 148) bn = 256;
+  p->block_n = bn;
+  p->grid_x = (int)mtiles;
+  p->grid_y = (a.n_valid + bn - 1) / bn;
+  for (int s = 0; s < 2; ++s) {
+    if (!a.A[s] || (s == 1 && !use1)) continue;
+    if ((reinterpret_cast<uintptr_t>(a.A[s]) & 15) || (a.a_ld[s] % 8) || (a.a_bstride[s] % 8))
+      GEMM_FAIL("gemm: A[%d] must be 16-byte aligned with strides multiple of 8 elements", s);
+    int r = tma_encode_3d(&p->tmA[s], a.A[s], a.bf16, (uint64_t)a.a_cols[s], (uint64_t)a.a_rows[s],
+                          (uint64_t)a.nbatch, (uint64_t)a.a_ld[s] * 2,
+                          (uint64_t)(a.nbatch > 1 ? a.a_bstride[s] : a.a_ld[s] * (long)a.a_rows[s]) * 2,
+                          BK, BM, 1);
+    if (r) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(A[%d]) failed (%d)", s, r);
+  }
+  if (!use1) p->tmA[1] = p->tmA[0];
+  if (reinterpret_cast<uintptr_t>(a.W) & 15) GEMM_FAIL("gemm: W must be 16-byte aligned");
+  int r = encode_2d(&p->tmW, a.W, a.bf16, (uint64_t)a.Ktot, (uint64_t)a.N, (uint64_t)a.Ktot * 2, BK,
+                    bn);
+  if (r) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(W) failed (%d)", r);
+  return 0;
+}
+
+int gemm_launch(const GemmParams& p, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<256>::kSmemBytes);
+    attr_done = true;
+  }
+  dim3 grid(p.grid_x, p.grid_y);
+  if (p.block_n == 256)
+    gemm_tc_kernel<256><<<grid, 192, GemmCfg<256>::kSmemBytes, stream>>>(p);
+  else
+    gemm_tc_kernel<128><<<grid, 192, GemmCfg<128>::kSmemBytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+}  // namespace cvflow

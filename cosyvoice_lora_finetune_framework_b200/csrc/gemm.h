@@ -1,0 +1,87 @@
+// Host-side description of one implicit-GEMM launch of the tcgen05 engine (gemm.cu).
+//
+//   D[b, i, n] = epilogue( sum_seg sum_k A_seg[b, i + shift_seg, col0_seg + k] * W[n, kofs_seg + k] )
+//
+// Every dense contraction of the estimator maps onto it (SURVEY.md §2.3 K1,K3,K4,K6,K7 and their
+// dgrads): nn.Linear (1 segment, 1 batch), Conv1d k=3 (3 row-shifted segments), the two phases
+// of ConvTranspose1d / strided-conv dgrad (2 segments + interleaved output rows), stride-2 conv
+// (segments on even/odd row views) and channel-concatenated inputs (segments on two sources).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvflow {
+
+enum GemmAct { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_MUL_GELU_TANH_GRAD = 3,
+               ACT_MUL_GELU_ERF_GRAD = 4 };
+
+struct GemmSeg {
+  int a_map;      // which A source (0/1)
+  int row_shift;  // row offset added to the tile's first row (may be negative; OOB rows read 0)
+  int a_col0;     // first column of A consumed by this segment
+  int nkb;        // number of 64-column k-blocks
+};
+
+struct GemmArgs {
+  // A sources: 16-bit tensors viewed as [nbatch][a_rows][a_cols], row stride a_ld and batch stride
+  // a_bstride in elements. Rows outside [0, a_rows) read as zero (TMA out-of-bounds fill).
+  const void* A[2] = {nullptr, nullptr};
+  int a_rows[2] = {0, 0};
+  int a_cols[2] = {0, 0};
+  long a_ld[2] = {0, 0};
+  long a_bstride[2] = {0, 0};
+  int nbatch = 1;
+  // B operand: weights [N][Ktot] row-major, 16-bit, K contiguous (nn.Linear layout).
+  const void* W = nullptr;
+  int N = 0;       // rows of W (padded to a multiple of the N tile by the caller or zero-filled by TMA)
+  int Ktot = 0;
+  GemmSeg seg[8];
+  int nseg = 0;
+  int bf16 = 0;
+  // iteration space: R output-tile rows per batch; tile row i maps to output row i*rmul+roff,
+  // written iff that is < out_rows.
+  int R = 0;
+  int rmul = 1, roff = 0;
+  int out_rows = 0;  // rows per batch of the output tensor
+  // epilogue: x = acc*alpha + bias[n]; x = act(x); x *= rowmask[row]; x += resid[row][n]
+  void* out = nullptr;
+  int out_f32 = 0;
+  long ldc = 0;
+  int col_off = 0;
+  int n_valid = 0;            // columns actually stored (<= N)
+  int transposed_out = 0;     // fp32 out[(b*n_valid + n)*out_rows + row] (channel-major API edge)
+  float alpha = 1.f;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  void* aux_out = nullptr;    // ACT_GELU_*: 16-bit pre-activation stash, ld = ld_aux
+  const void* mul_src = nullptr;  // ACT_MUL_*: 16-bit pre-activation, ld = ld_aux
+  long ld_aux = 0;
+  const float* rowmask = nullptr;  // [nbatch*out_rows]
+  const float* resid = nullptr;    // fp32 [nbatch*out_rows][ldr] (may alias out)
+  long ldr = 0;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmW;
+  GemmSeg seg[8];
+  int nseg, nkb_total;
+  int bf16;
+  int R, rmul, roff, out_rows, nbatch, tiles_per_batch;
+  void* out; int out_f32; long ldc; int col_off; int n_valid; int transposed_out;
+  float alpha; const float* bias; int act; void* aux_out; const void* mul_src; long ld_aux;
+  const float* rowmask; const float* resid; long ldr;
+  int block_n;   // 128 or 256
+  int grid_x, grid_y;
+};
+
+// Encode tensor maps and pick the tile shape. Returns 0 or a negative error (message via err).
+int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen);
+int gemm_launch(const GemmParams& p, cudaStream_t stream);
+// One-off: fetch cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).
+int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1, uint64_t d2,
+                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                  uint32_t b2);
+
+}  // namespace cvflow
