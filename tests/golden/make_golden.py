@@ -1,0 +1,163 @@
+"""Generate golden vectors by running the REAL reference implementation (read-only checkout at
+/root/reference) on seeded synthetic weights and inputs. Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference; tests read the committed .pt files. Weights are not stored:
+they are a pure function of (parameter name, shape, seed) - oracle.flow_oracle.synth_tensor - and
+each fixture records a checksum so a drift in that generator is detected.
+"""
+import os
+import sys
+
+import torch
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("CVFLOW_REF", "/root/reference/cosyvoice_flow_finetune")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import flow_model as ref_flow          # noqa: E402  (reference)
+import lora as ref_lora                # noqa: E402
+import modules as ref_modules          # noqa: E402
+import utils as ref_utils              # noqa: E402
+
+from oracle import flow_oracle as O    # noqa: E402
+from cosyvoice_lora_finetune_framework_b200 import modules as our_modules  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+WSEED = 1234
+
+
+def build_ref(n_blocks, n_mid, r=8, alpha=16, targets=('to_q', 'to_k', 'to_v', 'to_out')):
+    est = ref_modules.ConditionalDecoder(in_channels=320, out_channels=80, channels=(256, 256), dropout=0.0,
+                                         attention_head_dim=64, n_blocks=n_blocks, num_mid_blocks=n_mid,
+                                         num_heads=8, act_fn='gelu')
+    stats = None
+    if r:
+        stats = ref_lora.apply_lora_to_model(est, r=r, lora_alpha=alpha, lora_dropout=0.0,
+                                             target_modules=list(targets))
+    spec = {k: tuple(v.shape) for k, v in est.state_dict().items()}
+    sd = O.synth_state_dict(spec, WSEED)
+    est.load_state_dict(sd, strict=True)
+    cfm = ref_flow.ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, sigma_min=1e-6, t_scheduler='cosine',
+                                  training_cfg_rate=0.2, inference_cfg_rate=0.7, estimator=est)
+    return cfm, sd, stats
+
+
+def wsum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def train_case(name, n_blocks, n_mid, B, T, lengths, prompt_lens, data_seed, step_seed, keep_grads):
+    cfm, sd, stats = build_ref(n_blocks, n_mid)
+    cfm.train()
+    g = torch.Generator().manual_seed(data_seed)
+    x1 = torch.randn(B, 80, T, generator=g)
+    mu = torch.randn(B, 80, T, generator=g)
+    spks = torch.randn(B, 80, generator=g)
+    cond = torch.zeros(B, 80, T)
+    if prompt_lens:
+        for i, p in enumerate(prompt_lens):
+            cond[i, :, :p] = x1[i, :, :p]
+    lens = torch.tensor(lengths)
+    mask = (~ref_utils.make_pad_mask(lens, T)).float().unsqueeze(1)
+    # replicate the reference's three draws (flow_model.py:146,151,159) for the fixture
+    torch.manual_seed(step_seed)
+    t_rand = torch.rand([B, 1, 1])
+    z = torch.randn_like(x1)
+    cfg_rand = torch.rand(B)
+    torch.manual_seed(step_seed)
+    loss, y = cfm.compute_loss(x1, mask, mu, spks, cond=cond, prompt_lens=prompt_lens)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in cfm.estimator.named_parameters() if p.grad is not None}
+    # pred via a second forward with identical draws
+    with torch.no_grad():
+        t = 1 - torch.cos(t_rand * 0.5 * 3.14159265359)
+        keep = (cfg_rand > 0.2)
+        cfm.estimator.prompt_isolation_len = max(prompt_lens) if prompt_lens else 0
+        pred = cfm.estimator(y, mask, mu * keep.view(-1, 1, 1), t.view(B), spks * keep.view(-1, 1),
+                             cond * keep.view(-1, 1, 1))
+        cfm.estimator.prompt_isolation_len = 0
+    fx = dict(kind="train", n_blocks=n_blocks, n_mid=n_mid, wseed=WSEED, wsum=wsum(sd), lora_stats=stats,
+              x1=x1, mu=mu, spks=spks, cond=cond, mask=mask, lengths=lens, prompt_lens=prompt_lens,
+              t_rand=t_rand, z=z, cfg_rand=cfg_rand, loss=loss.detach(), y=y.detach(), pred=pred,
+              grad_norms={k: float(v.norm()) for k, v in grads.items()},
+              grad_total_norm=float(torch.sqrt(sum(v.double().pow(2).sum() for v in grads.values()))),
+              grads={k: v for k, v in grads.items() if keep_grads(k)})
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "gradnorm", fx["grad_total_norm"], "ngrads", len(grads), "kept", len(fx["grads"]))
+
+
+def estimator_case(name, n_blocks, n_mid, Ts, seed):
+    """export_onnx.py:34-41,95-116 protocol: batch 2, torch.rand inputs, random T."""
+    cfm, sd, _ = build_ref(n_blocks, n_mid, r=0)
+    est = cfm.estimator.eval()
+    cases = []
+    g = torch.Generator().manual_seed(seed)
+    for T in Ts:
+        x = torch.rand(2, 80, T, generator=g)
+        mu = torch.rand(2, 80, T, generator=g)
+        t = torch.rand(2, generator=g)
+        spks = torch.rand(2, 80, generator=g)
+        cond = torch.rand(2, 80, T, generator=g)
+        mask = torch.ones(2, 1, T)
+        with torch.no_grad():
+            out = est(x, mask, mu, t, spks, cond)
+        cases.append(dict(T=T, x=x, mu=mu, t=t, spks=spks, cond=cond, mask=mask, out=out))
+    torch.save(dict(kind="estimator", n_blocks=n_blocks, n_mid=n_mid, wseed=WSEED, wsum=wsum(sd), cases=cases),
+               os.path.join(HERE, name + ".pt"))
+    print(name, [float(c["out"].abs().max()) for c in cases])
+
+
+def euler_case(name, n_blocks, n_mid, T, prompt, n_steps, seed):
+    cfm, sd, _ = build_ref(n_blocks, n_mid, r=0)
+    cfm.eval()
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(1, 80, T, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    cond = torch.zeros(1, 80, T)
+    cond[:, :, :prompt] = torch.randn(1, 80, prompt, generator=g)
+    mask = torch.ones(1, 1, T)
+    torch.manual_seed(seed + 1)
+    z = torch.randn_like(mu)
+    torch.manual_seed(seed + 1)
+    mel, cache = cfm(mu=mu.clone(), mask=mask, n_timesteps=n_steps, temperature=1.0, spks=spks, cond=cond,
+                     prompt_len=prompt, cache=None)
+    torch.save(dict(kind="euler", n_blocks=n_blocks, n_mid=n_mid, wseed=WSEED, wsum=wsum(sd), mu=mu, spks=spks,
+                    cond=cond, mask=mask, z=z, n_steps=n_steps, prompt=prompt, mel=mel.clone(), cache=cache.clone()),
+               os.path.join(HERE, name + ".pt"))
+    print(name, "mel sum", float(mel.sum()), "absmax", float(mel.abs().max()), tuple(cache.shape))
+
+
+def structure_checks():
+    """Our module tree == the reference's (names, shapes, and same-seed random init)."""
+    for nb, nm in [(1, 1), (4, 12)]:
+        ref_utils.set_all_random_seed(4321)
+        a = ref_modules.ConditionalDecoder(320, 80, channels=(256, 256), dropout=0.0, attention_head_dim=64,
+                                           n_blocks=nb, num_mid_blocks=nm, num_heads=8, act_fn='gelu')
+        ref_utils.set_all_random_seed(4321)
+        b = our_modules.ConditionalDecoder(320, 80, channels=(256, 256), dropout=0.0, attention_head_dim=64,
+                                           n_blocks=nb, num_mid_blocks=nm, num_heads=8, act_fn='gelu')
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys()), "state_dict key order differs"
+        for k in sa:
+            assert sa[k].shape == sb[k].shape and torch.equal(sa[k], sb[k]), k
+        print("structure ok", nb, nm, len(sa), "keys; same-seed init identical")
+    spec = {k: tuple(v.shape) for k, v in sa.items()}
+    torch.save(dict(keys=list(spec.keys()), shapes=[spec[k] for k in spec]), os.path.join(HERE, "estimator_spec_300m.pt"))
+
+
+if __name__ == "__main__":
+    structure_checks()
+    first_mid_last = lambda k: any(s in k for s in ("down_blocks.0.1.0.", "mid_blocks.5.1.2.", "up_blocks.1.1.3."))
+    train_case("train_tiny", 1, 1, 2, 37, [37, 21], None, 99, 7, lambda k: True)
+    train_case("train_tiny_prompt", 1, 1, 3, 64, [64, 50, 33], [12, 0, 9], 100, 8, lambda k: True)
+    train_case("train_c1", 4, 12, 2, 200, [200, 160], None, 99, 7, first_mid_last)
+    train_case("train_c1_prompt", 4, 12, 2, 200, [200, 160], [30, 0], 99, 7, first_mid_last)
+    estimator_case("estimator_tiny", 1, 1, [16, 77, 130, 257], 5)
+    estimator_case("estimator_300m", 4, 12, [100, 301], 6)
+    euler_case("euler_tiny", 1, 1, 90, 30, 10, 11)
+    euler_case("euler_300m", 4, 12, 140, 40, 10, 12)

@@ -1,0 +1,61 @@
+"""Pin the CPU oracle (oracle/flow_oracle.py) against vectors produced by the real reference
+(tests/golden/make_golden.py) and against the reference's docstring known-answers."""
+import pytest
+import torch
+
+from oracle import flow_oracle as O
+from tests.helpers import build_estimator, load_golden, lora_scaling_of, wsum
+
+
+def test_make_pad_mask_docstring_kat():
+    # reference utils.py:28-33
+    got = O.make_pad_mask(torch.tensor([5, 3, 2])).int().tolist()
+    assert got == [[0, 0, 0, 0, 0], [0, 0, 0, 1, 1], [0, 0, 1, 1, 1]]
+    from cosyvoice_lora_finetune_framework_b200 import utils
+    assert utils.make_pad_mask(torch.tensor([5, 3, 2])).int().tolist() == got
+    assert utils.make_pad_mask(torch.tensor([2, 1]), 4).int().tolist() == [[0, 0, 1, 1], [0, 1, 1, 1]]
+    b = utils.mask_to_bias(torch.tensor([True, False]), torch.float32)
+    assert b.tolist() == [0.0, -1.0e10]
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_prompt", "train_c1", "train_c1_prompt"])
+def test_train_step_matches_reference(name):
+    fx = load_golden(name)
+    est, sd, stats = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    assert abs(wsum(sd) - fx["wsum"]) <= 1e-6 * fx["wsum"]
+    assert stats["replaced_layers"] == fx["lora_stats"]["replaced_layers"]
+    assert stats["lora_params"] == fx["lora_stats"]["lora_params"]
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    loss, y, pred = O.cfm_compute_loss(P, fx["x1"], fx["mask"], fx["mu"], fx["spks"], fx["cond"], fx["prompt_lens"],
+                                       fx["t_rand"], fx["z"], fx["cfg_rand"], lora_scaling=lora_scaling_of(sd))
+    assert torch.allclose(y, fx["y"], atol=1e-6)
+    assert torch.allclose(pred, fx["pred"], atol=2e-4, rtol=1e-4)
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+    loss.backward()
+    for k, g in fx["grads"].items():
+        assert torch.allclose(P[k].grad, g, atol=1e-6 + 1e-3 * float(g.abs().max()), rtol=1e-3), k
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-9, k
+
+
+@pytest.mark.parametrize("name", ["estimator_tiny", "estimator_300m"])
+def test_estimator_matches_reference(name):
+    fx = load_golden(name)
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"])
+    assert abs(wsum(sd) - fx["wsum"]) <= 1e-6 * fx["wsum"]
+    for c in fx["cases"]:
+        with torch.no_grad():
+            out = O.estimator_forward(sd, c["x"], c["mask"], c["mu"], c["t"], c["spks"], c["cond"])
+        # the reference's own export check uses rtol 1e-2 / atol 1e-4 (export_onnx.py:115)
+        assert torch.allclose(out, c["out"], rtol=1e-3, atol=1e-4), c["T"]
+
+
+@pytest.mark.parametrize("name", ["euler_tiny", "euler_300m"])
+def test_euler_matches_reference(name):
+    fx = load_golden(name)
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"])
+    with torch.no_grad():
+        mel, cache = O.cfm_forward(sd, fx["mu"], fx["mask"], fx["n_steps"], fx["z"].clone(), fx["spks"], fx["cond"],
+                                   prompt_len=fx["prompt"])
+    assert cache.shape == fx["cache"].shape and torch.equal(cache, fx["cache"])
+    assert torch.allclose(mel, fx["mel"], atol=2e-3, rtol=1e-3)
