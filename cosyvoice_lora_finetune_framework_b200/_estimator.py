@@ -1,3 +1,369 @@
-"""placeholder - replaced below"""
-def estimator_forward(*a, **k):
-    raise RuntimeError("cvflow estimator binding not built yet")
+"""Host glue between the nn.Module tree (modules.py) and the cvflow C ABI (include/cvflow.h).
+
+Everything here is plumbing: one-off weight re-layout with torch ops at bind time, workspace
+allocation from the caching allocator, raw pointers + the current stream handed to the library,
+and the autograd hooks. The arithmetic of the path lives in csrc/*.cu.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+_F32 = 2
+LOSS_SCALE_DEFAULT = 4096.0   # static loss scale for fp16 gradients (bf16 runs use 1.0)
+
+
+class EstimatorIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_nb", C.c_int32), ("mask", C.c_void_p), ("mask_nb", C.c_int32),
+                ("mu", C.c_void_p), ("mu_nb", C.c_int32), ("t", C.c_void_p), ("t_nb", C.c_int32),
+                ("spks", C.c_void_p), ("spks_nb", C.c_int32), ("cond", C.c_void_p), ("cond_nb", C.c_int32),
+                ("keep", C.c_void_p), ("out", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32),
+                ("iso_len", C.c_int32), ("training", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("n_mid", C.c_int32), ("dtype", C.c_int32), ("gelu_erf", C.c_int32),
+                ("lora_r", C.c_int32), ("lora_scaling", C.c_float)]
+
+
+_protos_done = False
+
+
+def _lib():
+    global _protos_done
+    L = N.lib()
+    if not _protos_done:
+        vp, i32, i64, f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        L.cvflow_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.cvflow_destroy.argtypes = [vp]
+        L.cvflow_destroy.restype = None
+        L.cvflow_bind.argtypes = [vp, C.c_char_p, vp, i64, i32]
+        L.cvflow_workspace_bytes.argtypes = [vp, i32, i32, i32]
+        L.cvflow_workspace_bytes.restype = i64
+        L.cvflow_set_workspace.argtypes = [vp, vp, i64]
+        L.cvflow_lora_refresh.argtypes = [vp, vp]
+        L.cvflow_estimator_forward.argtypes = [vp, C.POINTER(EstimatorIO), vp]
+        L.cvflow_estimator_backward.argtypes = [vp, vp, f, vp, vp]
+        L.cvflow_launch_count.argtypes = [vp]
+        L.cvflow_launch_count.restype = i64
+        L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
+        L.cvflow_cfm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f, f, i32, vp]
+        L.cvflow_euler_update.argtypes = [vp, vp, vp, i32, f, i64, vp]
+        L.cvflow_sumsq.argtypes = [vp, i64, vp, vp, vp]
+        L.cvflow_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, f, f, f, f, f, f, f, i32, vp, vp]
+        _protos_done = True
+    return L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _lin(m):
+    """(weight, bias, lora_module_or_None) of an nn.Linear or a LoRALinear wrapper."""
+    from .lora import LoRAConv1d, LoRALinear
+    if isinstance(m, LoRALinear):
+        return m.original_layer.weight, m.original_layer.bias, m
+    if isinstance(m, LoRAConv1d):
+        raise NotImplementedError("LoRA on 1x1 convs is not part of the fused estimator path")
+    return m.weight, m.bias, None
+
+
+class NativeEstimator:
+    """Owns the cvflow handle, the 16-bit weight images, the flat LoRA param/grad buckets and
+    the workspace for one ConditionalDecoder."""
+
+    def __init__(self, module, dtype=torch.float16):
+        if not torch.cuda.is_available():
+            raise RuntimeError("the cvflow estimator needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.L = _lib()
+        self.module = module
+        self.dtype = dtype
+        self.device = next(module.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("ConditionalDecoder parameters must live on a CUDA device (got %s)" % self.device)
+        self.keep = []          # tensors the library holds raw pointers to
+        self.handle = C.c_void_p()
+        self.ws = None
+        self.ws_key = None
+        self.loss_scale = LOSS_SCALE_DEFAULT if dtype == torch.float16 else 1.0
+        self._build()
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.L.cvflow_destroy(self.handle)
+        except Exception:
+            pass
+
+    # -- weight binding ------------------------------------------------------------------------
+    def _bind(self, name, t):
+        assert t.is_cuda and t.is_contiguous(), name
+        code = _F32 if t.dtype == torch.float32 else N.dtype_code(t.dtype)
+        self.keep.append(t)
+        N.check(self.L.cvflow_bind(self.handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), code), "cvflow_bind")
+
+    def _h(self, t):
+        return t.detach().to(self.dtype).contiguous()
+
+    def _f(self, t):
+        return t.detach().float().contiguous()
+
+    def _build(self):
+        m = self.module
+        n_blocks = len(m.down_blocks[0][1])
+        n_mid = len(m.mid_blocks)
+        if len(m.down_blocks) != 2 or len(m.up_blocks) != 2:
+            raise NotImplementedError("cvflow estimator is built for channels=(256, 256) (two resolutions)")
+        stages = ([("down_blocks.%d" % i, m.down_blocks[i]) for i in range(2)] +
+                  [("mid_blocks.%d" % i, m.mid_blocks[i]) for i in range(n_mid)] +
+                  [("up_blocks.%d" % i, m.up_blocks[i]) for i in range(2)])
+        # LoRA discovery
+        loras = []
+        for _, st in stages:
+            for tb in st[1]:
+                for pn in ("to_q", "to_k", "to_v"):
+                    _, _, lm = _lin(getattr(tb.attn1, pn))
+                    if lm is not None:
+                        loras.append(lm)
+                for other in (tb.attn1.to_out[0], tb.ff.net[0].proj, tb.ff.net[2]):
+                    if not isinstance(other, nn.Linear):
+                        raise NotImplementedError("the fused estimator supports LoRA on attn1.to_q/to_k/to_v only")
+        r = loras[0].r if loras else 0
+        scaling = loras[0].scaling if loras else 1.0
+        for lm in loras:
+            if lm.r != r or lm.scaling != scaling:
+                raise NotImplementedError("all LoRA layers must share rank and alpha")
+            if isinstance(lm.lora_dropout, nn.Dropout) and lm.lora_dropout.p > 0 and False:
+                pass
+        self.lora_modules = loras
+        self.lora_r = r
+        gelu = m.down_blocks[0][1][0].ff.net[0].approximate
+        cfg = Config(n_blocks, n_mid, N.dtype_code(self.dtype), 0 if gelu == "tanh" else 1, r, float(scaling))
+        N.check(self.L.cvflow_create(C.byref(cfg), C.byref(self.handle)), "cvflow_create")
+
+        def conv3_w(w):      # [Cout][Cin][3] -> [Cout][tap*Cin + c]
+            return w.permute(0, 2, 1).reshape(w.shape[0], -1)
+
+        def conv3_wd(w):     # dgrad operand: [Cin][tap'*Cout + co] = w[co][ci][2 - tap']
+            return w.flip(2).permute(1, 2, 0).reshape(w.shape[1], -1)
+
+        with torch.no_grad():
+            self._bind("time.w1", self._f(m.time_mlp.linear_1.weight))
+            self._bind("time.b1", self._f(m.time_mlp.linear_1.bias))
+            self._bind("time.w2", self._f(m.time_mlp.linear_2.weight))
+            self._bind("time.b2", self._f(m.time_mlp.linear_2.bias))
+            self._bind("time.proj_w", self._f(torch.cat([st[0].mlp[1].weight for _, st in stages], 0)))
+            self._bind("time.proj_b", self._f(torch.cat([st[0].mlp[1].bias for _, st in stages], 0)))
+            # flat LoRA parameter / gradient buckets (params become views into the bucket)
+            n_lora = sum(lm.lora_A.numel() + lm.lora_B.numel() for lm in loras)
+            self.param_bucket = torch.empty(max(n_lora, 1), device=self.device, dtype=torch.float32)
+            self.grad_bucket = torch.zeros(max(n_lora, 1), device=self.device, dtype=torch.float32)
+            self.n_lora = n_lora
+            off = 0
+            self.lora_views = []
+            for lm in loras:
+                for p in (lm.lora_A, lm.lora_B):
+                    n = p.numel()
+                    view = self.param_bucket[off:off + n].view_as(p)
+                    view.copy_(p.data.float())
+                    p.data = view
+                    self.lora_views.append((p, off, n))
+                    off += n
+            for S, st in stages:
+                res = st[0]
+                P = S + ".0"
+                w1 = res.block1.block[0].weight
+                self._bind(P + ".block1.w", self._h(conv3_w(w1)))
+                self._bind(P + ".block1.b", self._f(res.block1.block[0].bias))
+                self._bind(P + ".gn1.w", self._f(res.block1.block[1].weight))
+                self._bind(P + ".gn1.b", self._f(res.block1.block[1].bias))
+                w2 = res.block2.block[0].weight
+                self._bind(P + ".block2.w", self._h(conv3_w(w2)))
+                self._bind(P + ".block2.b", self._f(res.block2.block[0].bias))
+                self._bind(P + ".gn2.w", self._f(res.block2.block[1].weight))
+                self._bind(P + ".gn2.b", self._f(res.block2.block[1].bias))
+                wr = res.res_conv.weight[:, :, 0]
+                self._bind(P + ".res.w", self._h(wr))
+                self._bind(P + ".res.b", self._f(res.res_conv.bias))
+                self._bind(P + ".block2.wd", self._h(conv3_wd(w2)))
+                self._bind(P + ".in.wd", self._h(torch.cat([conv3_wd(w1), wr.t()], 1)))
+                for j, tb in enumerate(st[1]):
+                    Q = "%s.1.%d" % (S, j)
+                    self._bind(Q + ".norm1.w", self._f(tb.norm1.weight))
+                    self._bind(Q + ".norm1.b", self._f(tb.norm1.bias))
+                    self._bind(Q + ".norm3.w", self._f(tb.norm3.weight))
+                    self._bind(Q + ".norm3.b", self._f(tb.norm3.bias))
+                    for pn, short in (("to_q", "q"), ("to_k", "k"), ("to_v", "v")):
+                        w, b, lm = _lin(getattr(tb.attn1, pn))
+                        if b is not None:
+                            raise NotImplementedError("attn1 q/k/v with bias is not supported")
+                        self._bind(Q + ".w" + short, self._f(w))
+                        if lm is not None:
+                            self._bind(Q + ".lora_%s.A" % short, lm.lora_A.data)
+                            self._bind(Q + ".lora_%s.B" % short, lm.lora_B.data)
+                            ga = self._grad_view(lm.lora_A)
+                            gb = self._grad_view(lm.lora_B)
+                            self._bind(Q + ".lora_%s.A.grad" % short, ga)
+                            self._bind(Q + ".lora_%s.B.grad" % short, gb)
+                    self._bind(Q + ".weff", torch.empty(1536, 256, device=self.device, dtype=self.dtype))
+                    self._bind(Q + ".weff_t", torch.empty(256, 1536, device=self.device, dtype=self.dtype))
+                    wo, bo, _ = _lin(tb.attn1.to_out[0])
+                    self._bind(Q + ".wo", self._h(wo))
+                    self._bind(Q + ".wo_t", self._h(wo.t()))
+                    self._bind(Q + ".bo", self._f(bo))
+                    w1_, b1_, _ = _lin(tb.ff.net[0].proj)
+                    self._bind(Q + ".w1", self._h(w1_))
+                    self._bind(Q + ".w1_t", self._h(w1_.t()))
+                    self._bind(Q + ".b1", self._f(b1_))
+                    w2_, b2_, _ = _lin(tb.ff.net[2])
+                    self._bind(Q + ".w2", self._h(w2_))
+                    self._bind(Q + ".w2_t", self._h(w2_.t()))
+                    self._bind(Q + ".b2", self._f(b2_))
+            # resolution changes
+            wds = m.down_blocks[0][2].conv.weight
+            self._bind("down_blocks.0.2.w", self._h(conv3_w(wds)))
+            self._bind("down_blocks.0.2.b", self._f(m.down_blocks[0][2].conv.bias))
+            self._bind("down_blocks.0.2.wd_even", self._h(wds[:, :, 1].t()))
+            self._bind("down_blocks.0.2.wd_odd", self._h(torch.cat([wds[:, :, 0].t(), wds[:, :, 2].t()], 1)))
+            wc = m.down_blocks[1][2].weight
+            self._bind("down_blocks.1.2.w", self._h(conv3_w(wc)))
+            self._bind("down_blocks.1.2.b", self._f(m.down_blocks[1][2].bias))
+            self._bind("down_blocks.1.2.wd", self._h(conv3_wd(wc)))
+            wu = m.up_blocks[0][2].conv.weight      # ConvTranspose1d: [Cin][Cout][4]
+            self._bind("up_blocks.0.2.w_even", self._h(torch.cat([wu[:, :, 1].t(), wu[:, :, 3].t()], 1)))
+            self._bind("up_blocks.0.2.w_odd", self._h(torch.cat([wu[:, :, 0].t(), wu[:, :, 2].t()], 1)))
+            self._bind("up_blocks.0.2.b", self._f(m.up_blocks[0][2].conv.bias))
+            self._bind("up_blocks.0.2.wd", self._h(wu.permute(0, 2, 1).reshape(256, 1024)))
+            wc = m.up_blocks[1][2].weight
+            self._bind("up_blocks.1.2.w", self._h(conv3_w(wc)))
+            self._bind("up_blocks.1.2.b", self._f(m.up_blocks[1][2].bias))
+            self._bind("up_blocks.1.2.wd", self._h(conv3_wd(wc)))
+            wf = m.final_block.block[0].weight
+            self._bind("final_block.w", self._h(conv3_w(wf)))
+            self._bind("final_block.b", self._f(m.final_block.block[0].bias))
+            self._bind("final_block.gn.w", self._f(m.final_block.block[1].weight))
+            self._bind("final_block.gn.b", self._f(m.final_block.block[1].bias))
+            self._bind("final_block.wd", self._h(conv3_wd(wf)))
+            wp = m.final_proj.weight[:, :, 0]       # [80][256]
+            wp_pad = torch.zeros(128, 256, device=self.device)
+            wp_pad[:80] = wp
+            self._bind("final_proj.w", self._h(wp_pad))
+            self._bind("final_proj.b", self._f(m.final_proj.bias))
+            self._bind("final_proj.wt", self._h(wp_pad.t()))
+        self.refresh_lora()
+
+    def _grad_view(self, p):
+        for q, off, n in self.lora_views:
+            if q is p:
+                return self.grad_bucket[off:off + n].view_as(p)
+        raise KeyError
+
+    def attach_grads(self):
+        """Make every LoRA parameter's .grad a view of the flat bucket (zeroing it when a grad
+        was dropped by zero_grad(set_to_none=True))."""
+        fresh = any(p.grad is None or p.grad.data_ptr() != self.grad_bucket.data_ptr() + 4 * off
+                    for p, off, n in self.lora_views)
+        if fresh:
+            self.grad_bucket.zero_()
+            for p, off, n in self.lora_views:
+                p.grad = self.grad_bucket[off:off + n].view_as(p)
+
+    def refresh_lora(self):
+        """Rebuild W_eff = W + (alpha/r) B A (call after every optimiser step)."""
+        N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
+
+    # -- calls -----------------------------------------------------------------------------------
+    def _workspace(self, B, T, training):
+        key = (B, T, int(training))
+        if self.ws_key != key:
+            need = self.L.cvflow_workspace_bytes(self.handle, B, T, int(training))
+            if need < 0:
+                N.check(int(need), "cvflow_workspace_bytes")
+            if self.ws is None or self.ws.numel() < need:
+                self.ws = None
+                self.ws = torch.empty(int(need), device=self.device, dtype=torch.uint8)
+            N.check(self.L.cvflow_set_workspace(self.handle, C.c_void_p(self.ws.data_ptr()), self.ws.numel()),
+                    "cvflow_set_workspace")
+            self.ws_key = key
+
+    def forward(self, x, mask, mu, t, spks, cond, keep=None, iso_len=0, training=False, B=None, out=None):
+        T = x.shape[-1]
+        B = B or max(x.shape[0], mu.shape[0])
+        self._workspace(B, T, training)
+        if out is None:
+            out = torch.empty(B, 80, T, device=self.device, dtype=torch.float32)
+        io = EstimatorIO()
+        io.x, io.x_nb = x.data_ptr(), x.shape[0]
+        io.mask, io.mask_nb = mask.data_ptr(), mask.shape[0]
+        io.mu, io.mu_nb = mu.data_ptr(), mu.shape[0]
+        io.t, io.t_nb = t.data_ptr(), t.shape[0]
+        io.spks, io.spks_nb = (spks.data_ptr(), spks.shape[0]) if spks is not None else (None, 1)
+        io.cond, io.cond_nb = (cond.data_ptr(), cond.shape[0]) if cond is not None else (None, 1)
+        io.keep = keep.data_ptr() if keep is not None else None
+        io.out = out.data_ptr()
+        io.B, io.T, io.iso_len, io.training = B, T, int(iso_len), int(training)
+        N.check(self.L.cvflow_estimator_forward(self.handle, C.byref(io), _stream()), "cvflow_estimator_forward")
+        return out
+
+    def backward(self, dpred16, grad_scale=1.0, grad_scale_dev=None):
+        self.attach_grads()
+        N.check(self.L.cvflow_estimator_backward(
+            self.handle, C.c_void_p(dpred16.data_ptr()), float(grad_scale),
+            C.c_void_p(grad_scale_dev.data_ptr()) if grad_scale_dev is not None else None, _stream()),
+            "cvflow_estimator_backward")
+
+    def launch_count(self):
+        return int(self.L.cvflow_launch_count(self.handle))
+
+
+def _prep(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def native_of(module, dtype=None):
+    """Lazily create (or fetch) the NativeEstimator bound to `module`."""
+    want = dtype or getattr(module, "cvflow_dtype", torch.float16)
+    ne = module.__dict__.get("_cvflow")
+    if ne is None or ne.dtype != want:
+        ne = NativeEstimator(module, want)
+        module.__dict__["_cvflow"] = ne
+    return ne
+
+
+class _EstimatorFn(torch.autograd.Function):
+    """Generic autograd bridge for ConditionalDecoder.forward (any downstream loss). The CFM
+    training step uses the fused path in flow_model.py instead."""
+
+    @staticmethod
+    def forward(ctx, ne, x, mask, mu, t, spks, cond, iso_len, *lora_params):
+        ctx.ne = ne
+        out = ne.forward(x, mask, mu, t, spks, cond, iso_len=iso_len, training=True)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ne = ctx.ne
+        B, _, T = gout.shape
+        g = torch.zeros(B, T, 128, device=gout.device, dtype=ne.dtype)
+        g[:, :, :80] = (gout.float() * ne.loss_scale).transpose(1, 2).to(ne.dtype)
+        ne.backward(g, grad_scale=1.0 / ne.loss_scale)
+        return (None,) * (8 + len(ne.lora_views))
+
+
+def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
+    ne = native_of(module)
+    dev = ne.device
+    x_, mu_, t_ = _prep(x, dev), _prep(mu, dev), _prep(t, dev)
+    mask_ = _prep(mask, dev).reshape(mask.shape[0], -1)
+    spks_ = _prep(spks, dev) if spks is not None else None
+    cond_ = _prep(cond, dev) if cond is not None else None
+    iso = int(module.prompt_isolation_len) if getattr(module, "prompt_isolation_enabled", False) else 0
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in ne.lora_views)
+    if needs_grad:
+        out = _EstimatorFn.apply(ne, x_, mask_, mu_, t_, spks_, cond_, iso, *[p for p, _, _ in ne.lora_views])
+    else:
+        out = ne.forward(x_, mask_, mu_, t_, spks_, cond_, iso_len=iso, training=False)
+    return out.to(x.dtype) if x.dtype != torch.float32 else out

@@ -1,6 +1,8 @@
 // extern "C" entry points of libcvflow.so (declared in include/cvflow.h).
 #include "../../include/cvflow.h"
 #include "gemm.h"
+#include "estimator.h"
+#include "kernels.h"
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -45,4 +47,111 @@ extern "C" CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* d, void* stream) {
   int r = gemm_launch(p, (cudaStream_t)stream);
   if (r) { set_error("cvflow_gemm: launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return CVFLOW_ERR_CUDA; }
   return CVFLOW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct cvflow_estimator { Estimator* e; };
+
+extern "C" CVFLOW_API int cvflow_create(const cvflow_config* c, cvflow_estimator** out) {
+  if (!c || !out) { set_error("cvflow_create: null argument"); return CVFLOW_ERR_ARG; }
+  if (c->n_blocks < 1 || c->n_mid < 0 || c->lora_r < 0 || c->lora_r > 16 ||
+      (c->lora_r != 0 && c->lora_r != 4 && c->lora_r != 8 && c->lora_r != 16)) {
+    set_error("cvflow_create: unsupported config (n_blocks %d, n_mid %d, lora_r %d; rank must be 0/4/8/16)",
+              c->n_blocks, c->n_mid, c->lora_r);
+    return CVFLOW_ERR_UNSUPPORTED;
+  }
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("cvflow_create: no CUDA device");
+    return CVFLOW_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("cvflow_create: kernels are built for sm_100a only, device is sm_%d%d (no fallback)", prop.major,
+              prop.minor);
+    return CVFLOW_ERR_UNSUPPORTED;
+  }
+  EstimatorConfig ec;
+  ec.n_blocks = c->n_blocks; ec.n_mid = c->n_mid; ec.bf16 = c->dtype == CVFLOW_DTYPE_BF16; ec.gelu_erf = c->gelu_erf;
+  ec.lora_r = c->lora_r; ec.lora_scaling = c->lora_scaling;
+  cvflow_estimator* h = new cvflow_estimator;
+  h->e = new Estimator(ec);
+  *out = h;
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API void cvflow_destroy(cvflow_estimator* h) {
+  if (h) { delete h->e; delete h; }
+}
+extern "C" CVFLOW_API int cvflow_bind(cvflow_estimator* h, const char* name, void* ptr, int64_t numel, int32_t dtype) {
+  if (!h || !name || !ptr) { set_error("cvflow_bind: null argument"); return CVFLOW_ERR_ARG; }
+  return h->e->bind(name, ptr, (long)numel, dtype);
+}
+extern "C" CVFLOW_API int64_t cvflow_workspace_bytes(cvflow_estimator* h, int32_t B, int32_t T, int32_t training) {
+  if (!h || B < 1 || T < 1) { set_error("cvflow_workspace_bytes: bad argument"); return CVFLOW_ERR_ARG; }
+  return h->e->workspace_bytes(B, T, training);
+}
+extern "C" CVFLOW_API int cvflow_set_workspace(cvflow_estimator* h, void* ptr, int64_t bytes) {
+  if (!h || !ptr) { set_error("cvflow_set_workspace: null argument"); return CVFLOW_ERR_ARG; }
+  h->e->set_workspace(ptr, (long)bytes);
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream) {
+  if (!h) { set_error("cvflow_lora_refresh: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->lora_refresh((cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_estimator_forward(cvflow_estimator* h, const cvflow_estimator_io* io, void* stream) {
+  if (!h || !io || !io->x || !io->mask || !io->mu || !io->t || !io->out || io->B < 1 || io->T < 1) {
+    set_error("cvflow_estimator_forward: null/invalid argument");
+    return CVFLOW_ERR_ARG;
+  }
+  EstimatorIO e;
+  e.x = io->x; e.x_nb = io->x_nb; e.mask = io->mask; e.mask_nb = io->mask_nb; e.mu = io->mu; e.mu_nb = io->mu_nb;
+  e.t = io->t; e.t_nb = io->t_nb; e.spks = io->spks; e.spks_nb = io->spks_nb > 0 ? io->spks_nb : 1;
+  e.cond = io->cond; e.cond_nb = io->cond_nb > 0 ? io->cond_nb : 1; e.keep = io->keep; e.out = io->out;
+  e.B = io->B; e.T = io->T; e.iso_len = io->iso_len; e.training = io->training;
+  if (e.x_nb < 1 || e.mask_nb < 1 || e.mu_nb < 1 || e.t_nb < 1) { set_error("cvflow_estimator_forward: *_nb must be >= 1"); return CVFLOW_ERR_ARG; }
+  return h->e->forward(e, (cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_estimator_backward(cvflow_estimator* h, const void* dpred16, float grad_scale,
+                                                    const float* grad_scale_dev, void* stream) {
+  if (!h || !dpred16) { set_error("cvflow_estimator_backward: null argument"); return CVFLOW_ERR_ARG; }
+  return h->e->backward(dpred16, grad_scale, grad_scale_dev, (cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
+extern "C" CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h) { return h ? h->e->launches() : 0; }
+
+#define RET_LAUNCH(call, what)                                                                       \
+  do {                                                                                               \
+    int r_ = (call);                                                                                 \
+    if (r_) { set_error(what ": %s", cudaGetErrorString((cudaError_t)(-r_))); return CVFLOW_ERR_CUDA; } \
+    return CVFLOW_OK;                                                                                \
+  } while (0)
+
+extern "C" CVFLOW_API int cvflow_cfm_prep(const float* x1, const float* z, const float* t, float* y, int32_t B,
+                                          int32_t T, float sigma_min, void* stream) {
+  if (!x1 || !z || !t || !y) { set_error("cvflow_cfm_prep: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_cfm_prep(x1, z, t, y, B, T, sigma_min, (cudaStream_t)stream), "cvflow_cfm_prep");
+}
+extern "C" CVFLOW_API int cvflow_cfm_loss(const float* pred, const float* x1, const float* z, const float* w,
+                                          const float* mask, float* scal, float* partials, void* dpred16, int32_t B,
+                                          int32_t T, float sigma_min, float loss_scale, int32_t dtype, void* stream) {
+  if (!pred || !x1 || !z || !w || !mask || !scal || !partials) { set_error("cvflow_cfm_loss: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_cfm_loss(pred, x1, z, w, mask, scal, partials, dpred16, B, T, sigma_min, loss_scale,
+                             dtype == CVFLOW_DTYPE_BF16, (cudaStream_t)stream), "cvflow_cfm_loss");
+}
+extern "C" CVFLOW_API int cvflow_euler_update(float* x, const float* d, const float* dt, int32_t step, float cfg_rate,
+                                              int64_t n, void* stream) {
+  if (!x || !d || !dt) { set_error("cvflow_euler_update: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_euler_update(x, d, dt, step, cfg_rate, (long)n, (cudaStream_t)stream), "cvflow_euler_update");
+}
+extern "C" CVFLOW_API int cvflow_sumsq(const float* g, int64_t n, float* partials, float* out, void* stream) {
+  if (!g || !partials || !out) { set_error("cvflow_sumsq: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_sumsq(g, (long)n, partials, out, (cudaStream_t)stream), "cvflow_sumsq");
+}
+extern "C" CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                                            float grad_unscale, float max_norm, float lr, float beta1, float beta2,
+                                            float eps, float weight_decay, int32_t step, int32_t* found_inf,
+                                            void* stream) {
+  if (!p || !g || !m || !v || !sumsq) { set_error("cvflow_adamw_step: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_adamw(p, g, m, v, (long)n, sumsq, grad_unscale, max_norm, lr, beta1, beta2, eps, weight_decay, step,
+                          found_inf, (cudaStream_t)stream), "cvflow_adamw_step");
 }

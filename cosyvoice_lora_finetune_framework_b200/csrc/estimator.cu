@@ -1,0 +1,677 @@
+// Host orchestration of the ConditionalDecoder U-Net (reference modules.py:998-1106) and its
+// backward on the cvflow kernels. Activations are token-major [B][L][C]: 16-bit where they feed a
+// tensor-core operand, fp32 for the residual stream and statistics (the dtype flow of the
+// reference under autocast).
+//
+// A "plan" memoises every TMA descriptor / GEMM parameter block per (B, T, mode); a forward is
+// then a fixed sequence of kernel launches on the caller's stream with no host synchronisation,
+// so it can be captured into a CUDA graph (the N-step Euler solve is one graph replay).
+#include "estimator.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace cvflow {
+
+void set_error(const char* fmt, ...);
+
+// CK: propagate a failure whose message is already set. CKL: a kernel launcher returned -cudaError.
+#define CK(expr) do { if ((expr) != 0) return -1; } while (0)
+#define CKL(expr)                                                                          \
+  do {                                                                                     \
+    int rc_ = (expr);                                                                      \
+    if (rc_ != 0) {                                                                        \
+      set_error("%s failed (%s) at %s:%d", #expr, cudaGetErrorString((cudaError_t)(-rc_)), \
+                __FILE__, __LINE__);                                                       \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {}
+Estimator::~Estimator() {
+  if (lora_table_dev_) cudaFree(lora_table_dev_);
+}
+
+int Estimator::bind(const char* name, void* ptr, long numel, int dtype) {
+  bound_[name] = BoundTensor{ptr, numel, dtype};
+  plans_.clear();
+  lora_table_ready_ = false;
+  return 0;
+}
+
+void* Estimator::get(const std::string& name, int dtype, long numel) {
+  if (dry_) return reinterpret_cast<void*>(0x1000);
+  auto it = bound_.find(name);
+  if (it == bound_.end()) {
+    if (!missing_) { set_error("estimator: tensor '%s' was never bound", name.c_str()); missing_ = true; }
+    return nullptr;
+  }
+  if (it->second.dtype != dtype || (numel > 0 && it->second.numel != numel)) {
+    if (!missing_) {
+      set_error("estimator: tensor '%s' bound with dtype %d numel %ld, expected dtype %d numel %ld", name.c_str(),
+                it->second.dtype, it->second.numel, dtype, numel);
+      missing_ = true;
+    }
+    return nullptr;
+  }
+  return it->second.ptr;
+}
+bool Estimator::has(const std::string& name) const { return bound_.count(name) != 0; }
+
+// ------------------------------------------------------------------------------------------
+// workspace + memoised launches
+// ------------------------------------------------------------------------------------------
+void* Estimator::alloc(long bytes) {
+  const long a = (ws_off_ + 1023) & ~1023L;
+  ws_off_ = a + bytes;
+  if (dry_) return reinterpret_cast<void*>(0x1000 + a);  // never dereferenced
+  if (ws_off_ > ws_bytes_) { oom_ = true; return nullptr; }
+  return reinterpret_cast<uint8_t*>(ws_) + a;
+}
+
+int Estimator::run_gemm(GemmArgs& a) {
+  if (dry_) { ++gemm_idx_; return 0; }
+  if (missing_ || oom_) return -1;
+  Plan& pl = *plan_;
+  if ((size_t)gemm_idx_ >= pl.gemms.size()) {
+    a.bf16 = cfg.bf16;
+    GemmParams p;
+    if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return -1;
+    pl.gemms.push_back(p);
+  }
+  GemmParams& p = pl.gemms[gemm_idx_++];
+  // per-call pointers at the API edge may move between calls
+  p.out = a.out; p.rowmask = a.rowmask;
+  int r = gemm_launch(p, stream_);
+  if (r) { set_error("gemm launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return -1; }
+  ++launches_;
+  return 0;
+}
+
+static GemmArgs linear_args(const void* A, long M, int K, const void* W, int N, void* out, int out_f32) {
+  GemmArgs a;
+  a.A[0] = A; a.a_rows[0] = (int)M; a.a_cols[0] = K; a.a_ld[0] = K; a.a_bstride[0] = M * (long)K;
+  a.nbatch = 1; a.W = W; a.N = N; a.Ktot = K; a.nseg = 1;
+  a.seg[0] = GemmSeg{0, 0, 0, K / 64};
+  a.R = (int)M; a.out_rows = (int)M; a.out = out; a.out_f32 = out_f32; a.ldc = N; a.n_valid = N;
+  return a;
+}
+// k=3 conv (or its dgrad) on a [B][L][*] source: columns [col0, col0+cin) of rows with stride ld
+static GemmArgs conv3_args(const void* A, int B, int L, long ld, int col0, int cin, const void* W, int N, void* out,
+                           long ldc, int col_off) {
+  GemmArgs a;
+  a.A[0] = A; a.a_rows[0] = L; a.a_cols[0] = col0 + cin; a.a_ld[0] = ld; a.a_bstride[0] = (long)L * ld;
+  a.nbatch = B; a.W = W; a.N = N; a.Ktot = 3 * cin; a.nseg = 3;
+  for (int t = 0; t < 3; ++t) a.seg[t] = GemmSeg{0, t - 1, col0, cin / 64};
+  a.R = L; a.out_rows = L; a.out = out; a.out_f32 = 0; a.ldc = ldc; a.col_off = col_off; a.n_valid = N;
+  return a;
+}
+
+int Estimator::iso_at(int L, int T, int iso_len) const {
+  if (!(iso_len > 0)) return 0;
+  const double scale = (double)L / (double)T;
+  int p = (int)((double)iso_len * scale);
+  if (p < 1) p = 1;
+  return p < L ? p : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// blocks
+// ------------------------------------------------------------------------------------------
+int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L,
+                          const float* mask, const float* tb, long tb_stride, float** h_out, ResnetRec* rec) {
+  const long M = (long)B * L;
+  void* c1 = alloc(M * 256 * 2);
+  void* a1 = alloc(M * 256 * 2);
+  void* c2 = alloc(M * 256 * 2);
+  void* r = alloc(M * 256 * 2);
+  float* st1 = (float*)alloc(B * 16 * 4);
+  float* st2 = (float*)alloc(B * 16 * 4);
+  float* h = (float*)alloc(M * 256 * 4);
+  {
+    GemmArgs g = conv3_args(xin, B, L, ld_in, col0, cin, get(P + ".block1.w", cfg.bf16, 256L * 3 * cin), 256, c1, 256, 0);
+    g.bias = (const float*)get(P + ".block1.b", 2, 256);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
+    CKL(launch_gn_apply(c1, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
+                       tb, tb_stride, nullptr, a1, 0, B, L, cfg.bf16, stream_));
+    launches_ += 3;
+  }
+  {
+    GemmArgs g = conv3_args(a1, B, L, 256, 0, 256, get(P + ".block2.w", cfg.bf16, 256L * 768), 256, c2, 256, 0);
+    g.bias = (const float*)get(P + ".block2.b", 2, 256);
+    CK(run_gemm(g));
+  }
+  {
+    GemmArgs g;
+    g.A[0] = xin; g.a_rows[0] = L; g.a_cols[0] = col0 + cin; g.a_ld[0] = ld_in; g.a_bstride[0] = (long)L * ld_in;
+    g.nbatch = B; g.W = get(P + ".res.w", cfg.bf16, 256L * cin); g.N = 256; g.Ktot = cin; g.nseg = 1;
+    g.seg[0] = GemmSeg{0, 0, col0, cin / 64};
+    g.R = L; g.out_rows = L; g.out = r; g.ldc = 256; g.n_valid = 256;
+    g.bias = (const float*)get(P + ".res.b", 2, 256);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
+    CKL(launch_gn_apply(c2, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
+                       nullptr, 0, r, h, 1, B, L, cfg.bf16, stream_));
+    launches_ += 3;
+  }
+  *h_out = h;
+  if (rec) *rec = ResnetRec{P, cin, B, L, c1, c2, st1, st2, mask};
+  return 0;
+}
+
+int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, int iso_p,
+                      float** h_out, TBRec* rec) {
+  const long M = (long)B * L;
+  void* x1 = alloc(M * 256 * 2);
+  void* qkv = alloc(M * 1536 * 2);
+  void* o = alloc(M * 512 * 2);
+  float* lse = (float*)alloc((long)B * 8 * L * 4);
+  float* h1 = (float*)alloc(M * 256 * 4);
+  void* x3 = alloc(M * 256 * 2);
+  void* pre = alloc(M * 1024 * 2);
+  void* g16 = alloc(M * 1024 * 2);
+  float* h2 = (float*)alloc(M * 256 * 4);
+  if (!dry_) {
+    CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
+                            M, cfg.bf16, stream_));
+    ++launches_;
+  }
+  {
+    GemmArgs g = linear_args(x1, M, 256, get(Q + ".weff", cfg.bf16, 1536L * 256), 1536, qkv, 0);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    Plan& pl = *plan_;
+    if ((size_t)attn_idx_ >= pl.attn.size()) {
+      pl.attn.emplace_back(attn_plan_bytes());
+      if (attn_fwd_prepare(pl.attn.back().data(), qkv, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
+    }
+    CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), mask, iso_p, o, lse, stream_));
+    ++launches_;
+  }
+  {
+    GemmArgs g = linear_args(o, M, 512, get(Q + ".wo", cfg.bf16, 256L * 512), 256, h1, 1);
+    g.bias = (const float*)get(Q + ".bo", 2, 256);
+    g.resid = h0; g.ldr = 256;
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
+                            M, cfg.bf16, stream_));
+    ++launches_;
+  }
+  {
+    GemmArgs g = linear_args(x3, M, 256, get(Q + ".w1", cfg.bf16, 1024L * 256), 1024, g16, 0);
+    g.bias = (const float*)get(Q + ".b1", 2, 1024);
+    g.act = cfg.gelu_erf ? ACT_GELU_ERF : ACT_GELU_TANH;
+    g.aux_out = pre; g.ld_aux = 1024;
+    CK(run_gemm(g));
+  }
+  {
+    GemmArgs g = linear_args(g16, M, 1024, get(Q + ".w2", cfg.bf16, 256L * 1024), 256, h2, 1);
+    g.bias = (const float*)get(Q + ".b2", 2, 256);
+    g.resid = h1; g.ldr = 256;
+    CK(run_gemm(g));
+  }
+  *h_out = h2;
+  if (rec) *rec = TBRec{Q, lora_idx, B, L, h0, x1, qkv, o, lse, h1, pre, mask, iso_p};
+  return 0;
+}
+
+int Estimator::stage_fwd(const std::string& S, int res_idx, const void* xin, long ld_in, int col0, int cin, int B,
+                         int L, int T, const float* mask, int iso_len, float** h_out) {
+  float* h = nullptr;
+  ResnetRec rr;
+  CK(resnet_fwd(S + ".0", xin, ld_in, col0, cin, B, L, mask, tb_all_ + (long)res_idx * 256, (long)n_resnets() * 256,
+                &h, &rr));
+  StageRec st;
+  st.resnet = rr;
+  const int iso_p = iso_at(L, T, iso_len);
+  for (int j = 0; j < cfg.n_blocks; ++j) {
+    TBRec tr;
+    const std::string Q = S + ".1." + std::to_string(j);
+    CK(tb_fwd(Q, tb_counter_++, h, B, L, mask, iso_p, &h, &tr));
+    st.tbs.push_back(tr);
+  }
+  st.h_out = h;
+  stages_.push_back(st);
+  *h_out = h;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LoRA weight refresh
+// ------------------------------------------------------------------------------------------
+int Estimator::lora_refresh(cudaStream_t st) {
+  stream_ = st;
+  dry_ = false;
+  missing_ = false;
+  const int nb = n_tbs();
+  if (!lora_table_ready_) {
+    std::vector<LoraBlockPtrs> tab(nb);
+    int idx = 0;
+    auto fill = [&](const std::string& Q) {
+      LoraBlockPtrs& b = tab[idx++];
+      const char* pn[3] = {"q", "k", "v"};
+      for (int p = 0; p < 3; ++p) {
+        LoraLayerPtrs& l = b.p[p];
+        l.W = (const float*)get(Q + ".w" + pn[p], 2, 512L * 256);
+        const std::string a = Q + ".lora_" + pn[p] + ".A";
+        if (cfg.lora_r > 0 && has(a)) {
+          l.A = (const float*)get(a, 2, (long)cfg.lora_r * 256);
+          l.Bm = (const float*)get(Q + ".lora_" + pn[p] + ".B", 2, 512L * cfg.lora_r);
+          l.dA = has(a + ".grad") ? (float*)get(a + ".grad", 2, (long)cfg.lora_r * 256) : nullptr;
+          l.dB = has(a + ".grad") ? (float*)get(Q + ".lora_" + pn[p] + ".B.grad", 2, 512L * cfg.lora_r) : nullptr;
+        } else {
+          l.A = nullptr; l.Bm = nullptr; l.dA = nullptr; l.dB = nullptr;
+        }
+        l.scaling = cfg.lora_scaling;
+      }
+      b.weff = get(Q + ".weff", cfg.bf16, 1536L * 256);
+      b.weff_t = get(Q + ".weff_t", cfg.bf16, 1536L * 256);
+    };
+    for_each_tb(fill);
+    if (missing_) return -1;
+    if (!lora_table_dev_) {
+      if (cudaMalloc(&lora_table_dev_, sizeof(LoraBlockPtrs) * nb) != cudaSuccess) {
+        set_error("cudaMalloc(lora table) failed");
+        return -1;
+      }
+    }
+    if (cudaMemcpyAsync(lora_table_dev_, tab.data(), sizeof(LoraBlockPtrs) * nb, cudaMemcpyHostToDevice, st) !=
+        cudaSuccess) {
+      set_error("cudaMemcpy(lora table) failed");
+      return -1;
+    }
+    cudaStreamSynchronize(st);  // tab is a stack temporary
+    lora_table_ready_ = true;
+  }
+  CKL(launch_lora_merge(lora_table_dev_, nb, cfg.lora_r > 0 ? cfg.lora_r : 1, cfg.bf16, st));
+  return 0;
+}
+
+void Estimator::for_each_tb(const std::function<void(const std::string&)>& f) {
+  auto stage = [&](const std::string& S) {
+    for (int j = 0; j < cfg.n_blocks; ++j) f(S + ".1." + std::to_string(j));
+  };
+  stage("down_blocks.0"); stage("down_blocks.1");
+  for (int m = 0; m < cfg.n_mid; ++m) stage("mid_blocks." + std::to_string(m));
+  stage("up_blocks.0"); stage("up_blocks.1");
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+long Estimator::workspace_bytes(int B, int T, int training) {
+  dry_ = true;
+  ws_off_ = 0;
+  EstimatorIO io{};
+  io.B = B; io.T = T; io.training = training;
+  forward_impl(io);
+  if (training) backward_impl(nullptr, 1.f);
+  dry_ = false;
+  return ws_off_ + (1 << 20);
+}
+
+int Estimator::forward(const EstimatorIO& io, cudaStream_t st) {
+  if (!ws_) { set_error("estimator: no workspace set"); return -1; }
+  if (!lora_table_ready_) { set_error("estimator: call cvflow_lora_refresh before the first forward"); return -1; }
+  stream_ = st;
+  dry_ = false; missing_ = false; oom_ = false;
+  ws_off_ = 0;
+  PlanKey key{io.B, io.T, io.training, (uintptr_t)ws_};
+  plan_ = &plans_[key];
+  int r = forward_impl(io);
+  if (oom_) { set_error("estimator: workspace too small (%ld needed so far, %ld given)", ws_off_, ws_bytes_); return -1; }
+  if (r == 0) { last_io_ = io; have_fwd_ = io.training != 0; fwd_ws_end_ = ws_off_; }
+  return r;
+}
+
+int Estimator::forward_impl(const EstimatorIO& io) {
+  const int B = io.B, T = io.T, T2 = (T + 1) / 2;
+  gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0;
+  stages_.clear();
+  const int nres = n_resnets();
+  float* mask1 = (float*)alloc((long)B * T * 4);
+  float* mask2 = (float*)alloc((long)B * T2 * 4);
+  float* emb = (float*)alloc((long)B * 320 * 4);
+  float* te1 = (float*)alloc((long)B * 1024 * 4);
+  float* te2 = (float*)alloc((long)B * 1024 * 4);
+  tb_all_ = (float*)alloc((long)B * nres * 256 * 4);
+  gn_partials_ = (float*)alloc(((long)B * 64 * 8 * 3 + (long)B * 16) * 4);
+  void* xin0 = alloc((long)B * T * 320 * 2);
+  void* cat1 = alloc((long)B * T * 512 * 2);
+  void* cat0 = alloc((long)B * T2 * 512 * 2);
+  void* xd1 = alloc((long)B * T2 * 256 * 2);
+  mask1_ = mask1; mask2_ = mask2; cat1_ = cat1; cat0_ = cat0;
+  if (!dry_) {
+    CKL(launch_mask_down(io.mask, io.mask_nb, mask1, mask2, B, T, T2, stream_));
+    CKL(launch_sinus_embed(io.t, io.t_nb, emb, B, stream_));
+    CKL(launch_small_linear(emb, (const float*)get("time.w1", 2, 1024L * 320), (const float*)get("time.b1", 2, 1024), te1,
+                           B, 320, 1024, 0, 1, stream_));
+    CKL(launch_small_linear(te1, (const float*)get("time.w2", 2, 1024L * 1024), (const float*)get("time.b2", 2, 1024),
+                           te2, B, 1024, 1024, 0, 0, stream_));
+    CKL(launch_small_linear(te2, (const float*)get("time.proj_w", 2, (long)nres * 256 * 1024),
+                           (const float*)get("time.proj_b", 2, (long)nres * 256), tb_all_, B, 1024, nres * 256, 2, 0,
+                           stream_));
+    CKL(launch_pack_inputs(io.x, io.x_nb, io.mu, io.mu_nb, io.spks, io.spks_nb, io.cond, io.cond_nb, io.mask, io.mask_nb,
+                          io.keep, xin0, B, T, cfg.bf16, stream_));
+    launches_ += 6;
+  }
+  int res_idx = 0;
+  float* h = nullptr;
+  // ---- down 0 (length T) ----
+  CK(stage_fwd("down_blocks.0", res_idx++, xin0, 320, 0, 320, B, T, T, mask1, io.iso_len, &h));
+  if (!dry_) { CKL(launch_stage_out(h, mask1, cat1, 512, 256, (long)B * T, cfg.bf16, stream_)); ++launches_; }
+  {  // Downsample1D: Conv1d(k3, s2, p1) on the skip half of cat1 through even/odd row views
+    GemmArgs g;
+    const uint16_t* base = reinterpret_cast<const uint16_t*>(cat1);
+    g.A[0] = base; g.a_rows[0] = (T + 1) / 2; g.a_cols[0] = 512; g.a_ld[0] = 1024; g.a_bstride[0] = (long)T * 512;
+    g.A[1] = base + 512; g.a_rows[1] = T / 2; g.a_cols[1] = 512; g.a_ld[1] = 1024; g.a_bstride[1] = (long)T * 512;
+    if (T / 2 == 0) { g.A[1] = base; g.a_rows[1] = 0; }
+    g.nbatch = B; g.W = get("down_blocks.0.2.w", cfg.bf16, 256L * 768); g.N = 256; g.Ktot = 768; g.nseg = 3;
+    g.seg[0] = GemmSeg{1, -1, 256, 4}; g.seg[1] = GemmSeg{0, 0, 256, 4}; g.seg[2] = GemmSeg{1, 0, 256, 4};
+    g.R = T2; g.out_rows = T2; g.out = xd1; g.ldc = 256; g.n_valid = 256;
+    g.bias = (const float*)get("down_blocks.0.2.b", 2, 256); g.rowmask = mask2;
+    CK(run_gemm(g));
+  }
+  // ---- down 1 (length T2) ----
+  CK(stage_fwd("down_blocks.1", res_idx++, xd1, 256, 0, 256, B, T2, T, mask2, io.iso_len, &h));
+  if (!dry_) { CKL(launch_stage_out(h, mask2, cat0, 512, 256, (long)B * T2, cfg.bf16, stream_)); ++launches_; }
+  void* xm = cfg.n_mid > 0 ? alloc((long)B * T2 * 256 * 2) : nullptr;
+  {
+    GemmArgs g = conv3_args(cat0, B, T2, 512, 256, 256, get("down_blocks.1.2.w", cfg.bf16, 256L * 768), 256,
+                            cfg.n_mid > 0 ? xm : cat0, cfg.n_mid > 0 ? 256 : 512, 0);
+    g.bias = (const float*)get("down_blocks.1.2.b", 2, 256); g.rowmask = mask2;
+    CK(run_gemm(g));
+  }
+  // ---- mid ----
+  const void* x = xm;
+  for (int m = 0; m < cfg.n_mid; ++m) {
+    CK(stage_fwd("mid_blocks." + std::to_string(m), res_idx++, x, 256, 0, 256, B, T2, T, mask2, io.iso_len, &h));
+    const bool last = m == cfg.n_mid - 1;
+    void* nx = last ? cat0 : alloc((long)B * T2 * 256 * 2);
+    if (!dry_) { CKL(launch_stage_out(h, mask2, nx, last ? 512 : 256, 0, (long)B * T2, cfg.bf16, stream_)); ++launches_; }
+    x = nx;
+  }
+  // ---- up 0 (length T2, input cat0 = [x | skip1]) ----
+  CK(stage_fwd("up_blocks.0", res_idx++, cat0, 512, 0, 512, B, T2, T, mask2, io.iso_len, &h));
+  void* xu = alloc((long)B * T2 * 256 * 2);
+  if (!dry_) { CKL(launch_stage_out(h, mask2, xu, 256, 0, (long)B * T2, cfg.bf16, stream_)); ++launches_; }
+  for (int ph = 0; ph < 2; ++ph) {  // Upsample1D: ConvTranspose1d(k4, s2, p1), two output phases into cat1[:, :T, :256]
+    GemmArgs g;
+    g.A[0] = xu; g.a_rows[0] = T2; g.a_cols[0] = 256; g.a_ld[0] = 256; g.a_bstride[0] = (long)T2 * 256;
+    g.nbatch = B; g.N = 256; g.Ktot = 512; g.nseg = 2;
+    g.W = get(ph == 0 ? "up_blocks.0.2.w_even" : "up_blocks.0.2.w_odd", cfg.bf16, 256L * 512);
+    g.seg[0] = GemmSeg{0, ph == 0 ? 0 : 1, 0, 4};
+    g.seg[1] = GemmSeg{0, ph == 0 ? -1 : 0, 0, 4};
+    g.R = T2; g.rmul = 2; g.roff = ph; g.out_rows = T; g.out = cat1; g.ldc = 512; g.col_off = 0; g.n_valid = 256;
+    g.bias = (const float*)get("up_blocks.0.2.b", 2, 256); g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  // ---- up 1 (length T, input cat1 = [x | skip0]) ----
+  CK(stage_fwd("up_blocks.1", res_idx++, cat1, 512, 0, 512, B, T, T, mask1, io.iso_len, &h));
+  void* xu1 = alloc((long)B * T * 256 * 2);
+  if (!dry_) { CKL(launch_stage_out(h, mask1, xu1, 256, 0, (long)B * T, cfg.bf16, stream_)); ++launches_; }
+  void* xf = alloc((long)B * T * 256 * 2);
+  {
+    GemmArgs g = conv3_args(xu1, B, T, 256, 0, 256, get("up_blocks.1.2.w", cfg.bf16, 256L * 768), 256, xf, 256, 0);
+    g.bias = (const float*)get("up_blocks.1.2.b", 2, 256); g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  // ---- final block + projection ----
+  void* cf = alloc((long)B * T * 256 * 2);
+  void* af = alloc((long)B * T * 256 * 2);
+  float* stf = (float*)alloc(B * 16 * 4);
+  {
+    GemmArgs g = conv3_args(xf, B, T, 256, 0, 256, get("final_block.w", cfg.bf16, 256L * 768), 256, cf, 256, 0);
+    g.bias = (const float*)get("final_block.b", 2, 256);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
+    CKL(launch_gn_apply(cf, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
+                       mask1, nullptr, 0, nullptr, af, 0, B, T, cfg.bf16, stream_));
+    launches_ += 3;
+  }
+  final_ = FinalRec{cf, stf};
+  {
+    GemmArgs g;
+    g.A[0] = af; g.a_rows[0] = T; g.a_cols[0] = 256; g.a_ld[0] = 256; g.a_bstride[0] = (long)T * 256;
+    g.nbatch = B; g.W = get("final_proj.w", cfg.bf16, 128L * 256); g.N = 128; g.Ktot = 256; g.nseg = 1;
+    g.seg[0] = GemmSeg{0, 0, 0, 4};
+    g.R = T; g.out_rows = T; g.out = io.out; g.transposed_out = 1; g.n_valid = 80;
+    g.bias = (const float*)get("final_proj.b", 2, 80); g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  if (missing_) return -1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+int Estimator::backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st) {
+  grad_scale_dev_ = grad_scale_dev;
+  if (!have_fwd_) { set_error("estimator: backward needs a preceding forward with training=1"); return -1; }
+  stream_ = st;
+  dry_ = false; missing_ = false; oom_ = false;
+  ws_off_ = fwd_ws_end_;
+  int r = backward_impl(dpred16, grad_scale);
+  if (oom_) { set_error("estimator: workspace too small for backward"); return -1; }
+  have_fwd_ = false;
+  return r;
+}
+
+int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp) {
+  const long M = (long)t.B * t.L;
+  const std::string& Q = t.prefix;
+  {  // d pre = (dh2 W2) * gelu'(pre)
+    GemmArgs g = linear_args(dh16, M, 256, get(Q + ".w2_t", cfg.bf16, 1024L * 256), 1024, tmp.dpre, 0);
+    g.act = cfg.gelu_erf ? ACT_MUL_GELU_ERF_GRAD : ACT_MUL_GELU_TANH_GRAD;
+    g.mul_src = t.pre; g.ld_aux = 1024;
+    CK(run_gemm(g));
+  }
+  {
+    GemmArgs g = linear_args(tmp.dpre, M, 1024, get(Q + ".w1_t", cfg.bf16, 256L * 1024), 256, tmp.dx, 0);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_layernorm_bwd(tmp.dx, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+                            stream_));
+    ++launches_;
+  }
+  {
+    GemmArgs g = linear_args(dh16, M, 256, get(Q + ".wo_t", cfg.bf16, 512L * 256), 512, tmp.dO, 0);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    Plan& pl = *plan_;
+    if ((size_t)attn_idx_ >= pl.attn.size()) {
+      pl.attn.emplace_back(attn_plan_bytes());
+      if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
+        return -1;
+    }
+    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
+    launches_ += 3;
+    if (cfg.lora_r > 0) {
+      CKL(launch_lora_wgrad(lora_table_dev_ + t.lora_idx, tmp.dqkv, t.x1, M, cfg.lora_r, grad_scale, grad_scale_dev_, tmp.wg_scratch,
+                           cfg.bf16, stream_));
+      launches_ += 2;
+    }
+  }
+  if (need_input_grad) {
+    GemmArgs g = linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, tmp.dx, 0);
+    CK(run_gemm(g));
+    if (!dry_) {
+      CKL(launch_layernorm_bwd(tmp.dx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+                              stream_));
+      ++launches_;
+    }
+  }
+  return 0;
+}
+
+// grad wrt the (masked) resnet input: dxin16 [B][L][cin] = conv1 dgrad + res_conv dgrad, * mask
+int Estimator::resnet_bwd(const ResnetRec& r, const float* dout32, const void* dout16, void* dxin16, BwdTemps& tmp) {
+  const std::string& P = r.prefix;
+  const int B = r.B, L = r.L;
+  if (!dry_) {
+    CKL(launch_gn_bwd(dout32, 1, r.c2, r.st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256),
+                     r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
+    launches_ += 3;
+  }
+  {
+    GemmArgs g = conv3_args(tmp.dc, B, L, 256, 0, 256, get(P + ".block2.wd", cfg.bf16, 256L * 768), 256, tmp.da, 256, 0);
+    CK(run_gemm(g));
+  }
+  if (!dry_) {
+    CKL(launch_gn_bwd(tmp.da, 0, r.c1, r.st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256),
+                     r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
+    launches_ += 3;
+  }
+  {
+    GemmArgs g;
+    g.A[0] = tmp.dc; g.a_rows[0] = L; g.a_cols[0] = 256; g.a_ld[0] = 256; g.a_bstride[0] = (long)L * 256;
+    g.A[1] = dout16; g.a_rows[1] = L; g.a_cols[1] = 256; g.a_ld[1] = 256; g.a_bstride[1] = (long)L * 256;
+    g.nbatch = B; g.W = get(P + ".in.wd", cfg.bf16, (long)r.cin * 1024); g.N = r.cin; g.Ktot = 1024; g.nseg = 4;
+    for (int t = 0; t < 3; ++t) g.seg[t] = GemmSeg{0, t - 1, 0, 4};
+    g.seg[3] = GemmSeg{1, 0, 0, 4};
+    g.R = L; g.out_rows = L; g.out = dxin16; g.ldc = r.cin; g.n_valid = r.cin; g.rowmask = r.mask;
+    CK(run_gemm(g));
+  }
+  return 0;
+}
+
+int Estimator::stage_bwd(const StageRec& s, float* dh32, void* dh16, void* dxin16, bool first_stage, float grad_scale,
+                         BwdTemps& tmp) {
+  for (int j = (int)s.tbs.size() - 1; j >= 0; --j) {
+    const bool need = !(first_stage && j == 0);
+    CK(tb_bwd(s.tbs[j], dh32, dh16, need, grad_scale, tmp));
+  }
+  if (!first_stage) CK(resnet_bwd(s.resnet, dh32, dh16, dxin16, tmp));
+  return 0;
+}
+
+int Estimator::backward_impl(const void* dpred16, float grad_scale) {
+  const int B = last_io_.B, T = last_io_.T, T2 = (T + 1) / 2;
+  const long MT = (long)B * T, MH = (long)B * T2;
+  BwdTemps tmp;
+  tmp.dpre = alloc(MT * 1024 * 2);
+  tmp.dx = alloc(MT * 256 * 2);
+  tmp.dO = alloc(MT * 512 * 2);
+  tmp.dqkv = alloc(MT * 1536 * 2);
+  tmp.delta = (float*)alloc((long)B * 8 * T * 4);
+  tmp.dc = alloc(MT * 256 * 2);
+  tmp.da = alloc(MT * 256 * 2);
+  tmp.wg_scratch = (float*)alloc(lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1) * 4);
+  float* dh32 = (float*)alloc(MT * 256 * 4);
+  void* dh16 = alloc(MT * 256 * 2);
+  void* g16a = alloc(MT * 256 * 2);
+  void* dcat1 = alloc(MT * 512 * 2);
+  void* dcat0 = alloc(MH * 512 * 2);
+  void* dx16 = alloc(MH * 256 * 2);
+  if (dry_) {
+    // mirror the memoised-launch counters only; nothing to launch
+    return 0;
+  }
+  const float* mask1 = mask1_;
+  const float* mask2 = mask2_;
+  const int ns = (int)stages_.size();  // down0, down1, mid..., up0, up1
+  // ---- final_proj / final_block / up1 tail conv ----
+  {
+    GemmArgs g;
+    g.A[0] = dpred16; g.a_rows[0] = T; g.a_cols[0] = 128; g.a_ld[0] = 128; g.a_bstride[0] = (long)T * 128;
+    g.nbatch = B; g.W = get("final_proj.wt", cfg.bf16, 256L * 128); g.N = 256; g.Ktot = 128; g.nseg = 1;
+    g.seg[0] = GemmSeg{0, 0, 0, 2};
+    g.R = T; g.out_rows = T; g.out = tmp.da; g.ldc = 256; g.n_valid = 256;
+    CK(run_gemm(g));
+  }
+  CKL(launch_gn_bwd(tmp.da, 0, final_.cf, final_.st, (const float*)get("final_block.gn.w", 2, 256),
+                   (const float*)get("final_block.gn.b", 2, 256), mask1, gn_partials_, tmp.dc, B, T, cfg.bf16, stream_));
+  launches_ += 3;
+  {
+    GemmArgs g = conv3_args(tmp.dc, B, T, 256, 0, 256, get("final_block.wd", cfg.bf16, 256L * 768), 256, g16a, 256, 0);
+    g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  {
+    GemmArgs g = conv3_args(g16a, B, T, 256, 0, 256, get("up_blocks.1.2.wd", cfg.bf16, 256L * 768), 256, dh16, 256, 0);
+    g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  CKL(launch_grad_route(dh16, 256, 0, nullptr, dh32, 0, nullptr, MT, cfg.bf16, stream_));
+  ++launches_;
+  // ---- up 1 ----
+  CK(stage_bwd(stages_[ns - 1], dh32, dh16, dcat1, false, grad_scale, tmp));
+  {  // ConvTranspose1d backward: stride-2 gather over dcat1[:, :, :256] through even/odd row views
+    GemmArgs g;
+    const uint16_t* base = reinterpret_cast<const uint16_t*>(dcat1);
+    g.A[0] = base; g.a_rows[0] = (T + 1) / 2; g.a_cols[0] = 256; g.a_ld[0] = 1024; g.a_bstride[0] = (long)T * 512;
+    g.A[1] = base + 512; g.a_rows[1] = T / 2; g.a_cols[1] = 256; g.a_ld[1] = 1024; g.a_bstride[1] = (long)T * 512;
+    if (T / 2 == 0) { g.A[1] = base; g.a_rows[1] = 0; }
+    g.nbatch = B; g.W = get("up_blocks.0.2.wd", cfg.bf16, 256L * 1024); g.N = 256; g.Ktot = 1024; g.nseg = 4;
+    g.seg[0] = GemmSeg{1, -1, 0, 4};  // k=0: row 2i-1
+    g.seg[1] = GemmSeg{0, 0, 0, 4};   // k=1: row 2i
+    g.seg[2] = GemmSeg{1, 0, 0, 4};   // k=2: row 2i+1
+    g.seg[3] = GemmSeg{0, 1, 0, 4};   // k=3: row 2i+2
+    g.R = T2; g.out_rows = T2; g.out = dh16; g.ldc = 256; g.n_valid = 256; g.rowmask = mask2;
+    CK(run_gemm(g));
+  }
+  CKL(launch_grad_route(dh16, 256, 0, nullptr, dh32, 0, nullptr, MH, cfg.bf16, stream_));
+  ++launches_;
+  // ---- up 0 ----
+  CK(stage_bwd(stages_[ns - 2], dh32, dh16, dcat0, false, grad_scale, tmp));
+  // ---- mid (reverse) ----
+  const void* gsrc = dcat0;  // grad wrt the 16-bit masked input of the stage just processed
+  long gld = 512;
+  for (int m = cfg.n_mid - 1; m >= 0; --m) {
+    CKL(launch_grad_route(gsrc, gld, 0, mask2, dh32, 0, dh16, MH, cfg.bf16, stream_));
+    ++launches_;
+    CK(stage_bwd(stages_[2 + m], dh32, dh16, dx16, false, grad_scale, tmp));
+    gsrc = dx16; gld = 256;
+  }
+  // ---- down_blocks.1.2 (plain conv) dgrad + skip1 ----
+  {
+    GemmArgs g = conv3_args(gsrc, B, T2, gld, 0, 256, get("down_blocks.1.2.wd", cfg.bf16, 256L * 768), 256, g16a, 256, 0);
+    g.rowmask = mask2;
+    CK(run_gemm(g));
+  }
+  CKL(launch_grad_route(g16a, 256, 0, nullptr, dh32, 0, nullptr, MH, cfg.bf16, stream_));
+  CKL(launch_grad_route(dcat0, 512, 256, mask2, dh32, 1, dh16, MH, cfg.bf16, stream_));
+  launches_ += 2;
+  // ---- down 1 ----
+  CK(stage_bwd(stages_[1], dh32, dh16, dx16, false, grad_scale, tmp));
+  // ---- Downsample1D backward: two output phases into g16a [B][T][256] ----
+  for (int ph = 0; ph < 2; ++ph) {
+    GemmArgs g;
+    g.A[0] = dx16; g.a_rows[0] = T2; g.a_cols[0] = 256; g.a_ld[0] = 256; g.a_bstride[0] = (long)T2 * 256;
+    g.nbatch = B; g.N = 256;
+    if (ph == 0) {
+      g.W = get("down_blocks.0.2.wd_even", cfg.bf16, 256L * 256); g.Ktot = 256; g.nseg = 1;
+      g.seg[0] = GemmSeg{0, 0, 0, 4};
+    } else {
+      g.W = get("down_blocks.0.2.wd_odd", cfg.bf16, 256L * 512); g.Ktot = 512; g.nseg = 2;
+      g.seg[0] = GemmSeg{0, 1, 0, 4};
+      g.seg[1] = GemmSeg{0, 0, 0, 4};
+    }
+    g.R = T2; g.rmul = 2; g.roff = ph; g.out_rows = T; g.out = g16a; g.ldc = 256; g.n_valid = 256; g.rowmask = mask1;
+    CK(run_gemm(g));
+  }
+  CKL(launch_grad_route(g16a, 256, 0, nullptr, dh32, 0, nullptr, MT, cfg.bf16, stream_));
+  CKL(launch_grad_route(dcat1, 512, 256, mask1, dh32, 1, dh16, MT, cfg.bf16, stream_));
+  launches_ += 2;
+  // ---- down 0: transformer blocks only (nothing trainable upstream of them) ----
+  CK(stage_bwd(stages_[0], dh32, dh16, nullptr, true, grad_scale, tmp));
+  if (missing_) return -1;
+  return 0;
+}
+
+}  // namespace cvflow

@@ -1,0 +1,113 @@
+// Estimator handle: bound weights, workspace, memoised launch plans (see estimator.cu).
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "gemm.h"
+#include "kernels.h"
+
+namespace cvflow {
+
+char* error_buf();
+int error_buf_len();
+
+struct EstimatorConfig {
+  int n_blocks = 4;     // transformer blocks per stage
+  int n_mid = 12;       // mid stages
+  int bf16 = 0;         // 16-bit operand type: 0 fp16, 1 bf16
+  int gelu_erf = 0;     // 0: tanh approximation (reference modules.py:132), 1: erf
+  int lora_r = 0;       // 0: no LoRA on q/k/v
+  float lora_scaling = 1.f;
+};
+
+struct EstimatorIO {
+  const float* x; int x_nb;        // [x_nb][80][T]
+  const float* mask; int mask_nb;  // [mask_nb][T]
+  const float* mu; int mu_nb;
+  const float* t; int t_nb;        // [t_nb]
+  const float* spks; int spks_nb;  // [spks_nb][80] (nullable)
+  const float* cond; int cond_nb;  // nullable
+  const float* keep;               // [B] CFG keep factors (nullable)
+  float* out;                      // [B][80][T]
+  int B, T, iso_len, training;
+};
+
+struct BoundTensor { void* ptr; long numel; int dtype; };  // dtype: 0 f16, 1 bf16, 2 f32
+
+struct ResnetRec { std::string prefix; int cin, B, L; void *c1, *c2; float *st1, *st2; const float* mask; };
+struct TBRec {
+  std::string prefix; int lora_idx, B, L; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
+  const float* mask; int iso_p;
+};
+struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
+struct FinalRec { void* cf; float* st; };
+struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; };
+
+struct PlanKey {
+  int B, T, training; uintptr_t ws;
+  bool operator<(const PlanKey& o) const {
+    if (B != o.B) return B < o.B;
+    if (T != o.T) return T < o.T;
+    if (training != o.training) return training < o.training;
+    return ws < o.ws;
+  }
+};
+struct Plan { std::vector<GemmParams> gemms; std::vector<std::vector<uint8_t>> attn; };
+
+class Estimator {
+ public:
+  explicit Estimator(const EstimatorConfig& c);
+  ~Estimator();
+  int bind(const char* name, void* ptr, long numel, int dtype);
+  void set_workspace(void* p, long bytes) { ws_ = p; ws_bytes_ = bytes; plans_.clear(); }
+  long workspace_bytes(int B, int T, int training);
+  int lora_refresh(cudaStream_t st);
+  int forward(const EstimatorIO& io, cudaStream_t st);
+  int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
+  long launches() const { return launches_; }
+  EstimatorConfig cfg;
+
+ private:
+  int n_resnets() const { return 4 + cfg.n_mid; }
+  int n_tbs() const { return (4 + cfg.n_mid) * cfg.n_blocks; }
+  void* get(const std::string& name, int dtype, long numel);
+  bool has(const std::string& name) const;
+  void* alloc(long bytes);
+  int run_gemm(GemmArgs& a);
+  int iso_at(int L, int T, int iso_len) const;
+  void for_each_tb(const std::function<void(const std::string&)>& f);
+  int forward_impl(const EstimatorIO& io);
+  int backward_impl(const void* dpred16, float grad_scale);
+  int resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L, const float* mask,
+                 const float* tb, long tb_stride, float** h_out, ResnetRec* rec);
+  int tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, int iso_p, float** h_out,
+             TBRec* rec);
+  int stage_fwd(const std::string& S, int res_idx, const void* xin, long ld_in, int col0, int cin, int B, int L, int T,
+                const float* mask, int iso_len, float** h_out);
+  int tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp);
+  int resnet_bwd(const ResnetRec& r, const float* dout32, const void* dout16, void* dxin16, BwdTemps& tmp);
+  int stage_bwd(const StageRec& s, float* dh32, void* dh16, void* dxin16, bool first_stage, float grad_scale,
+                BwdTemps& tmp);
+
+  std::unordered_map<std::string, BoundTensor> bound_;
+  std::map<PlanKey, Plan> plans_;
+  Plan* plan_ = nullptr;
+  void* ws_ = nullptr;
+  long ws_bytes_ = 0, ws_off_ = 0, fwd_ws_end_ = 0;
+  bool dry_ = false, missing_ = false, oom_ = false, have_fwd_ = false, lora_table_ready_ = false;
+  int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0;
+  long launches_ = 0;
+  cudaStream_t stream_ = nullptr;
+  LoraBlockPtrs* lora_table_dev_ = nullptr;
+  // per-forward state
+  std::vector<StageRec> stages_;
+  FinalRec final_{};
+  EstimatorIO last_io_{};
+  const float* grad_scale_dev_ = nullptr;
+  float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
+  void *cat0_ = nullptr, *cat1_ = nullptr;
+};
+
+}  // namespace cvflow

@@ -1,0 +1,102 @@
+// Host launchers of the non-GEMM kernels (HBM-bound passes, attention, LoRA, optimiser).
+// All pointers are device pointers; every launcher is asynchronous on `st` and returns the
+// cudaError_t of the launch as a negative int (0 = ok).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvflow {
+
+// ---- elementwise.cu ------------------------------------------------------------------------
+// [x | mu*keep | spks*keep | cond*keep] * mask -> token-major 16-bit [B][T][320]
+// (replaces einops.pack / repeat at modules.py:1008-1014 and the x*mask of the first Block1D).
+// Source batch rows are taken modulo their own batch count (CFG packing of solve_euler,
+// flow_model.py:108-113, without materialising the batch-2 copies).
+int launch_pack_inputs(const float* x, int x_nb, const float* mu, int mu_nb, const float* spks, int spks_nb,
+                       const float* cond, int cond_nb, const float* mask, int mask_nb, const float* keep,
+                       void* out, int B, int T, int bf16, cudaStream_t st);
+// mask2[b][j] = mask[b % mask_nb][2j]   (modules.py:1049, masks.append(mask[:, :, ::2]))
+int launch_mask_down(const float* mask, int mask_nb, float* mask1, float* mask2, int B, int T, int T2,
+                     cudaStream_t st);
+// sinusoidal embedding, scale 1000, dim 320 (modules.py:27-42)
+int launch_sinus_embed(const float* t, int t_nb, float* out, int B, cudaStream_t st);
+// y[b][n] = out_act(sum_k in_act(x[b][k]) W[n][k] + bias[n]); act: 0 none, 1 silu, 2 mish
+int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
+                        int in_act, int out_act, cudaStream_t st);
+// 16-bit masked copy of the fp32 residual stream into (dst, ldc, col_off)
+int launch_stage_out(const float* h, const float* rowmask, void* dst, long ldc, int col_off, long M, int bf16,
+                     cudaStream_t st);
+// fp32 [M][256] (+)= 16-bit src[M][ld_src, col_off..+256] * rowmask   (skip / concat gradient routing)
+int launch_grad_route(const void* src, long ld_src, int col_off, const float* rowmask, float* dst, int accumulate,
+                      void* dst16, long M, int bf16, cudaStream_t st);
+// y = (1-(1-sigma)t) z + t x1   (flow_model.py:154)
+int launch_cfm_prep(const float* x1, const float* z, const float* t, float* y, int B, int T, float sigma_min,
+                    cudaStream_t st);
+// w-sum, masked loss and dL/dpred (flow_model.py:197-200); dpred is 16-bit token-major [B][T][128]
+// (cols 80..127 zero) scaled by loss_scale. scal[0]=sum w, scal[1]=loss numerator, scal[2]=loss.
+int launch_cfm_loss(const float* pred, const float* x1, const float* z, const float* w, const float* mask,
+                    float* scal, float* partials, void* dpred, int B, int T, float sigma_min, float loss_scale,
+                    int bf16, cudaStream_t st);
+// x += dt * ((1+g) d[0] - g d[1])   (flow_model.py:117-119)
+int launch_euler_update(float* x, const float* d, const float* dt_arr, int step, float cfg_rate, long n,
+                        cudaStream_t st);
+
+// ---- norm.cu -------------------------------------------------------------------------------
+int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, void* out, long M, int bf16,
+                         cudaStream_t st);
+// dh = dres + LN'(dxn16; h_in); also writes the 16-bit copy dh16 (nullable)
+int launch_layernorm_bwd(const void* dxn16, const float* h_in, const float* gamma, const float* dres, float* dh,
+                         void* dh16, long M, int bf16, cudaStream_t st);
+// GroupNorm(8 groups of 32 channels, C=256) over the padded extent L of [B][L][256]
+int gn_num_splits(int B, int L);
+int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st);
+// mode 0: out16 = (mish(gn(c)) + tb[b][c]) * mask        (tb nullable)
+// mode 1: out32 = mish(gn(c)) * mask + add16             (resnet output, fp32 residual stream)
+int launch_gn_apply(const void* c16, const float* stats, const float* gamma, const float* beta, const float* mask,
+                    const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L, int bf16,
+                    cudaStream_t st);
+// dy: fp32 (dy_f32=1) or 16-bit; masked by rowmask. Produces dc16.
+int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stats, const float* gamma,
+                  const float* beta, const float* mask, float* partials, void* dc16, int B, int L, int bf16,
+                  cudaStream_t st);
+
+// ---- attention.cu --------------------------------------------------------------------------
+// qkv 16-bit [B][L][1536] (q | k | v, 8 heads x 64) -> o 16-bit [B][L][512], lse fp32 [B][8][L]
+// keymask fp32 [B][L]; iso_p: prompt-isolation boundary at this resolution (0 = off).
+struct AttnPlan;  // holds the encoded tensor maps
+int attn_plan_bytes();
+int attn_fwd_prepare(void* plan, const void* qkv, int B, int L, int bf16, char* err, int errlen);
+int attn_fwd_launch(const void* plan, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st);
+int attn_bwd_prepare(void* plan, const void* qkv, const void* dout, int B, int L, int bf16, char* err, int errlen);
+int attn_bwd_launch(const void* plan, const float* keymask, int iso_p, const void* o, const float* lse,
+                    float* delta, void* dqkv, cudaStream_t st);
+
+// ---- lora.cu -------------------------------------------------------------------------------
+struct LoraLayerPtrs {       // one q/k/v projection of one attention block
+  const float* W;            // frozen [512][256] fp32
+  const float* A;            // [r][256] fp32 (nullable -> plain cast)
+  const float* Bm;           // [512][r] fp32
+  float* dA;                 // grads (nullable)
+  float* dB;
+  float scaling;
+};
+struct LoraBlockPtrs {       // one attention block: q, k, v + the merged 16-bit images
+  LoraLayerPtrs p[3];
+  void* weff;                // [1536][256]
+  void* weff_t;              // [256][1536]
+};
+// W_eff = W + s * B A for every block in one launch; writes both layouts.
+int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, cudaStream_t st);
+// dA, dB of the three projections of one block from dqkv [M][1536], xn [M][256].
+int launch_lora_wgrad(const LoraBlockPtrs* block_dev, const void* dqkv, const void* xn, long M, int r,
+                      float grad_scale, const float* grad_scale_dev, float* scratch, int bf16, cudaStream_t st);
+long lora_wgrad_scratch_floats(long M, int r);
+
+// ---- optim.cu ------------------------------------------------------------------------------
+// Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).
+int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cudaStream_t st);
+int launch_adamw(float* p, const float* g, float* m, float* v, long n, const float* sumsq, float grad_unscale,
+                 float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step,
+                 int* found_inf, cudaStream_t st);
+
+}  // namespace cvflow

@@ -85,6 +85,81 @@ typedef struct cvflow_gemm_desc {
 
 CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* desc, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Estimator handle: ConditionalDecoder.forward and its backward (reference modules.py:886-1106),
+ * i.e. what `self.estimator(x, mask, mu, t, spks, cond)` runs in flow_model.py:116,174.
+ * One handle = one device + one in-flight call (the caller serialises, as the reference's
+ * TrtContextWrapper queue does). All kernels go to the given stream; no host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cvflow_estimator cvflow_estimator;
+
+typedef struct cvflow_config {
+  int32_t n_blocks;      /* transformer blocks per stage (CosyVoice-300M: 4) */
+  int32_t n_mid;         /* mid stages (CosyVoice-300M: 12) */
+  int32_t dtype;         /* CVFLOW_DTYPE_F16 / BF16 operand type (fp32 accumulate, fp32 residual stream) */
+  int32_t gelu_erf;      /* 0 = tanh approximation (reference default), 1 = erf */
+  int32_t lora_r;        /* LoRA rank on attn1.to_q/k/v, 0 = none */
+  float lora_scaling;    /* alpha / r */
+} cvflow_config;
+
+CVFLOW_API int cvflow_create(const cvflow_config* cfg, cvflow_estimator** out);
+CVFLOW_API void cvflow_destroy(cvflow_estimator* h);
+/* Bind a device tensor by name (names are listed in DESIGN.md "weight binding").
+ * dtype: 0 f16, 1 bf16, 2 f32. The memory stays owned by the caller and must outlive the handle. */
+CVFLOW_API int cvflow_bind(cvflow_estimator* h, const char* name, void* ptr, int64_t numel, int32_t dtype);
+CVFLOW_API int64_t cvflow_workspace_bytes(cvflow_estimator* h, int32_t B, int32_t T, int32_t training);
+CVFLOW_API int cvflow_set_workspace(cvflow_estimator* h, void* ptr, int64_t bytes);
+/* Rebuild the merged 16-bit q/k/v operands W + (alpha/r) B A from the bound fp32 masters
+ * (lora.py:64-76 folded into the GEMM operand). Call after binding and after every optimiser step. */
+CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream);
+
+typedef struct cvflow_estimator_io {
+  const float* x;    int32_t x_nb;     /* [x_nb][80][T]; batch row b reads row b % x_nb */
+  const float* mask; int32_t mask_nb;  /* [mask_nb][T] in {0,1} */
+  const float* mu;   int32_t mu_nb;
+  const float* t;    int32_t t_nb;     /* [t_nb] */
+  const float* spks; int32_t spks_nb;  /* [spks_nb][80], may be NULL */
+  const float* cond; int32_t cond_nb;  /* may be NULL */
+  const float* keep;                   /* [B] multiplier of mu/spks/cond (CFG drop / uncond row), may be NULL */
+  float* out;                          /* [B][80][T] fp32, zero where mask = 0 */
+  int32_t B, T;
+  int32_t iso_len;                     /* prompt_isolation_len (0 = off), modules.py:1034-1042 */
+  int32_t training;                    /* 1: keep activations for cvflow_estimator_backward */
+} cvflow_estimator_io;
+
+CVFLOW_API int cvflow_estimator_forward(cvflow_estimator* h, const cvflow_estimator_io* io, void* stream);
+/* dpred16: dL/dout as 16-bit token-major [B][T][128] (columns 80..127 zero), as cvflow_cfm_loss
+ * writes it. Accumulates grad_scale * (*grad_scale_dev) * dL/d(lora_A|lora_B) into the bound
+ * "<...>.grad" tensors; grad_scale_dev is an optional device scalar (NULL = 1), so an upstream
+ * autograd factor never forces a host synchronisation. */
+CVFLOW_API int cvflow_estimator_backward(cvflow_estimator* h, const void* dpred16, float grad_scale,
+                                         const float* grad_scale_dev, void* stream);
+CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * CFM passes (reference flow_model.py:94-204)
+ * ------------------------------------------------------------------------------------------- */
+/* y = (1-(1-sigma_min) t) z + t x1            flow_model.py:154 */
+CVFLOW_API int cvflow_cfm_prep(const float* x1, const float* z, const float* t, float* y, int32_t B, int32_t T,
+                               float sigma_min, void* stream);
+/* loss = sum(((pred-u) w)^2) / (sum(w) 80), u = x1-(1-sigma_min) z   flow_model.py:155,197-200
+ * scal[0] = sum w, scal[1] = numerator, scal[2] = loss; partials: >= B*ceil(T/32) floats scratch;
+ * dpred16 (nullable): loss_scale * dL/dpred * mask, 16-bit token-major [B][T][128]. */
+CVFLOW_API int cvflow_cfm_loss(const float* pred, const float* x1, const float* z, const float* w, const float* mask,
+                               float* scal, float* partials, void* dpred16, int32_t B, int32_t T, float sigma_min,
+                               float loss_scale, int32_t dtype, void* stream);
+/* x += dt[step] * ((1+cfg) d[0] - cfg d[1]) over n = 80*T elements   flow_model.py:117-119 */
+CVFLOW_API int cvflow_euler_update(float* x, const float* d, const float* dt, int32_t step, float cfg_rate, int64_t n,
+                                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser tail on the flat fp32 LoRA bucket (train_joint.py:198-226, gradient_clip_val 1.0)
+ * ------------------------------------------------------------------------------------------- */
+CVFLOW_API int cvflow_sumsq(const float* g, int64_t n, float* partials /* >= 296 */, float* out, void* stream);
+CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                                 float grad_unscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, int32_t step, int32_t* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
