@@ -89,6 +89,8 @@ class NativeEstimator:
         self.ws = None
         self.ws_key = None
         self.loss_scale = LOSS_SCALE_DEFAULT if dtype == torch.float16 else 1.0
+        self._dirty = False
+        self._merged_version = -1
         self._build()
 
     def __del__(self):
@@ -274,6 +276,26 @@ class NativeEstimator:
     def refresh_lora(self):
         """Rebuild W_eff = W + (alpha/r) B A (call after every optimiser step)."""
         N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
+        self._merged_version = self.param_bucket._version
+        self._dirty = False
+
+    def mark_dirty(self):
+        self._dirty = True
+
+    def sync_lora(self):
+        """Refresh W_eff when the LoRA parameters changed since the last merge (torch in-place
+        updates bump the bucket's version counter; raw-pointer updates call mark_dirty)."""
+        if self._dirty or self.param_bucket._version != self._merged_version:
+            self.refresh_lora()
+
+    def check_trainable(self, est):
+        if est.training and not getattr(est, "cvflow_ignore_lora_dropout", False):
+            for lm in self.lora_modules:
+                if isinstance(lm.lora_dropout, nn.Dropout) and lm.lora_dropout.p > 0:
+                    raise NotImplementedError(
+                        "lora_dropout=%g: the fused q/k/v path folds B A into the GEMM operand and therefore "
+                        "supports lora_dropout == 0 only (set estimator.cvflow_ignore_lora_dropout = True to "
+                        "train without LoRA dropout, or call estimator.eval())" % lm.lora_dropout.p)
 
     # -- calls -----------------------------------------------------------------------------------
     def _workspace(self, B, T, training):
@@ -355,6 +377,7 @@ class _EstimatorFn(torch.autograd.Function):
 
 def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
     ne = native_of(module)
+    ne.sync_lora()
     dev = ne.device
     x_, mu_, t_ = _prep(x, dev), _prep(mu, dev), _prep(t, dev)
     mask_ = _prep(mask, dev).reshape(mask.shape[0], -1)

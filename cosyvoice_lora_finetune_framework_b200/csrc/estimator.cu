@@ -499,7 +499,7 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
       if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
     }
-    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
+    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
     launches_ += 3;
     if (cfg.lora_r > 0) {
       CKL(launch_lora_wgrad(lora_table_dev_ + t.lora_idx, tmp.dqkv, t.x1, M, cfg.lora_r, grad_scale, grad_scale_dev_, tmp.wg_scratch,

@@ -68,8 +68,8 @@ int attn_plan_bytes();
 int attn_fwd_prepare(void* plan, const void* qkv, int B, int L, int bf16, char* err, int errlen);
 int attn_fwd_launch(const void* plan, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st);
 int attn_bwd_prepare(void* plan, const void* qkv, const void* dout, int B, int L, int bf16, char* err, int errlen);
-int attn_bwd_launch(const void* plan, const float* keymask, int iso_p, const void* o, const float* lse,
-                    float* delta, void* dqkv, cudaStream_t st);
+int attn_bwd_launch(const void* plan, const void* dout, const float* keymask, int iso_p, const void* o,
+                    const float* lse, float* delta, void* dqkv, cudaStream_t st);
 
 // ---- lora.cu -------------------------------------------------------------------------------
 struct LoraLayerPtrs {       // one q/k/v projection of one attention block
