@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the flow-LoRA hot path (BASELINE.json metric: LoRA flow train mel-frames/sec; Euler-ODE
+inference RTF reported alongside).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A "step" is one full optimiser step of the data-parallel LoRA fine-tune on one synthetic batch per
+rank: CFM interpolation -> estimator forward -> masked loss -> estimator backward -> (N>1) NCCL
+allreduce of the flat LoRA-gradient bucket -> fused clip + AdamW -> W_eff refresh. Workload =
+BASELINE.json configs[2] (CosyVoice-300M flow estimator, LoRA r=8 on attn1 q/k/v, batch 32 x 400
+frames per GPU, weak scaling). Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "flow_lora_train_mel_frames_per_sec"
+UNIT = "mel-frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cvflow", choices=["cvflow", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=400, help="padded mel frames per utterance")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": "configs[2]: CosyVoice-300M flow estimator (16 resnets, 64 transformer blocks), LoRA r=8 "
+                        "alpha=16 on attn1 to_q/to_k/to_v, batch %d x %d frames per GPU, ragged lengths in "
+                        "(0.6T, T]" % (a.batch, a.frames),
+            "global_batch": a.batch * world, "frames": a.frames, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (stashed activations ~5 GB) >> 126 MB L2, no explicit flush needed"}
+
+
+def make_batch(B, T, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    x1 = torch.randn(B, 80, T, generator=g)
+    mu = torch.randn(B, 80, T, generator=g)
+    spks = torch.randn(B, 80, generator=g)
+    cond = torch.zeros(B, 80, T)
+    lens = torch.randint(int(0.6 * T) + 1, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
+    t = dict(x1=x1, mu=mu, spks=spks, cond=cond, mask=mask)
+    return {k: v.to(device) for k, v in t.items()}, lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(a, device, dtype):
+    from cosyvoice_lora_finetune_framework_b200 import lora, modules, utils
+    from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
+    utils.set_all_random_seed(1234)
+    est = modules.ConditionalDecoder(in_channels=320, out_channels=80, channels=(256, 256), dropout=0.0,
+                                     attention_head_dim=64, n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn='gelu')
+    stats = lora.apply_lora_to_model(est, r=8, lora_alpha=16, lora_dropout=0.0,
+                                     target_modules=['to_q', 'to_k', 'to_v', 'to_out'])
+    est = est.to(device).train()
+    est.cvflow_dtype = dtype
+    cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, sigma_min=1e-6, t_scheduler='cosine',
+                         training_cfg_rate=0.2, inference_cfg_rate=0.7, estimator=est)
+    return cfm, est, stats
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1435.3), d.get("hbm_gbs", 6452.2), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_train_step_timer(B, T, steps, warmup):
+    """The reference algorithm (oracle port, plain PyTorch fp32 + autograd + AdamW) on the host cores."""
+    from oracle import flow_oracle as O
+    from cosyvoice_lora_finetune_framework_b200 import lora, modules, utils
+    torch.set_num_threads(os.cpu_count() or 1)
+    utils.set_all_random_seed(1234)
+    est = modules.ConditionalDecoder(in_channels=320, out_channels=80, channels=(256, 256), dropout=0.0,
+                                     attention_head_dim=64, n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn='gelu')
+    lora.apply_lora_to_model(est, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=['to_q', 'to_k', 'to_v'])
+    P = {k: v.detach().clone() for k, v in est.state_dict().items()}
+    train = [k for k in P if k.endswith(("lora_A", "lora_B"))]
+    for k in train:
+        P[k].requires_grad_(True)
+    scaling = {k[:-len(".lora_A")]: 2.0 for k in P if k.endswith(".lora_A")}
+    opt = torch.optim.AdamW([P[k] for k in train], lr=1e-4, weight_decay=0.01)
+    batch, _ = make_batch(B, T, 99, "cpu")
+    g = torch.Generator().manual_seed(7)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        t_rand = torch.rand(B, 1, 1, generator=g)
+        z = torch.randn(B, 80, T, generator=g)
+        cfg = torch.rand(B, generator=g)
+        loss, _, _ = O.cfm_compute_loss(P, batch["x1"], batch["mask"], batch["mu"], batch["spks"], batch["cond"], None,
+                                        t_rand, z, cfg, lora_scaling=scaling)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([P[k] for k in train], 1.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_s = 2
+    times = oracle_train_step_timer(B_s, a.frames, a.steps, a.warmup)
+    total = sum(times)
+    val = B_s * a.frames * len(times) / total
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = torch.get_num_threads()
+    sample = "each step = a bounded sample of the workload: %d x %d frames (fp32, fwd+bwd+clip+AdamW)" % (B_s, a.frames)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "reference algorithm restated in plain PyTorch fp32 (oracle/flow_oracle.py, pinned to the real "
+                   "reference by tests/golden) on all host cores; the reference itself is pure Python/PyTorch"}
+    print(json.dumps(out))
+
+
+def run_cvflow(a):
+    import torch.distributed as dist
+    from cosyvoice_lora_finetune_framework_b200 import _estimator as E
+    from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float16
+    B, T, K, W = a.batch, a.frames, a.steps, max(3, a.warmup)
+    cfm, est, stats = build_model(a, device, dtype)
+    trainer = FlowLoRATrainer(cfm, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0)
+    ne = trainer.ne
+    batch, lens = make_batch(B, T, 99 + rank, device)
+    torch.manual_seed(7 + rank)
+
+    def step(b):
+        return trainer.train_step(b["x1"], b["mask"], b["mu"], b["spks"], b["cond"])
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(W):
+        step(batch)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ne.launch_count()
+    ms = timed(lambda: step(batch), K)
+    launches = (ne.launch_count() - l0) + K * (1 + 3 + 2 + 1 + 1)   # + cfm_prep, loss(3), sumsq(2), adamw, merge
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * T * K / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    host = {k: v.cpu().pin_memory() for k, v in batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        loss = cfm.compute_loss(dev["x1"], dev["mask"], dev["mu"], dev["spks"], cond=dev["cond"])[0]
+        loss.backward()
+        trainer.micro = trainer.accumulate
+        trainer.optimizer_step()
+        return float(loss.item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    e2e_val = world * B * T * K / (ms_e2e / 1e3)
+
+    # ---- per-kernel-class device time (CUDA events on the launching stream) -----------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        L = E._lib()
+        L.cvflow_set_profile(ne.handle, 1)
+        for _ in range(2):
+            step(batch)
+        n = 5
+        msa, cnt, fl = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)()
+        L.cvflow_profile_read(ne.handle, msa, cnt, fl, n)
+        L.cvflow_set_profile(ne.handle, 0)
+        names = ["gemm_tc (tcgen05 implicit GEMM)", "attn_fwd (tcgen05)", "attn_bwd (tcgen05, 3 launches)", "-",
+                 "lora_wgrad"]
+        kernels = {names[i]: {"ms_per_step": msa[i] / 2, "launches_per_step": cnt[i] // 2,
+                              "tflops": (fl[i] / 2) / (msa[i] / 2 * 1e9) if msa[i] > 0 else None}
+                   for i in range(n) if cnt[i] > 0}
+        peak, _, how = peaks()
+        ach = (fl[0] / 2) / (msa[0] / 2 * 1e9)
+        roofline = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": how,
+                    "avg_launch_us": 1e3 * msa[0] / max(1, cnt[0]),
+                    "share_of_step": (msa[0] / 2) / (ms / K),
+                    "note": "algorithmic FLOPs = 2*M*N*K per launch with M = real (unpadded) rows, summed over the "
+                            "%d GEMM launches of a step; event-bracketed, so launch gaps are included" % (cnt[0] // 2)}
+
+    # ---- Euler-ODE inference (BASELINE configs[1]) -------------------------------------------------
+    inference = None
+    if rank == 0 and not a.no_inference:
+        est.eval()
+        Ti, P_, n_steps = 700, 200, 10
+        g = torch.Generator().manual_seed(5)
+        mu = torch.randn(1, 80, Ti, generator=g).to(device)
+        spk = torch.randn(1, 80, generator=g).to(device)
+        cond = torch.zeros(1, 80, Ti, device=device)
+        cond[:, :, :P_] = torch.randn(1, 80, P_, generator=g).to(device)
+        mask1 = torch.ones(1, 1, Ti, device=device)
+        run = lambda: cfm(mu=mu.clone(), mask=mask1, n_timesteps=n_steps, spks=spk, cond=cond, prompt_len=P_)
+        for _ in range(3):
+            run()
+        ms_inf = timed(run, 10) / 10 if world == 1 else None
+        if ms_inf:
+            audio_s = (Ti - P_) * 256 / 22050.0
+            inference = {"config": "configs[1]: 10 Euler steps + CFG, 500 target + 200 prompt frames, CUDA-graph replay",
+                         "ms_per_solve": ms_inf, "rtf": (ms_inf / 1e3) / audio_s,
+                         "target_frames_per_s": (Ti - P_) / (ms_inf / 1e3)}
+        est.train()
+
+    # ---- CPU baseline: the reference algorithm on this box's host cores ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        times = oracle_train_step_timer(2, 200, 3, 1)
+        best = min(times)
+        cpu = {"value": 2 * 200 / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "BASELINE configs[0]: 2 x 200 frames fp32 train step (fwd+bwd+clip+AdamW), best of 3"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, world), "clocks": clocks,
+               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "ms_per_step": ms_e2e / K},
+               "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+               "inference": inference, "valid_frames_per_step_rank0": int(lens.sum()),
+               "lora": {"replaced_layers": stats["replaced_layers"], "lora_params": stats["lora_params"]}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cvflow(args)

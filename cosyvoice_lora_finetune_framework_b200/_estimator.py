@@ -91,7 +91,8 @@ class NativeEstimator:
         self.loss_scale = LOSS_SCALE_DEFAULT if dtype == torch.float16 else 1.0
         self._dirty = False
         self._merged_version = -1
-        self._build()
+        with torch.inference_mode(False):   # buckets must be normal (version-tracked) tensors
+            self._build()
 
     def __del__(self):
         try:
@@ -276,8 +277,14 @@ class NativeEstimator:
     def refresh_lora(self):
         """Rebuild W_eff = W + (alpha/r) B A (call after every optimiser step)."""
         N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
-        self._merged_version = self.param_bucket._version
+        self._merged_version = self._version()
         self._dirty = False
+
+    def _version(self):
+        try:
+            return self.param_bucket._version
+        except RuntimeError:      # inference tensor
+            return -2
 
     def mark_dirty(self):
         self._dirty = True
@@ -285,7 +292,7 @@ class NativeEstimator:
     def sync_lora(self):
         """Refresh W_eff when the LoRA parameters changed since the last merge (torch in-place
         updates bump the bucket's version counter; raw-pointer updates call mark_dirty)."""
-        if self._dirty or self.param_bucket._version != self._merged_version:
+        if self._dirty or self._version() != self._merged_version:
             self.refresh_lora()
 
     def check_trainable(self, est):

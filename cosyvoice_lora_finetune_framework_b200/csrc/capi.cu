@@ -155,3 +155,16 @@ extern "C" CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, 
   RET_LAUNCH(launch_adamw(p, g, m, v, (long)n, sumsq, grad_unscale, max_norm, lr, beta1, beta2, eps, weight_decay, step,
                           found_inf, (cudaStream_t)stream), "cvflow_adamw_step");
 }
+
+extern "C" CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on) {
+  if (!h) return CVFLOW_ERR_ARG;
+  h->e->set_profile(on);
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* counts, double* flops, int32_t n) {
+  if (!h || !ms || !counts || !flops) return CVFLOW_ERR_ARG;
+  long c[16]; if (n > 16) n = 16;
+  int r = h->e->profile_read(ms, c, flops, n);
+  for (int i = 0; i < n; ++i) counts[i] = c[i];
+  return r ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}

@@ -61,6 +61,45 @@ void* Estimator::get(const std::string& name, int dtype, long numel) {
 bool Estimator::has(const std::string& name) const { return bound_.count(name) != 0; }
 
 // ------------------------------------------------------------------------------------------
+// optional per-launch profiling with CUDA events on the launching stream (bench.py roofline)
+// ------------------------------------------------------------------------------------------
+void Estimator::set_profile(int on) {
+  profile_ = on != 0;
+  prof_.clear();
+  ev_used_ = 0;
+}
+cudaEvent_t Estimator::ev_get() {
+  if (ev_used_ == ev_pool_.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ev_pool_.push_back(e);
+  }
+  return ev_pool_[ev_used_++];
+}
+void Estimator::prof_begin(int cls, double flops) {
+  if (!profile_ || dry_) return;
+  ProfRec r{cls, flops, ev_get(), ev_get()};
+  cudaEventRecord(r.a, stream_);
+  prof_.push_back(r);
+}
+void Estimator::prof_end() {
+  if (!profile_ || dry_) return;
+  cudaEventRecord(prof_.back().b, stream_);
+}
+int Estimator::profile_read(double* ms, long* counts, double* flops, int n) {
+  for (int i = 0; i < n; ++i) { ms[i] = 0; counts[i] = 0; flops[i] = 0; }
+  cudaStreamSynchronize(stream_);
+  for (auto& r : prof_) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return -1;
+    if (r.cls < n) { ms[r.cls] += t; counts[r.cls] += 1; flops[r.cls] += r.flops; }
+  }
+  prof_.clear();
+  ev_used_ = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // workspace + memoised launches
 // ------------------------------------------------------------------------------------------
 void* Estimator::alloc(long bytes) {
@@ -84,7 +123,9 @@ int Estimator::run_gemm(GemmArgs& a) {
   GemmParams& p = pl.gemms[gemm_idx_++];
   // per-call pointers at the API edge may move between calls
   p.out = a.out; p.rowmask = a.rowmask;
+  prof_begin(0, 2.0 * (double)a.nbatch * a.R * (double)a.n_valid * a.Ktot);
   int r = gemm_launch(p, stream_);
+  prof_end();
   if (r) { set_error("gemm launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return -1; }
   ++launches_;
   return 0;
@@ -193,7 +234,9 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       pl.attn.emplace_back(attn_plan_bytes());
       if (attn_fwd_prepare(pl.attn.back().data(), qkv, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
     }
+    prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
     CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), mask, iso_p, o, lse, stream_));
+    prof_end();
     ++launches_;
   }
   {
@@ -315,7 +358,13 @@ long Estimator::workspace_bytes(int B, int T, int training) {
   EstimatorIO io{};
   io.B = B; io.T = T; io.training = training;
   forward_impl(io);
-  if (training) backward_impl(nullptr, 1.f);
+  if (training) {
+    const EstimatorIO saved = last_io_;
+    last_io_ = io;
+    backward_impl(nullptr, 1.f);
+    last_io_ = saved;
+  }
+  stages_.clear();
   dry_ = false;
   return ws_off_ + (1 << 20);
 }
@@ -499,11 +548,15 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
       if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
     }
+    prof_begin(2, 10.0 * t.B * 8.0 * (double)t.L * t.L * 64);
     CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
+    prof_end();
     launches_ += 3;
     if (cfg.lora_r > 0) {
+      prof_begin(4, 0.0);
       CKL(launch_lora_wgrad(lora_table_dev_ + t.lora_idx, tmp.dqkv, t.x1, M, cfg.lora_r, grad_scale, grad_scale_dev_, tmp.wg_scratch,
                            cfg.bf16, stream_));
+      prof_end();
       launches_ += 2;
     }
   }

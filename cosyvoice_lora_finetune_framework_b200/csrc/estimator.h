@@ -67,6 +67,9 @@ class Estimator {
   int forward(const EstimatorIO& io, cudaStream_t st);
   int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
   long launches() const { return launches_; }
+  void set_profile(int on);
+  // class ids: 0 gemm, 1 attn_fwd, 2 attn_bwd, 3 norm/elementwise, 4 lora_wgrad
+  int profile_read(double* ms, long* counts, double* flops, int n);
   EstimatorConfig cfg;
 
  private:
@@ -106,6 +109,14 @@ class Estimator {
   FinalRec final_{};
   EstimatorIO last_io_{};
   const float* grad_scale_dev_ = nullptr;
+  struct ProfRec { int cls; double flops; cudaEvent_t a, b; };
+  bool profile_ = false;
+  std::vector<ProfRec> prof_;
+  std::vector<cudaEvent_t> ev_pool_;
+  size_t ev_used_ = 0;
+  cudaEvent_t ev_get();
+  void prof_begin(int cls, double flops);
+  void prof_end();
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
   void *cat0_ = nullptr, *cat1_ = nullptr;
 };

@@ -135,6 +135,11 @@ CVFLOW_API int cvflow_estimator_forward(cvflow_estimator* h, const cvflow_estima
 CVFLOW_API int cvflow_estimator_backward(cvflow_estimator* h, const void* dpred16, float grad_scale,
                                          const float* grad_scale_dev, void* stream);
 CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
+/* Measurement aid (bench.py roofline): when on, CUDA events bracket every tensor-core launch on
+ * the launching stream. cvflow_profile_read synchronises the stream and sums per class
+ * (0 gemm, 1 attention fwd, 2 attention bwd, 4 lora wgrad): milliseconds, launches, algorithmic FLOPs. */
+CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on);
+CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* counts, double* flops, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * CFM passes (reference flow_model.py:94-204)

@@ -31,10 +31,11 @@ def test_public_forward_draws_noise_like_reference():
     est, _, _ = build_estimator(1, 1)
     cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est.cuda().eval()).eval()
     mu = torch.randn(1, 80, 50, device="cuda")
+    spks = torch.randn(1, 80, device="cuda")
     torch.manual_seed(3)
     z = torch.randn_like(mu)
     torch.manual_seed(3)
-    mel, cache = cfm(mu=mu.clone(), mask=torch.ones(1, 1, 50, device="cuda"), n_timesteps=4, spks=torch.randn(1, 80, device="cuda"),
+    mel, cache = cfm(mu=mu.clone(), mask=torch.ones(1, 1, 50, device="cuda"), n_timesteps=4, spks=spks,
                      cond=torch.zeros(1, 80, 50, device="cuda"), prompt_len=0, cache=None)
     assert torch.equal(cache[:, :, :, 0], z[:, :, -34:])
     assert mel.shape == (1, 80, 50) and torch.isfinite(mel).all()
