@@ -344,6 +344,14 @@ class NativeEstimator:
             C.c_void_p(grad_scale_dev.data_ptr()) if grad_scale_dev is not None else None, _stream()),
             "cvflow_estimator_backward")
 
+    def dpred_buffer(self, B, T):
+        """Persistent dL/dpred buffer (its address is baked into a cached TMA descriptor)."""
+        buf = getattr(self, "_dpred", None)
+        if buf is None or buf.shape[0] != B or buf.shape[1] != T:
+            buf = torch.empty(B, T, 128, device=self.device, dtype=self.dtype)
+            self._dpred = buf
+        return buf
+
     def launch_count(self):
         return int(self.L.cvflow_launch_count(self.handle))
 

@@ -121,6 +121,11 @@ int Estimator::run_gemm(GemmArgs& a) {
     pl.gemms.push_back(p);
   }
   GemmParams& p = pl.gemms[gemm_idx_++];
+  if (p.src_A[0] != a.A[0] || p.src_A[1] != a.A[1] || p.src_W != a.W) {
+    // an operand owned by the caller moved (e.g. dL/dpred of this step): re-encode its tensor map
+    a.bf16 = cfg.bf16;
+    if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return -1;
+  }
   // per-call pointers at the API edge may move between calls
   p.out = a.out; p.rowmask = a.rowmask;
   prof_begin(0, 2.0 * (double)a.nbatch * a.R * (double)a.n_valid * a.Ktot);

@@ -303,6 +303,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   if (a.n_valid > a.N && !a.transposed_out) GEMM_FAIL("gemm: n_valid > N");
   p->nseg = a.nseg;
   p->nkb_total = nkb;
+  p->src_A[0] = a.A[0]; p->src_A[1] = a.A[1]; p->src_W = a.W;
   p->bf16 = a.bf16;
   p->R = a.R; p->rmul = a.rmul; p->roff = a.roff; p->out_rows = a.out_rows; p->nbatch = a.nbatch;
   p->tiles_per_batch = (a.R + BM - 1) / BM;

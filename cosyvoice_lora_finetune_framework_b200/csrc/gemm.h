@@ -72,6 +72,7 @@ struct alignas(64) GemmParams {
   void* out; int out_f32; long ldc; int col_off; int n_valid; int transposed_out;
   float alpha; const float* bias; int act; void* aux_out; const void* mul_src; long ld_aux;
   const float* rowmask; const float* resid; long ldr;
+  const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
   int block_n;   // 128 or 256
   int grid_x, grid_y;
 };

@@ -40,7 +40,7 @@ class _CFMLossFn(torch.autograd.Function):
         pred = ne.forward(y, mask, mu, t, spks, cond, keep=keep, iso_len=iso_len, training=True)
         scal = torch.zeros(4, device=x1.device, dtype=torch.float32)
         partials = torch.empty(B * ((T + 31) // 32), device=x1.device, dtype=torch.float32)
-        dpred = torch.empty(B, T, 128, device=x1.device, dtype=ne.dtype)
+        dpred = ne.dpred_buffer(B, T)
         N.check(L.cvflow_cfm_loss(pred.data_ptr(), x1.data_ptr(), z.data_ptr(), w.data_ptr(), mask.data_ptr(),
                                   scal.data_ptr(), partials.data_ptr(), dpred.data_ptr(), B, T, sigma_min,
                                   ne.loss_scale, N.dtype_code(ne.dtype), st), "cvflow_cfm_loss")
