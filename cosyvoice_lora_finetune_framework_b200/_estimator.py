@@ -211,6 +211,11 @@ class NativeEstimator:
                             gb = self._grad_view(lm.lora_B)
                             self._bind(Q + ".lora_%s.A.grad" % short, ga)
                             self._bind(Q + ".lora_%s.B.grad" % short, gb)
+                    if r > 0 and all(_lin(getattr(tb.attn1, pn))[2] is not None for pn in ("to_q", "to_k", "to_v")):
+                        self._bind(Q + ".acat16", torch.zeros(64, 256, device=self.device, dtype=self.dtype))
+                        self._bind(Q + ".bblk16", torch.zeros(64, 1536, device=self.device, dtype=self.dtype))
+                    elif r > 0:
+                        raise NotImplementedError("LoRA must wrap to_q, to_k and to_v of every attention block")
                     self._bind(Q + ".weff", torch.empty(1536, 256, device=self.device, dtype=self.dtype))
                     self._bind(Q + ".weff_t", torch.empty(256, 1536, device=self.device, dtype=self.dtype))
                     wo, bo, _ = _lin(tb.attn1.to_out[0])

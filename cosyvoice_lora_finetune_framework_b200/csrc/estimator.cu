@@ -324,6 +324,9 @@ int Estimator::lora_refresh(cudaStream_t st) {
       }
       b.weff = get(Q + ".weff", cfg.bf16, 1536L * 256);
       b.weff_t = get(Q + ".weff_t", cfg.bf16, 1536L * 256);
+      const bool lor = cfg.lora_r > 0 && has(Q + ".acat16");
+      b.acat16 = lor ? get(Q + ".acat16", cfg.bf16, 64L * 256) : nullptr;
+      b.bblk16 = lor ? get(Q + ".bblk16", cfg.bf16, 64L * 1536) : nullptr;
     };
     for_each_tb(fill);
     if (missing_) return -1;
@@ -390,7 +393,7 @@ int Estimator::forward(const EstimatorIO& io, cudaStream_t st) {
 
 int Estimator::forward_impl(const EstimatorIO& io) {
   const int B = io.B, T = io.T, T2 = (T + 1) / 2;
-  gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0;
+  gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0; wg_idx_ = 0;
   stages_.clear();
   const int nres = n_resnets();
   float* mask1 = (float*)alloc((long)B * T * 4);
@@ -557,10 +560,25 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
     prof_end();
     launches_ += 3;
-    if (cfg.lora_r > 0) {
-      prof_begin(4, 0.0);
-      CKL(launch_lora_wgrad(lora_table_dev_ + t.lora_idx, tmp.dqkv, t.x1, M, cfg.lora_r, grad_scale, grad_scale_dev_, tmp.wg_scratch,
-                           cfg.bf16, stream_));
+  }
+  if (cfg.lora_r > 0) {
+    {  // u = x1 A_cat^T, v = dqkv B_blk^T  ([M][64] each, columns p*r+j)
+      GemmArgs g = linear_args(t.x1, M, 256, get(Q + ".acat16", cfg.bf16, 64L * 256), 64, tmp.u16, 0);
+      CK(run_gemm(g));
+      GemmArgs g2 = linear_args(tmp.dqkv, M, 1536, get(Q + ".bblk16", cfg.bf16, 64L * 1536), 64, tmp.v16, 0);
+      CK(run_gemm(g2));
+    }
+    if (!dry_) {
+      Plan& pl = *plan_;
+      if ((size_t)wg_idx_ >= pl.wgrads.size()) {
+        pl.wgrads.emplace_back(lora_wgrad_plan_bytes());
+        if (lora_wgrad_prepare(pl.wgrads.back().data(), tmp.dqkv, t.x1, tmp.u16, tmp.v16, M, cfg.lora_r, tmp.wg_scratch,
+                               cfg.bf16, error_buf(), error_buf_len()))
+          return -1;
+      }
+      prof_begin(4, 2.0 * M * 64.0 * (1536 + 256));
+      CKL(lora_wgrad_launch(pl.wgrads[wg_idx_++].data(), lora_table_dev_ + t.lora_idx, grad_scale, grad_scale_dev_,
+                            stream_));
       prof_end();
       launches_ += 2;
     }
@@ -630,6 +648,8 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   tmp.dc = alloc(MT * 256 * 2);
   tmp.da = alloc(MT * 256 * 2);
   tmp.wg_scratch = (float*)alloc(lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1) * 4);
+  tmp.u16 = alloc(MT * 64 * 2);
+  tmp.v16 = alloc(MT * 64 * 2);
   float* dh32 = (float*)alloc(MT * 256 * 4);
   void* dh16 = alloc(MT * 256 * 2);
   void* g16a = alloc(MT * 256 * 2);

@@ -43,7 +43,7 @@ struct TBRec {
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
-struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; };
+struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; void *u16, *v16; };
 
 struct PlanKey {
   int B, T, training; uintptr_t ws;
@@ -54,7 +54,7 @@ struct PlanKey {
     return ws < o.ws;
   }
 };
-struct Plan { std::vector<GemmParams> gemms; std::vector<std::vector<uint8_t>> attn; };
+struct Plan { std::vector<GemmParams> gemms; std::vector<std::vector<uint8_t>> attn; std::vector<std::vector<uint8_t>> wgrads; };
 
 class Estimator {
  public:
@@ -100,7 +100,7 @@ class Estimator {
   void* ws_ = nullptr;
   long ws_bytes_ = 0, ws_off_ = 0, fwd_ws_end_ = 0;
   bool dry_ = false, missing_ = false, oom_ = false, have_fwd_ = false, lora_table_ready_ = false;
-  int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0;
+  int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0, wg_idx_ = 0;
   long launches_ = 0;
   cudaStream_t stream_ = nullptr;
   LoraBlockPtrs* lora_table_dev_ = nullptr;

@@ -84,13 +84,19 @@ struct LoraBlockPtrs {       // one attention block: q, k, v + the merged 16-bit
   LoraLayerPtrs p[3];
   void* weff;                // [1536][256]
   void* weff_t;              // [256][1536]
+  void* acat16;              // [64][256]  rows p*r+j = A_p[j]      (nullable)
+  void* bblk16;              // [64][1536] rows p*r+j, cols p*512+n = B_p[n][j]
 };
 // W_eff = W + s * B A for every block in one launch; writes both layouts.
 int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, cudaStream_t st);
-// dA, dB of the three projections of one block from dqkv [M][1536], xn [M][256].
-int launch_lora_wgrad(const LoraBlockPtrs* block_dev, const void* dqkv, const void* xn, long M, int r,
-                      float grad_scale, const float* grad_scale_dev, float* scratch, int bf16, cudaStream_t st);
+// dA, dB of the three projections of one block: tcgen05 reductions over the token axis of
+// dY^T u and x^T v (u = x A_cat^T, v = dY B_blk^T are produced by two engine GEMMs, [M][64] each).
+int lora_wgrad_plan_bytes();
 long lora_wgrad_scratch_floats(long M, int r);
+int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, const void* v16, long M, int r,
+                       float* scratch, int bf16, char* err, int errlen);
+int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float grad_scale, const float* grad_scale_dev,
+                      cudaStream_t st);
 
 // ---- optim.cu ------------------------------------------------------------------------------
 // Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).

@@ -9,6 +9,8 @@
 // deterministic two-stage reduction (no atomics).
 #include "kernels.h"
 #include "common.cuh"
+#include "gemm.h"
+#include <string.h>
 
 namespace cvflow {
 
@@ -27,6 +29,18 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __
   for (int j = 0; j < 16; ++j) a[j] = (lp.A && j < r) ? lp.A[j * 256 + k] : 0.f;
   uint16_t* weff = reinterpret_cast<uint16_t*>(blk.weff);
   uint16_t* weff_t = reinterpret_cast<uint16_t*>(blk.weff_t);
+  // 16-bit factor images for the tensor-core wgrad: Acat16[p*r+j][k] = A_p[j][k],
+  // Bblk16[p*r+j][p*512+n] = B_p[n][j] (block diagonal; the zero pattern is written once at bind time)
+  if (lp.A && blk.acat16) {
+    uint16_t* acat = reinterpret_cast<uint16_t*>(blk.acat16);
+    uint16_t* bblk = reinterpret_cast<uint16_t*>(blk.bblk16);
+    if (blockIdx.x == 0)
+      for (int j = 0; j < r; ++j) acat[(p * r + j) * 256 + k] = f32_to_h16(a[j], bf);
+    if (k < 16 * r) {
+      const int i = k / r, j = k - i * r;
+      bblk[(long)(p * r + j) * 1536 + p * 512 + n0 + i] = f32_to_h16(lp.Bm[(n0 + i) * r + j], bf);
+    }
+  }
   for (int i = 0; i < 16; ++i) {
     const int n = n0 + i;
     float w = lp.W[n * 256 + k];
@@ -55,151 +69,196 @@ int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int b
 }
 
 // ------------------------------------------------------------------------------------------
-// wgrad. Stage 1: CTA c owns tokens [c*chunk, (c+1)*chunk), walks them 32 at a time, keeps
-// dA[3r][256] (thread = k) and dB[1536][r] (thread = n, n+256, ...) partial sums in registers
-// and writes them to scratch[c]. Stage 2 sums the partials in a fixed order.
+// wgrad on tcgen05. With u = x A_cat^T and v = dY B_blk^T (two small GEMMs of the implicit-GEMM
+// engine, 64 output columns each), the LoRA gradients are reductions over the token axis:
+//     dB_all[1536][*] = dY^T u        dA_all^T[256][*] = x^T v
+// Both operands of these contractions are token-major tensors whose contraction index is the row,
+// i.e. MN-major UMMA operands: a TMA box {64 channels, 64 tokens} (128B swizzle) is consumed as
+// is, with a_major = b_major = MN. CTA (s, t) reduces token split s for output row tile t
+// (t < 12: 128 channels of dY, t >= 12: 128 channels of x) into a fp32 partial; a small kernel
+// sums the splits in fixed order (deterministic) and accumulates into the fp32 gradient bucket.
 // ------------------------------------------------------------------------------------------
-static constexpr int kWgTok = 32;
-template <int R>
-__global__ void __launch_bounds__(256) lora_wgrad_kernel(const LoraBlockPtrs* __restrict__ blkp,
-                                                         const uint16_t* __restrict__ dqkv, const uint16_t* __restrict__ xn,
-                                                         long M, long chunk, float* __restrict__ scratch, int bf) {
-  extern __shared__ float sm[];
-  float* sx = sm;                       // [32][257]  xn tile
-  float* sdy = sx + kWgTok * 257;       // [32][513]  dY_p tile
-  float* sA = sdy + kWgTok * 513;       // [R][257]
-  float* sB = sA + R * 257;             // [512][R]
-  float* su = sB + 512 * R;             // [32][R]
-  float* sv = su + kWgTok * R;          // [32][R]
-  const LoraBlockPtrs& blk = *blkp;
-  const long m_begin = (long)blockIdx.x * chunk, m_end = min(M, m_begin + chunk);
-  const int tid = threadIdx.x;
-  float* out = scratch + (long)blockIdx.x * (3 * R * 256 + 1536 * R);
-  for (int p = 0; p < 3; ++p) {
-    const LoraLayerPtrs lp = blk.p[p];
-    float accA[R];
-    float accB[2][R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) { accA[j] = 0.f; accB[0][j] = 0.f; accB[1][j] = 0.f; }
-    if (lp.A) {
-      __syncthreads();
-      for (int i = tid; i < R * 256; i += 256) sA[(i >> 8) * 257 + (i & 255)] = lp.A[i];
-      for (int i = tid; i < 512 * R; i += 256) sB[i] = lp.Bm[i];
-      for (long m0 = m_begin; m0 < m_end; m0 += kWgTok) {
-        const int nt = (int)min((long)kWgTok, m_end - m0);
-        __syncthreads();
-        for (int i = tid; i < kWgTok * 32; i += 256) {   // xn: 32 rows x 32 uint4
-          const int row = i >> 5, c8 = (i & 31) * 8;
-          float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (row < nt) {
-            const uint4 u = *reinterpret_cast<const uint4*>(xn + (m0 + row) * 256 + c8);
-            unpack2_h16(u.x, bf, f[0], f[1]); unpack2_h16(u.y, bf, f[2], f[3]);
-            unpack2_h16(u.z, bf, f[4], f[5]); unpack2_h16(u.w, bf, f[6], f[7]);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sx[row * 257 + c8 + e] = f[e];
-        }
-        for (int i = tid; i < kWgTok * 64; i += 256) {   // dY_p: 32 rows x 64 uint4
-          const int row = i >> 6, c8 = (i & 63) * 8;
-          float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (row < nt) {
-            const uint4 u = *reinterpret_cast<const uint4*>(dqkv + (m0 + row) * 1536 + p * 512 + c8);
-            unpack2_h16(u.x, bf, f[0], f[1]); unpack2_h16(u.y, bf, f[2], f[3]);
-            unpack2_h16(u.z, bf, f[4], f[5]); unpack2_h16(u.w, bf, f[6], f[7]);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sdy[row * 513 + c8 + e] = f[e];
-        }
-        __syncthreads();
-        // u[m][j] = sum_k x[m][k] A[j][k];  v[m][j] = sum_n dy[m][n] B[n][j]
-        for (int i = tid; i < kWgTok * R; i += 256) {
-          const int m = i / R, j = i - m * R;
-          float au = 0.f, av = 0.f;
-          for (int k = 0; k < 256; ++k) au += sx[m * 257 + k] * sA[j * 257 + k];
-          for (int n = 0; n < 512; ++n) av += sdy[m * 513 + n] * sB[n * R + j];
-          su[i] = au;
-          sv[i] = av;
-        }
-        __syncthreads();
-        for (int m = 0; m < kWgTok; ++m) {
-          const float x = sx[m * 257 + tid];
-          const float d0 = sdy[m * 513 + tid], d1 = sdy[m * 513 + 256 + tid];
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            accA[j] += sv[m * R + j] * x;
-            accB[0][j] += d0 * su[m * R + j];
-            accB[1][j] += d1 * su[m * R + j];
-          }
-        }
+struct alignas(64) WgradParams {
+  CUtensorMap tmA[2];   // problem 0: dY [M][1536], problem 1: x [M][256]   (box {64, 64})
+  CUtensorMap tmW[2];   // problem 0: u [M][64],    problem 1: v [M][64]
+  long M;
+  int rows_per_split, S, r, bf16;
+  float* part_b;        // [S][1536][r]
+  float* part_a;        // [S][256][64]
+};
+static constexpr int kWgStages = 4;
+static constexpr int kWgStageBytes = 16384 + 8192;
+static constexpr int kWgSmem = kWgStages * kWgStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 2) lora_wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar = base + kWgStages * kWgStageBytes;
+  auto full_bar = [&](int s) { return bar + 8u * s; };
+  auto empty_bar = [&](int s) { return bar + 8u * (kWgStages + s); };
+  const uint32_t done_bar = bar + 8u * (2 * kWgStages);
+  const uint32_t tmem_slot = bar + 8u * (2 * kWgStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, tile = blockIdx.y;
+  const int prob = tile < 12 ? 0 : 1;
+  const int mt = prob == 0 ? tile : tile - 12;
+  const long tok_begin = (long)split * p.rows_per_split;
+  long tok_end = tok_begin + p.rows_per_split;
+  if (tok_end > p.M) tok_end = p.M;
+  const int nkb = tok_end > tok_begin ? (int)((tok_end - tok_begin + 63) / 64) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), kWgStageBytes);
+        const uint32_t sa = base + stage * kWgStageBytes;
+        const int tok = (int)(tok_begin + (long)kb * 64);
+        tma_load_3d(sa, &p.tmA[prob], full_bar(stage), mt * 128, tok, 0);
+        tma_load_3d(sa + 8192, &p.tmA[prob], full_bar(stage), mt * 128 + 64, tok, 0);
+        tma_load_3d(sa + 16384, &p.tmW[prob], full_bar(stage), 0, tok, 0);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
     }
-    float* oa = out + p * R * 256;
-    float* ob = out + 3 * R * 256 + p * 512 * R;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.bf16, 128, 64, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * kWgStageBytes;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      oa[j * 256 + tid] = accA[j];
-      ob[tid * R + j] = accB[0][j];
-      ob[(256 + tid) * R + j] = accB[1][j];
+        for (int k = 0; k < 4; ++k) {   // 16 tokens per MMA = 16 rows of 128 bytes
+          const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 2048, 8192);
+          const uint64_t db = umma_desc_mnmajor_sw128(sa + 16384 + k * 2048, 8192);
+          umma_f16_ss(tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;   // channel within the tile
+    if (nkb > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        __syncwarp();
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (prob == 0) {
+        const int pj = mt >> 2;                      // projection of this 128-row tile
+        float* dst = p.part_b + ((long)split * 1536 + mt * 128 + row) * p.r;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c * 32 + j - pj * p.r;
+          if (col >= 0 && col < p.r) dst[col] = __uint_as_float(v[j]);
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(p.part_a + ((long)split * 256 + mt * 128 + row) * 64 + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 64); }
 }
 
-template <int R>
-__global__ void __launch_bounds__(256) lora_wgrad_reduce_kernel(const LoraBlockPtrs* __restrict__ blkp,
-                                                                const float* __restrict__ scratch, int nchunks,
-                                                                float grad_scale, const float* __restrict__ gs_dev) {
-  const int per = 3 * R * 256 + 1536 * R;
+__global__ void __launch_bounds__(256) lora_wgrad_final_kernel(const LoraBlockPtrs* __restrict__ blkp,
+                                                               const float* __restrict__ part_b, const float* __restrict__ part_a,
+                                                               int S, int r, float grad_scale, const float* __restrict__ gs_dev) {
+  const int nb = 1536 * r, na = 3 * r * 256;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= per) return;
-  float s = 0.f;
-  for (int c = 0; c < nchunks; ++c) s += scratch[(long)c * per + i];
+  if (i >= nb + na) return;
   if (gs_dev) grad_scale *= gs_dev[0];
   const LoraBlockPtrs& blk = *blkp;
-  if (i < 3 * R * 256) {
-    const int p = i / (R * 256), off = i - p * R * 256;
-    if (blk.p[p].dA) blk.p[p].dA[off] += s * grad_scale * blk.p[p].scaling;
+  float s = 0.f;
+  if (i < nb) {
+    for (int sp = 0; sp < S; ++sp) s += part_b[(long)sp * nb + i];
+    const int n_all = i / r, j = i - n_all * r;
+    const int pj = n_all >> 9, n = n_all & 511;
+    if (blk.p[pj].dB) blk.p[pj].dB[n * r + j] += s * grad_scale * blk.p[pj].scaling;
   } else {
-    const int k = i - 3 * R * 256;
-    const int p = k / (512 * R), off = k - p * 512 * R;
-    if (blk.p[p].dB) blk.p[p].dB[off] += s * grad_scale * blk.p[p].scaling;
+    const int k2 = i - nb;                 // (p, j, k)
+    const int pj = k2 / (r * 256), rem = k2 - pj * r * 256;
+    const int j = rem >> 8, k = rem & 255;
+    for (int sp = 0; sp < S; ++sp) s += part_a[((long)sp * 256 + k) * 64 + pj * r + j];
+    if (blk.p[pj].dA) blk.p[pj].dA[j * 256 + k] += s * grad_scale * blk.p[pj].scaling;
   }
 }
 
-static int wgrad_chunks(long M) {
-  long c = (M + 255) / 256;
-  if (c > 148) c = 148;
-  if (c < 1) c = 1;
-  return (int)c;
+static int wgrad_splits(long M) {
+  long s = (M + 767) / 768;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return (int)s;
 }
-long lora_wgrad_scratch_floats(long M, int r) { return (long)wgrad_chunks(M) * (3L * r * 256 + 1536L * r); }
+long lora_wgrad_scratch_floats(long M, int r) {
+  const long S = wgrad_splits(M);
+  return S * (1536L * r + 256L * 64) + 64;
+}
+int lora_wgrad_plan_bytes() { return (int)sizeof(WgradParams); }
 
-template <int R>
-static int wgrad_launch(const LoraBlockPtrs* block_dev, const void* dqkv, const void* xn, long M, float grad_scale,
-                        const float* gs_dev, float* scratch, int bf16, cudaStream_t st) {
-  const int nch = wgrad_chunks(M);
-  long chunk = (M + nch - 1) / nch;
-  chunk = (chunk + kWgTok - 1) / kWgTok * kWgTok;
-  const size_t smem = (size_t)(kWgTok * 257 + kWgTok * 513 + R * 257 + 512 * R + 2 * kWgTok * R) * sizeof(float);
+int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, const void* v16, long M, int r,
+                       float* scratch, int bf16, char* err, int errlen) {
+  WgradParams* p = reinterpret_cast<WgradParams*>(plan);
+  memset(p, 0, sizeof(*p));
+  p->M = M; p->r = r; p->bf16 = bf16;
+  p->S = wgrad_splits(M);
+  long rows = (M + p->S - 1) / p->S;
+  p->rows_per_split = (int)((rows + 63) / 64 * 64);
+  p->part_b = scratch;
+  p->part_a = scratch + (long)p->S * 1536 * r;
+  int rc = 0;
+  rc |= tma_encode_3d(&p->tmA[0], dqkv, bf16, 1536, (uint64_t)M, 1, 1536 * 2, (uint64_t)M * 1536 * 2, 64, 64, 1);
+  rc |= tma_encode_3d(&p->tmA[1], xn, bf16, 256, (uint64_t)M, 1, 256 * 2, (uint64_t)M * 256 * 2, 64, 64, 1);
+  rc |= tma_encode_3d(&p->tmW[0], u16, bf16, 64, (uint64_t)M, 1, 64 * 2, (uint64_t)M * 64 * 2, 64, 64, 1);
+  rc |= tma_encode_3d(&p->tmW[1], v16, bf16, 64, (uint64_t)M, 1, 64 * 2, (uint64_t)M * 64 * 2, 64, 64, 1);
+  if (rc) { if (err) snprintf(err, errlen, "lora wgrad: cuTensorMapEncodeTiled failed"); return -1; }
+  return 0;
+}
+
+int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float grad_scale, const float* gs_dev,
+                      cudaStream_t st) {
+  const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(lora_wgrad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(lora_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
     attr_done = true;
   }
-  lora_wgrad_kernel<R><<<nch, 256, smem, st>>>(block_dev, reinterpret_cast<const uint16_t*>(dqkv),
-                                               reinterpret_cast<const uint16_t*>(xn), M, chunk, scratch, bf16);
-  const int per = 3 * R * 256 + 1536 * R;
-  lora_wgrad_reduce_kernel<R><<<(per + 255) / 256, 256, 0, st>>>(block_dev, scratch, nch, grad_scale, gs_dev);
+  lora_wgrad_tc_kernel<<<dim3(p->S, 14), 192, kWgSmem, st>>>(*p);
+  const int total = 1536 * p->r + 3 * p->r * 256;
+  lora_wgrad_final_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_dev, p->part_b, p->part_a, p->S, p->r, grad_scale,
+                                                              gs_dev);
   LAUNCH_RET();
-}
-
-int launch_lora_wgrad(const LoraBlockPtrs* block_dev, const void* dqkv, const void* xn, long M, int r,
-                      float grad_scale, const float* gs_dev, float* scratch, int bf16, cudaStream_t st) {
-  switch (r) {
-    case 4: return wgrad_launch<4>(block_dev, dqkv, xn, M, grad_scale, gs_dev, scratch, bf16, st);
-    case 8: return wgrad_launch<8>(block_dev, dqkv, xn, M, grad_scale, gs_dev, scratch, bf16, st);
-    case 16: return wgrad_launch<16>(block_dev, dqkv, xn, M, grad_scale, gs_dev, scratch, bf16, st);
-    default: return -1;
-  }
 }
 
 }  // namespace cvflow
