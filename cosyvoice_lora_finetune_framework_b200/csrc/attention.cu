@@ -6,8 +6,8 @@
 // materialised: the key mask comes from the [B,L] float mask and the isolation boundary from one
 // integer.
 //
-// Layout of one CTA (forward and dQ kernels): 128 query rows of one (batch, head); thread r of
-// warps 0-3 owns query row r (= TMEM lane r), warp 4 drives TMA and issues every tcgen05.mma.
+// Layout of one CTA (forward and dQ kernels): 128 query rows of one (batch, head); sixteen softmax
+// warps (warp w: TMEM lane quadrant w & 3 = 32 query rows, column group w >> 2), one MMA/TMA warp.
 //   S  = Q K^T   : A = Q [128 x 64] K-major, B = K block [128 keys x 64] K-major  -> TMEM cols [0,128)
 //   P  = softmax : tcgen05.ld row -> registers -> 16-bit, written to smem in the K-major
 //                  128B-swizzled operand layout (row = query, K = key)
@@ -32,11 +32,13 @@ static constexpr int kAQ = 128;   // query rows per CTA
 static constexpr int kAK = 128;   // keys per block
 static constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
 
-// named barrier among the 128 softmax threads only
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier among the 512 softmax threads only
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// forward. 16 softmax warps: warp w owns TMEM lane quadrant w & 3 (query rows) and column group
+// w >> 2 (32 of the 128 keys of a block / 16 of the 64 output columns), so every scheduler has
+// four warps to interleave; warp 16 drives TMA and issues the MMAs.
 // ------------------------------------------------------------------------------------------
 struct AttnFwdSmem {
   static constexpr int kQ = 0;
@@ -44,19 +46,22 @@ struct AttnFwdSmem {
   static constexpr int kK1 = 32768;
   static constexpr int kV = 49152;
   static constexpr int kP = 65536;          // 2 x 16 KB
-  static constexpr int kBar = 98304;        // barriers + scratch
-  static constexpr int kBytes = kBar + 256 + 1024;
+  static constexpr int kBar = 98304;        // barriers, then row-max / row-sum exchange
+  static constexpr int kMx = kBar + 128;    // float [2][128][4]
+  static constexpr int kBytes = kMx + 4096 + 1024;
 };
+static constexpr int kFwdThreads = 544;
 
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
                 uint16_t* __restrict__ o_out, float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar = base + AttnFwdSmem::kBar;
   const uint32_t bar_q = bar, bar_k0 = bar + 8, bar_k1 = bar + 16, bar_v = bar + 24, bar_s = bar + 32,
                  bar_p = bar + 40, bar_o = bar + 48, tmem_slot = bar + 56;
-  uint32_t* kvalid = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + AttnFwdSmem::kBar + 64);
+  float* mx = reinterpret_cast<float*>(gbase + AttnFwdSmem::kMx);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
@@ -65,11 +70,11 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_k0, 1); mbar_init(bar_k1, 1); mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 512); mbar_init(bar_o, 1);
     fence_barrier_init();
     tma_prefetch_desc(&plan.tm_qkv);
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -77,7 +82,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
 
-  if (warp == 4) {
+  if (warp == 16) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
       const uint32_t idesc_o = umma_idesc_f16(bf, 128, 64, 0, 1);
@@ -123,120 +128,99 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
       }
     }
   } else {
-    const int r = threadIdx.x;  // query row within the tile == TMEM lane
+    const int qd = warp & 3, g = warp >> 2;
+    const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
     const int qi = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float o[16];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    for (int j = 0; j < 16; ++j) o[j] = 0.f;
     const bool q_side = qi < iso_p;
-    uint8_t* sP = smem_raw + (base - smem_u32(smem_raw)) + AttnFwdSmem::kP;
+    uint8_t* sP = gbase + AttnFwdSmem::kP;
 
     for (int i = 0; i < nkb; ++i) {
       const int k0 = i * kAK;
-      {
-        const int key = k0 + r;
+      uint32_t vw;
+      {  // validity bits of this warp's 32 keys
+        const int key = k0 + g * 32 + lane;
         const bool ok = key < L && keymask[(long)b * L + key] != 0.f;
-        const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) kvalid[(i & 1) * 4 + warp] = word;
-      }
-      softmax_bar_sync();
-      uint32_t vw[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) vw[c] = kvalid[(i & 1) * 4 + c];
-      if (iso_p > 0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // keys [k0+32c, k0+32c+32): keep those on the query's side of the boundary
-          const int lo = k0 + 32 * c;
-          uint32_t below;  // bit j set iff key lo+j < iso_p
-          const int nb = iso_p - lo;
-          below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          vw[c] &= q_side ? below : ~below;
+        vw = __ballot_sync(0xffffffffu, ok);
+        if (iso_p > 0) {
+          const int nb = iso_p - (k0 + g * 32);
+          const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
+          vw &= q_side ? below : ~below;
         }
       }
       mbar_wait(bar_s, (uint32_t)(i & 1));
       tc_fence_after();
-      // pass 1: block row max
-      float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(tmem_S + lane_addr + g * 32, v);
+      tmem_ld_wait();
+      float m_loc = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if ((vw[c] >> j) & 1u) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-      }
-      m_blk *= kScaleLog2;  // scale > 0, max commutes
+      for (int j = 0; j < 32; ++j)
+        if ((vw >> j) & 1u) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
+      float* mrow = mx + ((i & 1) * 128 + r) * 4;
+      mrow[g] = m_loc;
+      softmax_bar_sync();
+      const float4 m4 = *reinterpret_cast<const float4*>(mrow);
+      const float m_blk = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2;
       const float m_new = fmaxf(m_run, m_blk);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = exp2f(m_run - m_use);
+      float p[32];
       float rowsum = 0.f;
-      // pass 2: probabilities -> smem (16-bit, swizzled K-major operand)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        float p[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pv = ((vw[c] >> j) & 1u) ? exp2f(__uint_as_float(v[j]) * kScaleLog2 - m_use) : 0.f;
-          p[j] = pv;
-          rowsum += pv;
-        }
-        uint8_t* chunk = sP + (c >> 1) * 16384 + r * 128;
+      for (int j = 0; j < 32; ++j) {
+        const float pv = ((vw >> j) & 1u) ? exp2f(__uint_as_float(v[j]) * kScaleLog2 - m_use) : 0.f;
+        p[j] = pv;
+        rowsum += pv;
+      }
+      {
+        uint8_t* chunk = sP + (g >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack2_h16(p[8 * u + 0], p[8 * u + 1], bf);
-          w.y = pack2_h16(p[8 * u + 2], p[8 * u + 3], bf);
-          w.z = pack2_h16(p[8 * u + 4], p[8 * u + 5], bf);
-          w.w = pack2_h16(p[8 * u + 6], p[8 * u + 7], bf);
-          const int unit = (c & 1) * 4 + u;
-          *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = w;
+          const int unit = (g & 1) * 4 + u;
+          *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = pack8_h16(p + 8 * u, bf);
         }
       }
-      l_run = l_run * alpha + rowsum;
+      l_run = l_run * alpha + rowsum;   // partial sum over this thread's key group
       m_run = m_new;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_p);
-      // O' = P V of this block
+      // O' = P V of this block: this thread accumulates output columns [16g, 16g+16)
       mbar_wait(bar_o, (uint32_t)(i & 1));
       tc_fence_after();
+      uint32_t ov[16];
+      __syncwarp();
+      tmem_ld_32x32b_x16(tmem_O + lane_addr + g * 16, ov);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[c * 32 + j] = o[c * 32 + j] * alpha + __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < 16; ++j) o[j] = o[j] * alpha + __uint_as_float(ov[j]);
     }
+    // total row sum = sum of the four groups' partial sums (same running max in all four)
+    float* lrow = mx + ((nkb & 1) * 128 + r) * 4;
+    softmax_bar_sync();
+    lrow[g] = l_run;
+    softmax_bar_sync();
+    const float4 l4 = *reinterpret_cast<const float4*>(lrow);
+    const float l_tot = (l4.x + l4.y) + (l4.z + l4.w);
     if (qi < L) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      uint16_t* dst = o_out + ((long)b * L + qi) * 512 + h * 64;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint4 w;
-        w.x = pack2_h16(o[8 * u + 0] * inv, o[8 * u + 1] * inv, bf);
-        w.y = pack2_h16(o[8 * u + 2] * inv, o[8 * u + 3] * inv, bf);
-        w.z = pack2_h16(o[8 * u + 4] * inv, o[8 * u + 5] * inv, bf);
-        w.w = pack2_h16(o[8 * u + 6] * inv, o[8 * u + 7] * inv, bf);
-        reinterpret_cast<uint4*>(dst)[u] = w;
-      }
-      if (lse_out) lse_out[((long)b * 8 + h) * L + qi] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+      for (int j = 0; j < 16; ++j) o[j] *= inv;
+      uint16_t* dst = o_out + ((long)b * L + qi) * 512 + h * 64 + g * 16;
+      reinterpret_cast<uint4*>(dst)[0] = pack8_h16(o, bf);
+      reinterpret_cast<uint4*>(dst)[1] = pack8_h16(o + 8, bf);
+      if (lse_out && g == 0) lse_out[((long)b * 8 + h) * L + qi] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 int attn_fwd_prepare(void* plan_, const void* qkv, int B, int L, int bf16, char* err, int errlen) {
@@ -257,7 +241,7 @@ int attn_fwd_launch(const void* plan_, const float* keymask, int iso_p, void* o,
     attr_done = true;
   }
   dim3 grid((p->L + kAQ - 1) / kAQ, 8, p->B);
-  attn_fwd_kernel<<<grid, 160, AttnFwdSmem::kBytes, st>>>(*p, keymask, iso_p, reinterpret_cast<uint16_t*>(o), lse);
+  attn_fwd_kernel<<<grid, kFwdThreads, AttnFwdSmem::kBytes, st>>>(*p, keymask, iso_p, reinterpret_cast<uint16_t*>(o), lse);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -26,7 +26,8 @@ struct AttnPlan {
 static constexpr float kScale = 0.125f;
 static constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
 
-__device__ __forceinline__ void rows_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void rows_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+static constexpr int kBwdThreads = 544;   // 16 row warps (quadrant = w & 3, column group = w >> 2) + 1 MMA/TMA warp
 
 // write 32 consecutive K-elements (columns c*32 .. c*32+31) of row r into a [128 x 128] 16-bit
 // K-major SW128 operand made of two 16 KB column chunks
@@ -34,13 +35,8 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* tile, int r, int c, con
   uint8_t* chunk = tile + (c >> 1) * 16384 + r * 128;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    uint4 w;
-    w.x = pack2_h16(v[8 * u + 0], v[8 * u + 1], bf);
-    w.y = pack2_h16(v[8 * u + 2], v[8 * u + 3], bf);
-    w.z = pack2_h16(v[8 * u + 4], v[8 * u + 5], bf);
-    w.w = pack2_h16(v[8 * u + 6], v[8 * u + 7], bf);
     const int unit = (c & 1) * 4 + u;
-    *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = w;
+    *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = pack8_h16(v + 8 * u, bf);
   }
 }
 
@@ -86,7 +82,7 @@ struct DqSmem {
   static constexpr int kBytes = kBar + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
                    const float* __restrict__ lse, const float* __restrict__ delta, uint16_t* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,10 +99,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv1, 1); mbar_init(bar_sp, 1);
-    mbar_init(bar_ds, 128); mbar_init(bar_dq, 1);
+    mbar_init(bar_ds, 512); mbar_init(bar_dq, 1);
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,7 +110,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dQ = tmem + 256;
 
-  if (warp == 4) {
+  if (warp == 16) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
       const uint32_t idesc_q = umma_idesc_f16(bf, 128, 64, 0, 1);
@@ -162,9 +158,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
       }
     }
   } else {
-    const int r = threadIdx.x;
+    const int qd = warp & 3, g = warp >> 2;
+    const int r = qd * 32 + lane;
     const int qi = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const bool q_side = qi < iso_p;
     const long stat_idx = ((long)b * 8 + h) * L + qi;
     const float my_lse = qi < L ? lse[stat_idx] : INFINITY;
@@ -172,70 +169,56 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
     uint8_t* sdS = gbase + DqSmem::kdS;
     for (int i = 0; i < nkb; ++i) {
       const int k0 = i * 128;
+      uint32_t vw;
       {
-        const int key = k0 + r;
+        const int key = k0 + g * 32 + lane;
         const bool ok = key < L && keymask[(long)b * L + key] != 0.f;
-        const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) kvalid[(i & 1) * 4 + warp] = word;
-      }
-      rows_bar_sync();
-      uint32_t vw[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        vw[c] = kvalid[(i & 1) * 4 + c];
+        vw = __ballot_sync(0xffffffffu, ok);
         if (iso_p > 0) {
-          const int nb = iso_p - (k0 + 32 * c);
+          const int nb = iso_p - (k0 + 32 * g);
           const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          vw[c] &= q_side ? below : ~below;
+          vw &= q_side ? below : ~below;
         }
       }
       mbar_wait(bar_sp, (uint32_t)(i & 1));
       if (i >= 1) mbar_wait(bar_dq, (uint32_t)((i - 1) & 1));  // dS tile no longer read by dQ MMA(i-1)
       tc_fence_after();
+      uint32_t sv[32], pv[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(tmem_S + lane_addr + g * 32, sv);
+      tmem_ld_32x32b_x32(tmem_dP + lane_addr + g * 32, pv);
+      tmem_ld_wait();
+      float ds[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], pv[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c * 32, sv);
-        tmem_ld_32x32b_x32(tmem_dP + lane_addr + c * 32, pv);
-        tmem_ld_wait();
-        float ds[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float p = ((vw[c] >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - my_lse) : 0.f;
-          ds[j] = p * (__uint_as_float(pv[j]) - my_delta) * kScale;
-        }
-        store_row_chunk(sdS, r, c, ds, bf);
+      for (int j = 0; j < 32; ++j) {
+        const float pj = ((vw >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - my_lse) : 0.f;
+        ds[j] = pj * (__uint_as_float(pv[j]) - my_delta) * kScale;
       }
+      store_row_chunk(sdS, r, g, ds, bf);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_ds);
     }
     mbar_wait(bar_dq, (uint32_t)((nkb - 1) & 1));
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
+    {
+      uint32_t v[16];
       __syncwarp();
-      tmem_ld_32x32b_x32(tmem_dQ + lane_addr + c * 32, v);
+      tmem_ld_32x32b_x16(tmem_dQ + lane_addr + g * 16, v);
       tmem_ld_wait();
       if (qi < L) {
-        uint16_t* dst = dqkv + ((long)b * L + qi) * 1536 + h * 64 + c * 32;
+        float f[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack2_h16(__uint_as_float(v[8 * u + 0]), __uint_as_float(v[8 * u + 1]), bf);
-          w.y = pack2_h16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]), bf);
-          w.z = pack2_h16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]), bf);
-          w.w = pack2_h16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]), bf);
-          reinterpret_cast<uint4*>(dst)[u] = w;
-        }
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        uint16_t* dst = dqkv + ((long)b * L + qi) * 1536 + h * 64 + g * 16;
+        reinterpret_cast<uint4*>(dst)[0] = pack8_h16(f, bf);
+        reinterpret_cast<uint4*>(dst)[1] = pack8_h16(f + 8, bf);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -250,7 +233,7 @@ struct DkvSmem {
   static constexpr int kBytes = kBar + 2304 + 1024;   // barriers + 2 x (lse, delta)[128]
 };
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
                     const float* __restrict__ lse, const float* __restrict__ delta, uint16_t* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
@@ -268,10 +251,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
 
   if (threadIdx.x == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q1, 1); mbar_init(bar_sp, 1);
-    mbar_init(bar_pd, 128); mbar_init(bar_acc, 1);
+    mbar_init(bar_pd, 512); mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -279,7 +262,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_ST = tmem, tmem_dPT = tmem + 128, tmem_dV = tmem + 256, tmem_dK = tmem + 320;
 
-  if (warp == 4) {
+  if (warp == 16) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
       const uint32_t idesc_a = umma_idesc_f16(bf, 128, 64, 0, 1);
@@ -333,50 +316,48 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
       }
     }
   } else {
-    const int r = threadIdx.x;   // key row
+    const int qd = warp & 3, g = warp >> 2;
+    const int r = qd * 32 + lane;   // key row
     const int kj = k0 + r;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const bool key_ok = kj < L && keymask[(long)b * L + kj] != 0.f;
     const bool k_side = kj < iso_p;
     uint8_t* sPT = gbase + DkvSmem::kPT;
     uint8_t* sdST = gbase + DkvSmem::kdST;
     for (int i = 0; i < nqb; ++i) {
       const int q0 = i * 128;
-      {
-        const int q = q0 + r;
+      if (threadIdx.x < 128) {
+        const int q = q0 + threadIdx.x;
         const long idx = ((long)b * 8 + h) * L + q;
-        s_lse[(i & 1) * 128 + r] = q < L ? lse[idx] : INFINITY;
-        s_delta[(i & 1) * 128 + r] = q < L ? delta[idx] : 0.f;
+        s_lse[(i & 1) * 128 + threadIdx.x] = q < L ? lse[idx] : INFINITY;
+        s_delta[(i & 1) * 128 + threadIdx.x] = q < L ? delta[idx] : 0.f;
       }
       rows_bar_sync();
-      const float* lse_i = s_lse + (i & 1) * 128;
-      const float* del_i = s_delta + (i & 1) * 128;
+      const float* lse_i = s_lse + (i & 1) * 128 + g * 32;
+      const float* del_i = s_delta + (i & 1) * 128 + g * 32;
       mbar_wait(bar_sp, (uint32_t)(i & 1));
       if (i >= 1) mbar_wait(bar_acc, (uint32_t)((i - 1) & 1));
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t col_ok = key_ok ? 0xffffffffu : 0u;
-        if (iso_p > 0) {
-          const int nb = iso_p - (q0 + 32 * c);
-          const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          col_ok &= k_side ? below : ~below;
-        }
-        uint32_t sv[32], pv[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_ST + lane_addr + c * 32, sv);
-        tmem_ld_32x32b_x32(tmem_dPT + lane_addr + c * 32, pv);
-        tmem_ld_wait();
-        float p[32], ds[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pj = ((col_ok >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - lse_i[c * 32 + j]) : 0.f;
-          p[j] = pj;
-          ds[j] = pj * (__uint_as_float(pv[j]) - del_i[c * 32 + j]) * kScale;
-        }
-        store_row_chunk(sPT, r, c, p, bf);
-        store_row_chunk(sdST, r, c, ds, bf);
+      uint32_t col_ok = key_ok ? 0xffffffffu : 0u;
+      if (iso_p > 0) {
+        const int nb = iso_p - (q0 + 32 * g);
+        const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        col_ok &= k_side ? below : ~below;
       }
+      uint32_t sv[32], pv[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(tmem_ST + lane_addr + g * 32, sv);
+      tmem_ld_32x32b_x32(tmem_dPT + lane_addr + g * 32, pv);
+      tmem_ld_wait();
+      float pp[32], ds[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pj = ((col_ok >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - lse_i[j]) : 0.f;
+        pp[j] = pj;
+        ds[j] = pj * (__uint_as_float(pv[j]) - del_i[j]) * kScale;
+      }
+      store_row_chunk(sPT, r, g, pp, bf);
+      store_row_chunk(sdST, r, g, ds, bf);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_pd);
@@ -385,30 +366,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
     tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {   // 0: dK -> cols 512.., 1: dV -> cols 1024..
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld_32x32b_x16((which == 0 ? tmem_dK : tmem_dV) + lane_addr + g * 16, v);
+      tmem_ld_wait();
+      if (kj < L) {
+        float f[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (kj < L) {
-          uint16_t* dst = dqkv + ((long)b * L + kj) * 1536 + (which == 0 ? 512 : 1024) + h * 64 + c * 32;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 w;
-            w.x = pack2_h16(__uint_as_float(v[8 * u + 0]), __uint_as_float(v[8 * u + 1]), bf);
-            w.y = pack2_h16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]), bf);
-            w.z = pack2_h16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]), bf);
-            w.w = pack2_h16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]), bf);
-            reinterpret_cast<uint4*>(dst)[u] = w;
-          }
-        }
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        uint16_t* dst = dqkv + ((long)b * L + kj) * 1536 + (which == 0 ? 512 : 1024) + h * 64 + g * 16;
+        reinterpret_cast<uint4*>(dst)[0] = pack8_h16(f, bf);
+        reinterpret_cast<uint4*>(dst)[1] = pack8_h16(f + 8, bf);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -436,8 +410,8 @@ int attn_bwd_launch(const void* plan_, const void* dout, const float* keymask, i
   attn_delta_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dout),
                                                              reinterpret_cast<const uint16_t*>(o), delta, p->L, M, p->bf16);
   dim3 grid((p->L + 127) / 128, 8, p->B);
-  attn_bwd_dq_kernel<<<grid, 160, DqSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta, reinterpret_cast<uint16_t*>(dqkv));
-  attn_bwd_dkv_kernel<<<grid, 160, DkvSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta,
+  attn_bwd_dq_kernel<<<grid, kBwdThreads, DqSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta, reinterpret_cast<uint16_t*>(dqkv));
+  attn_bwd_dkv_kernel<<<grid, kBwdThreads, DkvSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta,
                                                           reinterpret_cast<uint16_t*>(dqkv));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;

@@ -26,7 +26,28 @@ __device__ __forceinline__ uint16_t f32_to_h16(float f, int bf) {
   return __half_as_ushort(__float2half_rn(f));
 }
 __device__ __forceinline__ uint32_t pack2_h16(float a, float b, int bf) {
-  return (uint32_t)f32_to_h16(a, bf) | ((uint32_t)f32_to_h16(b, bf) << 16);
+  if (bf) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // one cvt.rn.bf16x2.f32
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 8 floats -> 8 packed 16-bit values with a single (kernel-uniform) dtype branch
+__device__ __forceinline__ uint4 pack8_h16(const float* v, int bf) {
+  uint4 w;
+  if (bf) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b);
+    w.z = *reinterpret_cast<uint32_t*>(&c); w.w = *reinterpret_cast<uint32_t*>(&d);
+  } else {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b);
+    w.z = *reinterpret_cast<uint32_t*>(&c); w.w = *reinterpret_cast<uint32_t*>(&d);
+  }
+  return w;
 }
 __device__ __forceinline__ void unpack2_h16(uint32_t v, int bf, float& a, float& b) {
   a = h16_to_f32((uint16_t)(v & 0xffffu), bf);

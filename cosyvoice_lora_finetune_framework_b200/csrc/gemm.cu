@@ -21,21 +21,29 @@ static constexpr int BK = 64;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
+  static constexpr int kChunksPerWarp = BN / 64; // 8 epilogue warps: 2 per TMEM lane quadrant
+};
+static constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+
+// epilogue operands of one 32-column chunk that do not depend on the accumulator: fetched before
+// the accumulator is ready so their latency overlaps the main loop / the previous chunk
+struct EpiPrefetch {
+  uint4 v[8];   // fp32 residual (8 x float4) or 16-bit pre-activation (first 4 x uint4)
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, (BN == 128) ? 2 : 1)
+__global__ void __launch_bounds__(kGemmThreads, (BN == 256) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barriers: full[s] at +8*s, empty[s] at +8*(kStages+s), tmem_full at +8*2*kStages, tmem ptr after
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
@@ -60,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     tma_prefetch_desc(&p.tmW);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -110,105 +118,117 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
+    // ------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp-2)/4 -------
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int i = i0 + q * 32 + lane;
     const int orow = i * p.rmul + p.roff;
     const bool valid = (i < p.R) && (orow < p.out_rows);
     const long frow = (long)b * p.out_rows + orow;
-    const float rm = (valid && p.rowmask) ? p.rowmask[frow] : 1.f;
     const int bf = p.bf16;
+    const bool is_gelu = p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF;
+    const bool is_mul = p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD;
+    const bool full_cols = n0 + BN <= p.n_valid;   // whole tile inside the valid columns
+    const float rm = (valid && p.rowmask) ? p.rowmask[frow] : 1.f;
+
+    auto prefetch = [&](int c, EpiPrefetch& pf) {
+      const int nn = n0 + c * 32;
+      if (nn >= p.n_valid || !valid) return;
+      if (p.resid) {
+        const uint4* rs = reinterpret_cast<const uint4*>(p.resid + frow * p.ldr + p.col_off + nn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pf.v[j] = rs[j];
+      } else if (is_mul) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mul_src) +
+                                                          frow * p.ld_aux + nn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pf.v[j] = __ldg(src + j);
+      }
+    };
+
+    EpiPrefetch pf;
+    prefetch(half, pf);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
+      const int c = cc * 2 + half;
       const int nn = n0 + c * 32;
       if (nn >= p.n_valid) break;  // warp-uniform
       uint32_t r[32];
       __syncwarp();
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
-      if (!valid) continue;
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
       if (p.bias) {
+        if (full_cols) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
-      }
-      if (p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF) {
-        if (p.aux_out) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) +
-                                                frow * p.ld_aux + nn);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v;
-            v.x = pack2_h16(x[8 * j + 0], x[8 * j + 1], bf);
-            v.y = pack2_h16(x[8 * j + 2], x[8 * j + 3], bf);
-            v.z = pack2_h16(x[8 * j + 4], x[8 * j + 5], bf);
-            v.w = pack2_h16(x[8 * j + 6], x[8 * j + 7], bf);
-            dst[j] = v;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(bp + j);
+            x[4 * j + 0] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
           }
-        }
-        if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
-        }
-      } else if (p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD) {
-        const uint4* src = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const uint16_t*>(p.mul_src) + frow * p.ld_aux + nn);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v = __ldg(src + j);
-          float pre[8];
-          unpack2_h16(v.x, bf, pre[0], pre[1]);
-          unpack2_h16(v.y, bf, pre[2], pre[3]);
-          unpack2_h16(v.z, bf, pre[4], pre[5]);
-          unpack2_h16(v.w, bf, pre[6], pre[7]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e])
-                                                               : gelu_erf_grad_f(pre[e]);
+          for (int j = 0; j < 32; ++j)
+            if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
         }
       }
-      if (p.rowmask) {
+      if (valid) {
+        if (is_gelu) {
+          if (p.aux_out) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) + frow * p.ld_aux + nn);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] *= rm;
-      }
-      if (p.resid) {
-        const float4* rs = reinterpret_cast<const float4*>(p.resid + frow * p.ldr + p.col_off + nn);
+            for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
+          }
+          if (p.act == ACT_GELU_TANH) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = rs[j];
-          x[4 * j + 0] += v.x; x[4 * j + 1] += v.y; x[4 * j + 2] += v.z; x[4 * j + 3] += v.w;
+            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
+          }
+        } else if (is_mul) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 v = pf.v[j];
+            float pre[8];
+            unpack2_h16(v.x, bf, pre[0], pre[1]);
+            unpack2_h16(v.y, bf, pre[2], pre[3]);
+            unpack2_h16(v.z, bf, pre[4], pre[5]);
+            unpack2_h16(v.w, bf, pre[6], pre[7]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e]) : gelu_erf_grad_f(pre[e]);
+          }
         }
-      }
-      if (p.transposed_out) {
-        float* o = reinterpret_cast<float*>(p.out);
+        if (p.rowmask) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
-      } else if (p.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc +
-                                                p.col_off + nn);
+          for (int j = 0; j < 32; ++j) x[j] *= rm;
+        }
+        if (p.resid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-      } else {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + frow * p.ldc +
-                                              p.col_off + nn);
+          for (int j = 0; j < 8; ++j) {
+            x[4 * j + 0] += __uint_as_float(pf.v[j].x); x[4 * j + 1] += __uint_as_float(pf.v[j].y);
+            x[4 * j + 2] += __uint_as_float(pf.v[j].z); x[4 * j + 3] += __uint_as_float(pf.v[j].w);
+          }
+        }
+        if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
+        if (p.transposed_out) {
+          float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          v.x = pack2_h16(x[8 * j + 0], x[8 * j + 1], bf);
-          v.y = pack2_h16(x[8 * j + 2], x[8 * j + 3], bf);
-          v.z = pack2_h16(x[8 * j + 4], x[8 * j + 5], bf);
-          v.w = pack2_h16(x[8 * j + 6], x[8 * j + 7], bf);
-          dst[j] = v;
+          for (int j = 0; j < 32; ++j)
+            if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
+        } else if (p.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc + p.col_off + nn);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + frow * p.ldc + p.col_off + nn);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
         }
       }
     }
@@ -217,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -314,8 +334,12 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->ldr = a.ldr;
   // tile shape: 256-wide tiles only when N divides evenly and there is more than a wave of them
   const long mtiles = (long)p->tiles_per_batch * a.nbatch;
-  int bn = 128;
-  if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= 2 * 148) bn = 256;
+  // tile width: these GEMMs are short (K = 256..1536) and latency-bound, so prefer enough CTAs to
+  // keep >= 2 resident per SM over wide tiles
+  int bn = 64;
+  if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= 4 * 148) bn = 256;
+  else if (mtiles * ((a.n_valid + 127) / 128) >= 2 * 148 || a.n_valid > 512) bn = 128;
+  if (a.transposed_out) bn = 128;
   p->block_n = bn;
   p->grid_x = (int)mtiles;
   p->grid_y = (a.n_valid + bn - 1) / bn;
@@ -340,6 +364,8 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
 int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GemmCfg<64>::kSmemBytes);
     cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          GemmCfg<128>::kSmemBytes);
     cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -348,9 +374,11 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   }
   dim3 grid(p.grid_x, p.grid_y);
   if (p.block_n == 256)
-    gemm_tc_kernel<256><<<grid, 192, GemmCfg<256>::kSmemBytes, stream>>>(p);
+    gemm_tc_kernel<256><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(p);
+  else if (p.block_n == 128)
+    gemm_tc_kernel<128><<<grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(p);
   else
-    gemm_tc_kernel<128><<<grid, 192, GemmCfg<128>::kSmemBytes, stream>>>(p);
+    gemm_tc_kernel<64><<<grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
