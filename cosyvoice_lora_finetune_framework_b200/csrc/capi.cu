@@ -41,7 +41,7 @@ extern "C" CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* d, void* stream) {
   a.out = d->out; a.out_f32 = d->out_f32; a.transposed_out = d->transposed_out; a.ldc = d->ldc;
   a.col_off = d->col_off; a.n_valid = d->n_valid; a.alpha = d->alpha; a.act = d->act;
   a.bias = d->bias; a.aux_out = d->aux_out; a.mul_src = d->mul_src; a.ld_aux = d->ld_aux;
-  a.rowmask = d->rowmask; a.resid = d->resid; a.ldr = d->ldr;
+  a.rowmask = d->rowmask; a.resid = d->resid; a.ldr = d->ldr; a.dbg = (long long*)d->dbg;
   GemmParams p;
   if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return CVFLOW_ERR_ARG;
   int r = gemm_launch(p, (cudaStream_t)stream);

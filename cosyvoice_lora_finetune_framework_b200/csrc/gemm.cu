@@ -26,6 +26,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
   static constexpr int kChunksPerWarp = BN / 64; // 8 epilogue warps: 2 per TMEM lane quadrant
 };
@@ -37,6 +38,10 @@ struct EpiPrefetch {
   uint4 v[8];   // fp32 residual (8 x float4) or 16-bit pre-activation (first 4 x uint4)
 };
 
+// Persistent CTAs: each loops over output tiles (tile id = m-tile * n_tiles + n-tile, so CTAs that
+// run together share the A tile in L2). Accumulators are double-buffered in TMEM (2 x BN columns),
+// so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the TMA + MMA main
+// loop of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, (BN == 256) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -46,29 +51,35 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::kStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int nt = blockIdx.y;
-  const int b = mt / p.tiles_per_batch;
-  const int i0 = (mt - b * p.tiles_per_batch) * BM;
-  const int n0 = nt * BN;
+  const int ntn = p.grid_y;                    // n-tiles
+  const int total_tiles = p.grid_x * ntn;
+  long long* dbg = p.dbg ? p.dbg + (long)blockIdx.x * 8 : nullptr;
+  auto stamp = [&](int k) {
+    if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kGemmThreads - 64);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmW);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_alloc(tmem_ptr_smem, 2 * Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -81,17 +92,23 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int kb_global = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const GemmSeg sg = p.seg[s];
-        const CUtensorMap* tm = &p.tmA[sg.a_map];
-        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
-          tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / ntn, nt = tile - mt * ntn;
+        const int b = mt / p.tiles_per_batch;
+        const int i0 = (mt - b * p.tiles_per_batch) * BM;
+        const int n0 = nt * BN;
+        int kb_global = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const GemmSeg sg = p.seg[s];
+          const CUtensorMap* tm = &p.tmA[sg.a_map];
+          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
+            tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -100,145 +117,165 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t idesc = umma_idesc_f16(p.bf16, BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.nkb_total; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-        const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::kABytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.nkb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom
-          umma_f16_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom
+            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        umma_commit(tfull_bar(acc));
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
     // ------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp-2)/4 -------
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int i = i0 + q * 32 + lane;
-    const int orow = i * p.rmul + p.roff;
-    const bool valid = (i < p.R) && (orow < p.out_rows);
-    const long frow = (long)b * p.out_rows + orow;
     const int bf = p.bf16;
     const bool is_gelu = p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF;
     const bool is_mul = p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD;
-    const bool full_cols = n0 + BN <= p.n_valid;   // whole tile inside the valid columns
-    const float rm = (valid && p.rowmask) ? p.rowmask[frow] : 1.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int mt = tile / ntn, nt = tile - mt * ntn;
+      const int b = mt / p.tiles_per_batch;
+      const int i0 = (mt - b * p.tiles_per_batch) * BM;
+      const int n0 = nt * BN;
+      const int i = i0 + q * 32 + lane;
+      const int orow = i * p.rmul + p.roff;
+      const bool valid = (i < p.R) && (orow < p.out_rows);
+      const long frow = (long)b * p.out_rows + orow;
+      const bool full_cols = n0 + BN <= p.n_valid;   // whole tile inside the valid columns
+      const float rm = (valid && p.rowmask) ? p.rowmask[frow] : 1.f;
 
-    auto prefetch = [&](int c, EpiPrefetch& pf) {
-      const int nn = n0 + c * 32;
-      if (nn >= p.n_valid || !valid) return;
-      if (p.resid) {
-        const uint4* rs = reinterpret_cast<const uint4*>(p.resid + frow * p.ldr + p.col_off + nn);
+      auto prefetch = [&](int c, EpiPrefetch& pf) {
+        const int nn = n0 + c * 32;
+        if (nn >= p.n_valid || !valid) return;
+        if (p.resid) {
+          const uint4* rs = reinterpret_cast<const uint4*>(p.resid + frow * p.ldr + p.col_off + nn);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pf.v[j] = rs[j];
-      } else if (is_mul) {
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mul_src) +
-                                                          frow * p.ld_aux + nn);
+          for (int j = 0; j < 8; ++j) pf.v[j] = rs[j];
+        } else if (is_mul) {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mul_src) +
+                                                            frow * p.ld_aux + nn);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pf.v[j] = __ldg(src + j);
-      }
-    };
-
-    EpiPrefetch pf;
-    prefetch(half, pf);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
-      const int c = cc * 2 + half;
-      const int nn = n0 + c * 32;
-      if (nn >= p.n_valid) break;  // warp-uniform
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      float x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
-      if (p.bias) {
-        if (full_cols) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(bp + j);
-            x[4 * j + 0] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
+          for (int j = 0; j < 4; ++j) pf.v[j] = __ldg(src + j);
         }
-      }
-      if (valid) {
-        if (is_gelu) {
-          if (p.aux_out) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) + frow * p.ld_aux + nn);
+      };
+
+      EpiPrefetch pf;
+      prefetch(half, pf);
+      mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
+        const int c = cc * 2 + half;
+        const int nn = n0 + c * 32;
+        if (nn >= p.n_valid) break;  // warp-uniform
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias) {
+          if (full_cols) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(bp + j);
+              x[4 * j + 0] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
+          }
+        }
+        if (valid) {
+          if (is_gelu) {
+            if (p.aux_out) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) + frow * p.ld_aux + nn);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
+            }
+            if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
+            }
+          } else if (is_mul) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 v = pf.v[j];
+              float pre[8];
+              unpack2_h16(v.x, bf, pre[0], pre[1]);
+              unpack2_h16(v.y, bf, pre[2], pre[3]);
+              unpack2_h16(v.z, bf, pre[4], pre[5]);
+              unpack2_h16(v.w, bf, pre[6], pre[7]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e]) : gelu_erf_grad_f(pre[e]);
+            }
+          }
+          if (p.rowmask) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= rm;
+          }
+          if (p.resid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              x[4 * j + 0] += __uint_as_float(pf.v[j].x); x[4 * j + 1] += __uint_as_float(pf.v[j].y);
+              x[4 * j + 2] += __uint_as_float(pf.v[j].z); x[4 * j + 3] += __uint_as_float(pf.v[j].w);
+            }
+          }
+          if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
+          if (p.transposed_out) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
+          } else if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc + p.col_off + nn);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + frow * p.ldc + p.col_off + nn);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
           }
-          if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
-          }
-        } else if (is_mul) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 v = pf.v[j];
-            float pre[8];
-            unpack2_h16(v.x, bf, pre[0], pre[1]);
-            unpack2_h16(v.y, bf, pre[2], pre[3]);
-            unpack2_h16(v.z, bf, pre[4], pre[5]);
-            unpack2_h16(v.w, bf, pre[6], pre[7]);
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e]) : gelu_erf_grad_f(pre[e]);
-          }
-        }
-        if (p.rowmask) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] *= rm;
-        }
-        if (p.resid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            x[4 * j + 0] += __uint_as_float(pf.v[j].x); x[4 * j + 1] += __uint_as_float(pf.v[j].y);
-            x[4 * j + 2] += __uint_as_float(pf.v[j].z); x[4 * j + 3] += __uint_as_float(pf.v[j].w);
-          }
-        }
-        if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
-        if (p.transposed_out) {
-          float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
-        } else if (p.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc + p.col_off + nn);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + frow * p.ldc + p.col_off + nn);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
         }
       }
+      // all of this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, 2 * Cfg::kTmemCols);
   }
+  if (threadIdx.x == 32) stamp(6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,6 +361,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->nseg = a.nseg;
   p->nkb_total = nkb;
   p->src_A[0] = a.A[0]; p->src_A[1] = a.A[1]; p->src_W = a.W;
+  p->dbg = a.dbg;
   p->bf16 = a.bf16;
   p->R = a.R; p->rmul = a.rmul; p->roff = a.roff; p->out_rows = a.out_rows; p->nbatch = a.nbatch;
   p->tiles_per_batch = (a.R + BM - 1) / BM;
@@ -372,7 +410,15 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
                          GemmCfg<256>::kSmemBytes);
     attr_done = true;
   }
-  dim3 grid(p.grid_x, p.grid_y);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long total = (long)p.grid_x * p.grid_y;
+  const long slots = (long)num_sms * (p.block_n == 256 ? 1 : 2);
+  dim3 grid((unsigned)(total < slots ? total : slots));
   if (p.block_n == 256)
     gemm_tc_kernel<256><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(p);
   else if (p.block_n == 128)

@@ -60,6 +60,7 @@ struct GemmArgs {
   const float* rowmask = nullptr;  // [nbatch*out_rows]
   const float* resid = nullptr;    // fp32 [nbatch*out_rows][ldr] (may alias out)
   long ldr = 0;
+  long long* dbg = nullptr;        // optional per-CTA phase timestamps (8 x int64 per CTA), profiling aid
 };
 
 struct alignas(64) GemmParams {
@@ -72,6 +73,7 @@ struct alignas(64) GemmParams {
   void* out; int out_f32; long ldc; int col_off; int n_valid; int transposed_out;
   float alpha; const float* bias; int act; void* aux_out; const void* mul_src; long ld_aux;
   const float* rowmask; const float* resid; long ldr;
+  long long* dbg;
   const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
   int block_n;   // 128 or 256
   int grid_x, grid_y;

@@ -81,6 +81,7 @@ typedef struct cvflow_gemm_desc {
   const float* rowmask;
   const float* resid;
   int64_t ldr;
+  int64_t* dbg;         /* optional: 8 x int64 globaltimer stamps per CTA (profiling aid), else NULL */
 } cvflow_gemm_desc;
 
 CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* desc, void* stream);

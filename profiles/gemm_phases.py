@@ -1,0 +1,42 @@
+"""Per-CTA phase timeline of the GEMM kernel from in-kernel globaltimer stamps (profiling aid)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cosyvoice_lora_finetune_framework_b200 import _native as N  # noqa: E402
+from tests.test_gemm_gpu import _desc  # noqa: E402
+
+dt = torch.bfloat16
+L = N.lib()
+names = ["start", "prologue done", "first stage landed", "last MMA issued", "accumulator ready", "epilogue done", "exit"]
+for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (12800, 1536, 256, "h16")]:
+    A = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
+    W = (torch.randn(Nn, K, device="cuda") * 0.1).to(dt)
+    out = torch.randn(M, Nn, device="cuda") if mode == "resid" else torch.empty(M, Nn, device="cuda", dtype=dt)
+    kw = {}
+    if mode == "resid":
+        kw = dict(resid=out, ldr=Nn, bias=torch.randn(Nn, device="cuda"))
+    if mode == "mulgrad":
+        kw = dict(act=N.ACT_MUL_GELU_TANH_GRAD, mul_src=torch.randn(M, Nn, device="cuda").to(dt), ld_aux=Nn)
+    dbg = torch.zeros(4096 * 8, device="cuda", dtype=torch.int64)
+    d = _desc(A, W, out, segs=[(0, 0, 0, K // 64)], R=M, dtype=dt, **kw)
+    d.dbg = dbg.data_ptr()
+    for _ in range(3):
+        L.cvflow_gemm(C.byref(d), N.current_stream())
+    torch.cuda.synchronize()
+    dbg.zero_()
+    L.cvflow_gemm(C.byref(d), N.current_stream())
+    torch.cuda.synchronize()
+    t = dbg.view(-1, 8).cpu()
+    t = t[t[:, 0] > 0].double()
+    t0 = t[:, 0].min()
+    print("== M=%d N=%d K=%d %s: %d CTAs, kernel span %.1f us" % (M, Nn, K, mode, t.shape[0], (t[:, 6].max() - t0) / 1e3))
+    for k in range(1, 7):
+        print("   %-20s +%.2f us after previous (mean), at %.2f us from CTA start" %
+              (names[k], float((t[:, k] - t[:, k - 1]).mean()) / 1e3, float((t[:, k] - t[:, 0]).mean()) / 1e3))
+    starts = ((t[:, 0] - t0) / 1e3)
+    print("   CTA start times: median %.1f us, max %.1f us; CTA duration mean %.2f us" %
+          (float(starts.median()), float(starts.max()), float((t[:, 6] - t[:, 0]).mean()) / 1e3))
