@@ -21,11 +21,12 @@ static constexpr int BK = 64;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 2 : 3);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 4096;   // one 32x32 fp32 (or 16-bit) chunk per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
   static constexpr int kChunksPerWarp = BN / 64; // 8 epilogue warps: 2 per TMEM lane quadrant
@@ -48,7 +49,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
@@ -77,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmW);
+    if (p.tma_out) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, 2 * Cfg::kTmemCols);
@@ -148,6 +151,33 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int bf = p.bf16;
     const bool is_gelu = p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF;
     const bool is_mul = p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD;
+    // per-warp staging tile for TMA stores: [32 rows][64 B] (16-bit, 64B swizzle) or [32][128 B] (fp32, 128B swizzle)
+    const uint32_t stg = staging_base + (uint32_t)(warp - 2) * 4096u;
+    auto stage_h16 = [&](const float* x) {   // this lane's row: 32 x 16-bit = 4 x 16 B
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 w = pack8_h16(x + 8 * u, bf);
+        const uint32_t addr = stg + (uint32_t)lane * 64u + (uint32_t)((u ^ ((lane >> 1) & 3)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+      }
+    };
+    auto stage_f32 = [&](const float* x) {   // this lane's row: 32 x fp32 = 8 x 16 B
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[4 * u]), "f"(x[4 * u + 1]),
+                     "f"(x[4 * u + 2]), "f"(x[4 * u + 3]) : "memory");
+      }
+    };
+    auto stage_release = [&]() {   // the previous TMA store has finished reading the staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    };
+    auto stage_store = [&](const CUtensorMap* tm, int col, int row0, int b) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_3d(tm, stg, col, row0, b); tma_store_commit(); }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -208,9 +238,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
           }
         }
-        if (valid) {
+        if (p.tma_out && is_gelu && p.aux_out) {   // pre-activation stash through the staging tile
+          stage_release();
+          stage_h16(x);
+          stage_store(&p.tmAux, nn, i0 + q * 32, b);
+        }
+        if (valid || p.tma_out) {
           if (is_gelu) {
-            if (p.aux_out) {
+            if (p.aux_out && !p.tma_out) {
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) + frow * p.ld_aux + nn);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
@@ -225,22 +260,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           } else if (is_mul) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 v = pf.v[j];
+              const uint4 v = valid ? pf.v[j] : make_uint4(0u, 0u, 0u, 0u);
               float pre[8];
               unpack2_h16(v.x, bf, pre[0], pre[1]);
               unpack2_h16(v.y, bf, pre[2], pre[3]);
               unpack2_h16(v.z, bf, pre[4], pre[5]);
               unpack2_h16(v.w, bf, pre[6], pre[7]);
+              if (p.act == ACT_MUL_GELU_TANH_GRAD) {   // kernel-uniform branch hoisted out of the element loop
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                x[8 * j + e] *= (p.act == ACT_MUL_GELU_TANH_GRAD) ? gelu_tanh_grad_f(pre[e]) : gelu_erf_grad_f(pre[e]);
+                for (int e = 0; e < 8; ++e) x[8 * j + e] *= gelu_tanh_grad_f(pre[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[8 * j + e] *= gelu_erf_grad_f(pre[e]);
+              }
             }
           }
           if (p.rowmask) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] *= rm;
           }
-          if (p.resid) {
+          if (p.resid && valid) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               x[4 * j + 0] += __uint_as_float(pf.v[j].x); x[4 * j + 1] += __uint_as_float(pf.v[j].y);
@@ -248,11 +287,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             }
           }
           if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
-          if (p.transposed_out) {
-            float* o = reinterpret_cast<float*>(p.out);
+          if (p.tma_out) {
+            stage_release();
+            if (p.out_f32) stage_f32(x); else stage_h16(x);
+            stage_store(&p.tmOut, p.col_off + nn, i0 + q * 32, b);
+          } else if (p.transposed_out) {
+            if (valid) {
+              float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
+              for (int j = 0; j < 32; ++j)
+                if (nn + j < p.n_valid) o[((long)b * p.n_valid + nn + j) * p.out_rows + orow] = x[j];
+            }
           } else if (p.out_f32) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + frow * p.ldc + p.col_off + nn);
 #pragma unroll
@@ -269,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_arrive(tempty_bar(acc));
     }
   }
+  if (warp >= 2 && lane == 0) tma_store_wait_all();   // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -298,20 +344,28 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1, uint64_t d2,
-                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
-                  uint32_t b2) {
+int tma_encode_3d_ex(CUtensorMap* tm, const void* base, int dtype, int swizzle_bytes, uint64_t d0, uint64_t d1,
+                     uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                     uint32_t b2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -100;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dtc = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                             : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(tm, dtc, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1, uint64_t d2,
+                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                  uint32_t b2) {
+  return tma_encode_3d_ex(tm, base, bf16 ? 1 : 0, 128, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, b2);
 }
 
 static int encode_2d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1,
@@ -392,6 +446,33 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
     if (r) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(A[%d]) failed (%d)", s, r);
   }
   if (!use1) p->tmA[1] = p->tmA[0];
+  // output tensor maps for the TMA-store epilogue: rows i -> i*rmul + roff as a strided row view
+  p->tma_out = 0;
+  if (!a.transposed_out) {
+    const int esz = p->out_f32 ? 4 : 2;
+    long rows_view = (a.out_rows - a.roff + a.rmul - 1) / a.rmul;
+    if (rows_view > a.R) rows_view = a.R;
+    if (rows_view < 1) rows_view = 1;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.out) + (long)a.roff * a.ldc * esz;
+    const bool ok = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((a.ldc * esz) % 16 == 0);
+    if (ok) {
+      int r2 = tma_encode_3d_ex(&p->tmOut, base, p->out_f32 ? 2 : (a.bf16 ? 1 : 0), p->out_f32 ? 128 : 64,
+                                (uint64_t)(a.col_off + a.n_valid), (uint64_t)rows_view, (uint64_t)a.nbatch,
+                                (uint64_t)a.rmul * a.ldc * esz,
+                                (uint64_t)(a.nbatch > 1 ? (long)a.out_rows * a.ldc * esz : (long)a.rmul * a.ldc * esz * rows_view),
+                                32, 32, 1);
+      if (r2) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(out) failed (%d)", r2);
+      p->tma_out = 1;
+      if (a.aux_out) {
+        if (a.rmul != 1 || a.roff != 0) GEMM_FAIL("gemm: aux_out needs contiguous output rows");
+        r2 = tma_encode_3d_ex(&p->tmAux, a.aux_out, a.bf16 ? 1 : 0, 64, (uint64_t)a.n_valid, (uint64_t)rows_view,
+                              (uint64_t)a.nbatch, (uint64_t)a.ld_aux * 2,
+                              (uint64_t)(a.nbatch > 1 ? (long)a.out_rows * a.ld_aux * 2 : (long)a.ld_aux * 2 * rows_view),
+                              32, 32, 1);
+        if (r2) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(aux) failed (%d)", r2);
+      }
+    }
+  }
   if (reinterpret_cast<uintptr_t>(a.W) & 15) GEMM_FAIL("gemm: W must be 16-byte aligned");
   int r = encode_2d(&p->tmW, a.W, a.bf16, (uint64_t)a.Ktot, (uint64_t)a.N, (uint64_t)a.Ktot * 2, BK,
                     bn);

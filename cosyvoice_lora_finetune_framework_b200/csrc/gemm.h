@@ -66,6 +66,9 @@ struct GemmArgs {
 struct alignas(64) GemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmW;
+  CUtensorMap tmOut;    // row-major output, box {32 cols, 32 rows, 1} (TMA store from the epilogue)
+  CUtensorMap tmAux;    // pre-activation stash, same box
+  int tma_out;          // 1: epilogue stores through TMA
   GemmSeg seg[8];
   int nseg, nkb_total;
   int bf16;
@@ -86,5 +89,9 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream);
 int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1, uint64_t d2,
                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
                   uint32_t b2);
+// dtype: 0 f16, 1 bf16, 2 f32; swizzle_bytes: 0, 32, 64 or 128
+int tma_encode_3d_ex(CUtensorMap* tm, const void* base, int dtype, int swizzle_bytes, uint64_t d0, uint64_t d1,
+                     uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                     uint32_t b2);
 
 }  // namespace cvflow

@@ -12,13 +12,15 @@ from tests.test_gemm_gpu import _desc  # noqa: E402
 dt = torch.bfloat16
 L = N.lib()
 names = ["start", "prologue done", "first stage landed", "last MMA issued", "accumulator ready", "epilogue done", "exit"]
-for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (12800, 1536, 256, "h16")]:
+for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6400, 1024, 256, "gelu"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (6400, 256, 1024, "h16"), (6400, 512, 256, "h16"), (6400, 256, 1536, "h16"), (6400, 64, 1536, "h16"), (12800, 1536, 256, "h16"), (12800, 256, 1024, "resid")]:
     A = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
     W = (torch.randn(Nn, K, device="cuda") * 0.1).to(dt)
     out = torch.randn(M, Nn, device="cuda") if mode == "resid" else torch.empty(M, Nn, device="cuda", dtype=dt)
     kw = {}
     if mode == "resid":
         kw = dict(resid=out, ldr=Nn, bias=torch.randn(Nn, device="cuda"))
+    if mode == "gelu":
+        kw = dict(act=N.ACT_GELU_TANH, aux_out=torch.empty(M, Nn, device="cuda", dtype=dt), ld_aux=Nn, bias=torch.randn(Nn, device="cuda"))
     if mode == "mulgrad":
         kw = dict(act=N.ACT_MUL_GELU_TANH_GRAD, mul_src=torch.randn(M, Nn, device="cuda").to(dt), ld_aux=Nn)
     dbg = torch.zeros(4096 * 8, device="cuda", dtype=torch.int64)
@@ -33,10 +35,8 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 1024, "resid"), (
     t = dbg.view(-1, 8).cpu()
     t = t[t[:, 0] > 0].double()
     t0 = t[:, 0].min()
-    print("== M=%d N=%d K=%d %s: %d CTAs, kernel span %.1f us" % (M, Nn, K, mode, t.shape[0], (t[:, 6].max() - t0) / 1e3))
-    for k in range(1, 7):
-        print("   %-20s +%.2f us after previous (mean), at %.2f us from CTA start" %
-              (names[k], float((t[:, k] - t[:, k - 1]).mean()) / 1e3, float((t[:, k] - t[:, 0]).mean()) / 1e3))
-    starts = ((t[:, 0] - t0) / 1e3)
-    print("   CTA start times: median %.1f us, max %.1f us; CTA duration mean %.2f us" %
-          (float(starts.median()), float(starts.max()), float((t[:, 6] - t[:, 0]).mean()) / 1e3))
+    span = (t[:, 6].max() - t0) / 1e3
+    fl = 2.0 * M * Nn * K
+    print("== M=%d N=%d K=%d %s: %d persistent CTAs, kernel span %.1f us (%.0f TFLOP/s), CTA start spread %.2f us, "
+          "CTA lifetime mean %.2f / max %.2f us" % (M, Nn, K, mode, t.shape[0], span, fl / span / 1e6,
+          float((t[:, 0].max() - t0) / 1e3), float((t[:, 6] - t[:, 0]).mean()) / 1e3, float((t[:, 6] - t[:, 0]).max()) / 1e3))
