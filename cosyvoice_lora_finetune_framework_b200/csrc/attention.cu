@@ -81,6 +81,8 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 16) {
     if (lane == 0) {
@@ -241,7 +243,7 @@ int attn_fwd_launch(const void* plan_, const float* keymask, int iso_p, void* o,
     attr_done = true;
   }
   dim3 grid((p->L + kAQ - 1) / kAQ, 8, p->B);
-  attn_fwd_kernel<<<grid, kFwdThreads, AttnFwdSmem::kBytes, st>>>(*p, keymask, iso_p, reinterpret_cast<uint16_t*>(o), lse);
+  launch_pdl(attn_fwd_kernel, grid, kFwdThreads, AttnFwdSmem::kBytes, st, *p, keymask, iso_p, reinterpret_cast<uint16_t*>(o), lse);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -45,6 +45,8 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* tile, int r, int c, con
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, const uint16_t* __restrict__ O,
                                                          float* __restrict__ delta, int L, long M, int bf) {
+  pdl_wait();
+  pdl_launch();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -109,6 +111,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dQ = tmem + 256;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 16) {
     if (lane == 0) {
@@ -261,6 +265,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_ST = tmem, tmem_dPT = tmem + 128, tmem_dV = tmem + 256, tmem_dK = tmem + 320;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 16) {
     if (lane == 0) {
@@ -407,11 +413,11 @@ int attn_bwd_launch(const void* plan_, const void* dout, const float* keymask, i
     attr_done = true;
   }
   const long M = (long)p->B * p->L;
-  attn_delta_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dout),
+  launch_pdl(attn_delta_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dout),
                                                              reinterpret_cast<const uint16_t*>(o), delta, p->L, M, p->bf16);
   dim3 grid((p->L + 127) / 128, 8, p->B);
-  attn_bwd_dq_kernel<<<grid, kBwdThreads, DqSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta, reinterpret_cast<uint16_t*>(dqkv));
-  attn_bwd_dkv_kernel<<<grid, kBwdThreads, DkvSmem::kBytes, st>>>(*p, keymask, iso_p, lse, delta,
+  launch_pdl(attn_bwd_dq_kernel, grid, kBwdThreads, DqSmem::kBytes, st, *p, keymask, iso_p, lse, delta, reinterpret_cast<uint16_t*>(dqkv));
+  launch_pdl(attn_bwd_dkv_kernel, grid, kBwdThreads, DkvSmem::kBytes, st, *p, keymask, iso_p, lse, delta,
                                                           reinterpret_cast<uint16_t*>(dqkv));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;

@@ -110,6 +110,14 @@ __device__ __forceinline__ float gelu_erf_grad_f(float x) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_pdl() may begin (barrier init,
+// TMEM allocation, descriptor prefetch) while its predecessor drains; it must execute pdl_wait()
+// before its first global-memory access. pdl_launch() lets the successor start early.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -305,4 +313,27 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int bf16, int M, int N, int a
   return d;
 }
 
+}  // namespace cvflow
+
+#include <cstdlib>
+#include <utility>
+namespace cvflow {
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CVFLOW_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// Launch with programmatic stream serialization (PDL). The kernel MUST call pdl_wait() before
+// touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 }  // namespace cvflow

@@ -138,6 +138,8 @@ int launch_small_linear(const float* x, const float* W, const float* bias, float
 __global__ void __launch_bounds__(256) stage_out_kernel(const float* __restrict__ h, const float* __restrict__ rowmask,
                                                         uint16_t* __restrict__ dst, long ldc, int col_off, long M,
                                                         int bf) {
+  pdl_wait();
+  pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 channels
   if (i >= M * 32) return;
   const long row = i >> 5;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) stage_out_kernel(const float* __restrict_
 int launch_stage_out(const float* h, const float* rowmask, void* dst, long ldc, int col_off, long M, int bf16,
                      cudaStream_t st) {
   const long n = M * 32;
-  stage_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, rowmask, reinterpret_cast<uint16_t*>(dst), ldc,
+  launch_pdl(stage_out_kernel, (unsigned)((n + 255) / 256), 256, 0, st, h, rowmask, reinterpret_cast<uint16_t*>(dst), ldc,
                                                                 col_off, M, bf16);
   LAUNCH_RET();
 }
@@ -163,6 +165,8 @@ int launch_stage_out(const float* h, const float* rowmask, void* dst, long ldc, 
 __global__ void __launch_bounds__(256) grad_route_kernel(const uint16_t* __restrict__ src, long ld_src, int col_off,
                                                          const float* __restrict__ rowmask, float* __restrict__ dst,
                                                          int accumulate, uint16_t* __restrict__ dst16, long M, int bf) {
+  pdl_wait();
+  pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * 32) return;
   const long row = i >> 5;
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(256) grad_route_kernel(const uint16_t* __restr
 int launch_grad_route(const void* src, long ld_src, int col_off, const float* rowmask, float* dst, int accumulate,
                       void* dst16, long M, int bf16, cudaStream_t st) {
   const long n = M * 32;
-  grad_route_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), ld_src,
+  launch_pdl(grad_route_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(src), ld_src,
                                                                  col_off, rowmask, dst, accumulate,
                                                                  reinterpret_cast<uint16_t*>(dst16), M, bf16);
   LAUNCH_RET();

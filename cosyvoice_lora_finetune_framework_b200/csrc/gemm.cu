@@ -90,6 +90,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory from here on
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -501,11 +503,11 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   const long slots = (long)num_sms * (p.block_n == 256 ? 1 : 2);
   dim3 grid((unsigned)(total < slots ? total : slots));
   if (p.block_n == 256)
-    gemm_tc_kernel<256><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(p);
+    launch_pdl(gemm_tc_kernel<256>, grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream, p);
   else if (p.block_n == 128)
-    gemm_tc_kernel<128><<<grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(p);
+    launch_pdl(gemm_tc_kernel<128>, grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream, p);
   else
-    gemm_tc_kernel<64><<<grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream>>>(p);
+    launch_pdl(gemm_tc_kernel<64>, grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(192, 2) lora_wgrad_tc_kernel(const __grid_cons
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(192, 2) lora_wgrad_tc_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) lora_wgrad_final_kernel(const LoraBlockPtrs* __restrict__ blkp,
                                                                const float* __restrict__ part_b, const float* __restrict__ part_a,
                                                                int S, int r, float grad_scale, const float* __restrict__ gs_dev) {
+  pdl_wait();
+  pdl_launch();
   const int nb = 1536 * r, na = 3 * r * 256;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= nb + na) return;
@@ -254,10 +258,10 @@ int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float gr
     cudaFuncSetAttribute(lora_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
     attr_done = true;
   }
-  lora_wgrad_tc_kernel<<<dim3(p->S, 14), 192, kWgSmem, st>>>(*p);
+  launch_pdl(lora_wgrad_tc_kernel, dim3(p->S, 14), 192, kWgSmem, st, *p);
   const int total = 1536 * p->r + 3 * p->r * 256;
-  lora_wgrad_final_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_dev, p->part_b, p->part_a, p->S, p->r, grad_scale,
-                                                              gs_dev);
+  launch_pdl(lora_wgrad_final_kernel, (total + 255) / 256, 256, 0, st, block_dev, (const float*)p->part_b,
+             (const float*)p->part_a, p->S, p->r, grad_scale, gs_dev);
   LAUNCH_RET();
 }
 

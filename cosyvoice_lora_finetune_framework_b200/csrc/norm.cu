@@ -41,6 +41,8 @@ __device__ __forceinline__ void store8_h16(uint16_t* p, int bf, const float (&v)
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, uint16_t* __restrict__ out,
                                                             long M, int bf) {
+  pdl_wait();
+  pdl_launch();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, void* out, long M, int bf16,
                          cudaStream_t st) {
-  layernorm_fwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h, gamma, beta, reinterpret_cast<uint16_t*>(out), M,
+  launch_pdl(layernorm_fwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, h, gamma, beta, reinterpret_cast<uint16_t*>(out), M,
                                                                bf16);
   LAUNCH_RET();
 }
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
                                                             const float* __restrict__ gamma, const float* __restrict__ dres,
                                                             float* __restrict__ dh, uint16_t* __restrict__ dh16, long M,
                                                             int bf) {
+  pdl_wait();
+  pdl_launch();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
 }
 int launch_layernorm_bwd(const void* dxn16, const float* h_in, const float* gamma, const float* dres, float* dh,
                          void* dh16, long M, int bf16, cudaStream_t st) {
-  layernorm_bwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dxn16), h_in, gamma,
+  launch_pdl(layernorm_bwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dxn16), h_in, gamma,
                                                                dres, dh, reinterpret_cast<uint16_t*>(dh16), M, bf16);
   LAUNCH_RET();
 }
@@ -124,6 +128,8 @@ int gn_num_splits(int B, int L) {
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restrict__ c, float* __restrict__ partials,
                                                        int L, int nsplit, int bf) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[8][8][2];
   const int b = blockIdx.y, sp = blockIdx.x;
   const int rows_per = (L + nsplit - 1) / nsplit;
@@ -156,6 +162,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restric
 }
 __global__ void gn_stats_final_kernel(const float* __restrict__ partials, float* __restrict__ stats, int nsplit,
                                       int total) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, g)
   if (i >= total) return;
   const int b = i >> 3, g = i & 7;
@@ -175,8 +183,8 @@ __global__ void gn_stats_final_kernel(const float* __restrict__ partials, float*
 }
 int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st) {
   const int ns = gn_num_splits(B, L);
-  gn_stats_kernel<<<dim3(ns, B), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(c16), partials, L, ns, bf16);
-  gn_stats_final_kernel<<<(B * 8 + 127) / 128, 128, 0, st>>>(partials, stats, ns, B * 8);
+  launch_pdl(gn_stats_kernel, dim3(ns, B), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials, L, ns, bf16);
+  launch_pdl(gn_stats_final_kernel, (B * 8 + 127) / 128, 128, 0, st, partials, stats, ns, B * 8);
   LAUNCH_RET();
 }
 
@@ -185,6 +193,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
                                                        const float* __restrict__ mask, const float* __restrict__ tb, long tb_stride,
                                                        const uint16_t* __restrict__ add16, void* __restrict__ out, int mode,
                                                        int L, long M, int bf) {
+  pdl_wait();
+  pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * 32) return;
   const long row = i >> 5;
@@ -221,7 +231,7 @@ int launch_gn_apply(const void* c16, const float* stats, const float* gamma, con
                     const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L, int bf16,
                     cudaStream_t st) {
   const long M = (long)B * L, n = M * 32;
-  gn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(c16), stats, gamma,
+  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), stats, gamma,
                                                                beta, mask, tb, tb_stride,
                                                                reinterpret_cast<const uint16_t*>(add16), out, mode, L,
                                                                M, bf16);
@@ -254,6 +264,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ partials,
                                                             int L, int nsplit, int bf) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[8][8][2];
   const int b = blockIdx.y, sp = blockIdx.x;
   const int rows_per = (L + nsplit - 1) / nsplit;
@@ -283,6 +295,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
 }
 __global__ void gn_bwd_final_kernel(float* __restrict__ partials, float* __restrict__ sums, int nsplit, int total,
                                     float inv_n) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = i >> 3, g = i & 7;
@@ -299,6 +313,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mask, const float* __restrict__ sums,
                                                            uint16_t* __restrict__ dc, int L, long M, int bf) {
+  pdl_wait();
+  pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * 32) return;
   const long row = i >> 5;
@@ -318,11 +334,11 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
                   cudaStream_t st) {
   const int ns = gn_num_splits(B, L);
   const uint16_t* c = reinterpret_cast<const uint16_t*>(c16);
-  gn_bwd_reduce_kernel<<<dim3(ns, B), 256, 0, st>>>(dy, dy_f32, c, stats, gamma, beta, mask, partials, L, ns, bf16);
+  launch_pdl(gn_bwd_reduce_kernel, dim3(ns, B), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, partials, L, ns, bf16);
   float* sums = partials + (long)B * ns * 8 * 2;
-  gn_bwd_final_kernel<<<(B * 8 + 127) / 128, 128, 0, st>>>(partials, sums, ns, B * 8, 1.f / (32.f * (float)L));
+  launch_pdl(gn_bwd_final_kernel, (B * 8 + 127) / 128, 128, 0, st, partials, sums, ns, B * 8, 1.f / (32.f * (float)L));
   const long M = (long)B * L, n = M * 32;
-  gn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, dy_f32, c, stats, gamma, beta, mask, sums,
+  launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, sums,
                                                                    reinterpret_cast<uint16_t*>(dc16), L, M, bf16);
   LAUNCH_RET();
 }

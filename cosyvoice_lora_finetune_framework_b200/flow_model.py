@@ -218,3 +218,259 @@ class ConditionalCFM(nn.Module):
                                    f(t_step).reshape(b), f(z), keep_, iso, float(self.sigma_min),
                                    *[p for p, _, _ in ne.lora_views])
         return loss, y.to(x1.dtype)
+
+
+# ==============================================================================================
+# Callers of the CUDA path: the flow model wrapper that prepares (x1, mask, mu, spks, cond) and
+# the model builder (reference flow_model.py:207-767). Host-side PyTorch; the conditional flow
+# matching itself runs through ConditionalCFM above.
+# ==============================================================================================
+import random  # noqa: E402
+from typing import Any, Dict  # noqa: E402
+
+import torch.nn.functional as F  # noqa: E402
+
+from .encoder import ConformerEncoder, InterpolateRegulator  # noqa: E402
+from .modules import ConditionalDecoder  # noqa: E402
+from .utils import make_pad_mask  # noqa: E402
+
+try:
+    from .config import MEL_MEAN, MEL_STD, NO_PROMPT_TRAINING_CONFIG
+except ImportError:  # pragma: no cover
+    MEL_MEAN, MEL_STD = -6.0, 2.0
+    NO_PROMPT_TRAINING_CONFIG = {'enabled': False, 'mode': 'full', 'no_prompt_ratio': 0.8, 'use_mean_embedding': False}
+
+
+def _ode_steps_for(total_mel_len: int) -> int:
+    """10 / 15 / 20 Euler steps for <=300 / <=500 / >500 frames (flow_model.py:530-536)."""
+    if total_mel_len > 500:
+        return 20
+    if total_mel_len > 300:
+        return 15
+    return 10
+
+
+class MaskedDiffWithXvec(nn.Module):
+    """Flow model wrapper: token embedding -> Conformer encoder -> length regulator -> CFM decoder."""
+
+    def __init__(self, input_size: int = 512, output_size: int = 80, spk_embed_dim: int = 192, vocab_size: int = 4096,
+                 input_frame_rate: int = 50, encoder: Optional[nn.Module] = None,
+                 length_regulator: Optional[nn.Module] = None, decoder: Optional[nn.Module] = None):
+        super().__init__()
+        self.input_size = input_size
+        self.output_size = output_size
+        self.vocab_size = vocab_size
+        self.input_frame_rate = input_frame_rate
+        self.input_embedding = nn.Embedding(vocab_size, input_size)
+        self.spk_embed_affine_layer = nn.Linear(spk_embed_dim, output_size)
+        self.encoder = encoder
+        assert self.encoder is not None
+        self.encoder_proj = nn.Linear(self.encoder.output_size(), output_size)
+        self.decoder = decoder
+        self.length_regulator = length_regulator
+        self.mel_mean = MEL_MEAN
+        self.mel_std = MEL_STD
+
+    def normalize_mel(self, mel: torch.Tensor) -> torch.Tensor:
+        return (mel - self.mel_mean) / self.mel_std
+
+    def denormalize_mel(self, mel: torch.Tensor) -> torch.Tensor:
+        return mel * self.mel_std + self.mel_mean
+
+    # -- shared pieces -----------------------------------------------------------------------------
+    def _speaker(self, embedding):
+        return self.spk_embed_affine_layer(F.normalize(embedding, dim=1))
+
+    def _encode(self, token, token_len, like):
+        keep = (~make_pad_mask(token_len)).unsqueeze(-1).to(like)
+        emb = self.input_embedding(torch.clamp(token, min=0)) * keep
+        h, _ = self.encoder(emb, token_len)
+        return self.encoder_proj(h)
+
+    def _loss(self, feat, feat_len, h, embedding, conds, prompt_lens):
+        mask = (~make_pad_mask(feat_len)).to(h)
+        loss, _ = self.decoder.compute_loss(feat.transpose(1, 2).contiguous(), mask.unsqueeze(1),
+                                            h.transpose(1, 2).contiguous(), embedding, cond=conds.transpose(1, 2),
+                                            prompt_lens=prompt_lens)
+        return {'loss': loss}
+
+    # -- training ----------------------------------------------------------------------------------
+    def forward(self, batch: dict, device: torch.device) -> Dict[str, Any]:
+        """Training forward with the reference's anti-leakage prompt strategies
+        (flow_model.py:248-400). Python's `random` is consumed in the same order as the reference."""
+        from .config import ANTI_LEAKAGE_CONFIG as AL
+        dtype = self.input_embedding.weight.dtype
+        token = batch['speech_token'].to(device)
+        token_len = batch['speech_token_len'].to(device)
+        feat = self.normalize_mel(batch['speech_feat'].to(device).to(dtype))
+        feat_len = batch['speech_feat_len'].to(device)
+        embedding = batch['embedding'].to(device).to(dtype)
+        if NO_PROMPT_TRAINING_CONFIG.get('enabled', False):
+            return self._forward_no_prompt(token, token_len, feat, feat_len, embedding, device, dtype)
+
+        cross_mel = cross_len = None
+        if 'cross_sample_mel' in batch:
+            cross_mel = self.normalize_mel(batch['cross_sample_mel'].to(device).to(dtype))
+            cross_len = batch.get('cross_sample_mel_len', None)
+            if cross_len is not None:
+                cross_len = cross_len.to(device)
+        embedding = self._speaker(embedding)
+        h = self._encode(token, token_len, torch.zeros((), dtype=dtype, device=device))
+        h, _ = self.length_regulator(h, feat_len)
+
+        silence_on = AL.get('silence_padding_enabled', False)
+        dynamic_on = AL.get('dynamic_prompt_enabled', True)
+        dropout_on = AL.get('prompt_dropout_enabled', True)
+        blind_on = AL.get('text_blinding_enabled', True)
+        cross_on = AL.get('cross_sample_enabled', True)
+        lo_ratio, hi_ratio = AL.get('prompt_min_ratio', 0.10), AL.get('prompt_max_ratio', 0.30)
+        p_drop, p_blind = AL.get('prompt_dropout_prob', 0.10), AL.get('text_blinding_prob', 0.7)
+        sil_lo, sil_hi = AL.get('silence_min_tokens', 5), AL.get('silence_max_tokens', 10)
+        silence_value = (AL.get('silence_mel_value', -11.5) - self.mel_mean) / self.mel_std
+
+        conds = torch.zeros(feat.shape, device=device, dtype=dtype)
+        prompt_lens = []
+        for i, n in enumerate(feat_len):
+            n = int(n.item())
+            if dropout_on and random.random() < p_drop:                 # strategy 3: prompt dropout
+                prompt_lens.append(0)
+                continue
+            if dynamic_on:                                              # strategy 2: dynamic prompt length
+                lo = max(1, int(lo_ratio * n))
+                p = random.randint(lo, max(lo + 1, int(hi_ratio * n)))
+            else:
+                p = max(1, int(0.3 * n))
+            source = feat                                               # strategy 5: cross-sample prompt
+            if cross_on and cross_mel is not None and cross_len is not None and cross_len[i].item() > 0:
+                source = cross_mel
+                p = min(p, int(cross_len[i].item()))
+            recorded = p
+            if silence_on:                                              # strategy 1: silence gap
+                gap = int(random.randint(sil_lo, sil_hi) * 22050 / 256 / self.input_frame_rate)
+                gap = max(3, min(gap, 20))
+                conds[i, :p] = source[i, :p]
+                if p + gap < n:
+                    conds[i, p:p + gap] = silence_value
+                    recorded = p + gap
+            else:
+                conds[i, :p] = source[i, :p]
+            prompt_lens.append(recorded)
+            if blind_on and random.random() < p_blind:                  # strategy 6: text-side blinding
+                h[i, :p, :] = 0.0
+        return self._loss(feat, feat_len, h, embedding, conds, prompt_lens)
+
+    def _forward_no_prompt(self, token, token_len, feat, feat_len, embedding, device, dtype) -> Dict[str, Any]:
+        """No-prompt training (flow_model.py:402-473): zero conditioning ('full') or a small prompt with
+        probability 1 - no_prompt_ratio ('mixed')."""
+        mode = NO_PROMPT_TRAINING_CONFIG.get('mode', 'full')
+        ratio = NO_PROMPT_TRAINING_CONFIG.get('no_prompt_ratio', 0.8)
+        embedding = self._speaker(embedding)
+        h = self._encode(token, token_len, torch.zeros((), dtype=dtype, device=device))
+        h, _ = self.length_regulator(h, feat_len)
+        conds = torch.zeros(feat.shape, device=device, dtype=dtype)
+        if mode == 'full':
+            prompt_lens = [0] * feat.shape[0]
+        else:
+            prompt_lens = []
+            for i, n in enumerate(feat_len):
+                n = int(n.item())
+                if random.random() < ratio:
+                    prompt_lens.append(0)
+                else:
+                    p = random.randint(1, max(2, int(0.1 * n)))
+                    conds[i, :p] = feat[i, :p]
+                    prompt_lens.append(p)
+        return self._loss(feat, feat_len, h, embedding, conds, prompt_lens)
+
+    # -- inference ---------------------------------------------------------------------------------
+    @torch.inference_mode()
+    def inference(self, token, token_len, prompt_token, prompt_token_len, prompt_feat, prompt_feat_len, embedding,
+                  flow_cache=None):
+        """Prompted inference (flow_model.py:475-551); no mel (de)normalisation, like upstream."""
+        assert token.shape[0] == 1
+        embedding = self._speaker(embedding)
+        n_prompt, n_target = prompt_token.shape[1], token.shape[1]
+        all_tokens = torch.concat([prompt_token, token], dim=1)
+        h = self._encode(all_tokens, prompt_token_len + token_len, embedding)
+        mel_len1 = prompt_feat.shape[1]
+        mel_len2 = int(n_target / self.input_frame_rate * 22050 / 256)
+        if hasattr(self.length_regulator, 'inference'):
+            h, _ = self.length_regulator.inference(h[:, :n_prompt], h[:, n_prompt:], mel_len1, mel_len2,
+                                                   self.input_frame_rate)
+        else:
+            h, _ = self.length_regulator(h, torch.tensor([mel_len1 + mel_len2], device=token.device))
+        total = mel_len1 + mel_len2
+        conds = torch.zeros([1, total, self.output_size], device=token.device).to(h.dtype)
+        conds[:, :mel_len1] = prompt_feat
+        mask = (~make_pad_mask(torch.tensor([total], device=token.device))).to(h)
+        feat, new_cache = self.decoder(mu=h.transpose(1, 2).contiguous(), mask=mask.unsqueeze(1), spks=embedding,
+                                       cond=conds.transpose(1, 2), n_timesteps=_ode_steps_for(total),
+                                       prompt_len=mel_len1, cache=flow_cache)
+        return feat[:, :, mel_len1:].float(), new_cache
+
+    @torch.inference_mode()
+    def inference_like_training(self, token, token_len, feat_len, embedding, prompt_feat=None, prompt_len=0,
+                                n_timesteps=10):
+        """Inference that mirrors the training layout: full token sequence, optional short prompt
+        (flow_model.py:553-638). Returns the whole mel, prompt region included."""
+        assert token.shape[0] == 1
+        n = int(feat_len.item()) if isinstance(feat_len, torch.Tensor) else int(feat_len)
+        embedding = self._speaker(embedding)
+        h = self._encode(token, token_len, embedding)
+        h, _ = self.length_regulator(h, torch.tensor([n], device=token.device))
+        conds = torch.zeros([1, n, self.output_size], device=token.device, dtype=h.dtype)
+        if prompt_feat is not None and prompt_len > 0:
+            k = min(prompt_len, prompt_feat.shape[1], n)
+            conds[:, :k] = prompt_feat[:, :k]
+        if n_timesteps is None or n_timesteps == 10:
+            n_timesteps = _ode_steps_for(n)
+        mask = torch.ones([1, 1, n], device=token.device, dtype=h.dtype)
+        feat, _ = self.decoder(mu=h.transpose(1, 2).contiguous(), mask=mask, spks=embedding, cond=conds.transpose(1, 2),
+                               n_timesteps=n_timesteps, prompt_len=prompt_len if prompt_feat is not None else 0,
+                               cache=None)
+        return feat.float()
+
+
+def build_flow_model(pretrained_path: Optional[str] = None, device: str = 'cuda', input_size: int = 512,
+                     output_size: int = 80, spk_embed_dim: int = 192, vocab_size: int = 4096,
+                     encoder_attention_heads: int = 8, encoder_linear_units: int = 2048, encoder_num_blocks: int = 6,
+                     decoder_channels: tuple = (256, 256), decoder_attention_head_dim: int = 64,
+                     decoder_n_blocks: int = 4, decoder_num_mid_blocks: int = 12,
+                     decoder_num_heads: int = 8) -> MaskedDiffWithXvec:
+    """CosyVoice-300M flow model (reference flow_model.py:641-767): same hyper-parameters, same
+    construction order (hence the same seeded init), strict `flow.pt` load with the reference's
+    shape-matched partial fallback."""
+    import os
+    encoder = ConformerEncoder(input_size=input_size, output_size=input_size, attention_heads=encoder_attention_heads,
+                               linear_units=encoder_linear_units, num_blocks=encoder_num_blocks, dropout_rate=0.1,
+                               positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True,
+                               cnn_module_kernel=15, use_cnn_module=False, macaron_style=False, causal=False)
+    length_regulator = InterpolateRegulator(channels=output_size, sampling_ratios=(1, 1, 1, 1),
+                                            out_channels=output_size, groups=1)
+    estimator = ConditionalDecoder(in_channels=320, out_channels=80, channels=decoder_channels, dropout=0.0,
+                                   attention_head_dim=decoder_attention_head_dim, n_blocks=decoder_n_blocks,
+                                   num_mid_blocks=decoder_num_mid_blocks, num_heads=decoder_num_heads, act_fn='gelu')
+    decoder = ConditionalCFM(in_channels=output_size, n_spks=1, spk_emb_dim=output_size, sigma_min=1e-6,
+                             t_scheduler='cosine', training_cfg_rate=0.2, inference_cfg_rate=0.7, estimator=estimator)
+    model = MaskedDiffWithXvec(input_size=input_size, output_size=output_size, spk_embed_dim=spk_embed_dim,
+                               vocab_size=vocab_size, input_frame_rate=50, encoder=encoder,
+                               length_regulator=length_regulator, decoder=decoder)
+    if pretrained_path is not None:
+        weight_file = os.path.join(pretrained_path, 'flow.pt') if os.path.isdir(pretrained_path) else pretrained_path
+        if os.path.exists(weight_file):
+            print(f"Loading pretrained weights from: {weight_file}")
+            state = torch.load(weight_file, map_location='cpu')
+            try:
+                model.load_state_dict(state, strict=True)
+                print("Weights loaded successfully (strict=True)")
+            except Exception as e:
+                print(f"Strict loading failed: {e}")
+                own = model.state_dict()
+                matched = {k: v for k, v in state.items() if k in own and own[k].shape == v.shape}
+                own.update(matched)
+                model.load_state_dict(own, strict=False)
+                print(f"Partial loading: {len(matched)}/{len(state)} weights loaded")
+        else:
+            print(f"Warning: Weight file not found: {weight_file}")
+            print("Using random initialization")
+    return model.to(device)

@@ -1,0 +1,82 @@
+"""The flow-model wrapper (callers of the CUDA path) against the REAL reference,
+imported from /root/reference when it is present (build container only; skipped on the GPU box):
+identical state-dict layout and seeded init of the full 104.9 M-parameter flow model, and bit-identical
+prepared tensors (x1, mask, mu, spks, cond, prompt_lens) handed to compute_loss / the ODE solver for the
+same `random` / torch seeds."""
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference/cosyvoice_flow_finetune"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+
+
+def test_wrapper_matches_reference():
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.pop(k) for k in ("flow_model", "utils", "config", "modules", "lora") if k in sys.modules}
+    sys.path.insert(0, REF)
+    try:
+        import config as RC
+        import flow_model as R
+        import utils as RU
+        from cosyvoice_lora_finetune_framework_b200 import flow_model as O
+        RU.set_all_random_seed(11); a=R.build_flow_model(None,'cpu')
+        RU.set_all_random_seed(11); b=O.build_flow_model(None,'cpu')
+        sa,sb=a.state_dict(),b.state_dict()
+        assert list(sa)==list(sb), set(sa)^set(sb)
+        assert all(torch.equal(sa[k],sb[k]) for k in sa)
+        print("full flow model: %d keys identical incl. seeded init"%len(sa), sum(p.numel() for p in b.parameters()))
+        # capture compute_loss args
+        def cap(store):
+            def f(x1,mask,mu,spks,cond=None,prompt_lens=None):
+                store.update(x1=x1,mask=mask,mu=mu,spks=spks,cond=cond,prompt_lens=prompt_lens); return torch.zeros(()),None
+            return f
+        g=torch.Generator().manual_seed(0)
+        B=3; tl=torch.tensor([40,33,21]); fl=torch.tensor([70,57,36])
+        batch=dict(speech_token=torch.randint(0,4096,(B,40),generator=g),speech_token_len=tl,speech_feat=torch.randn(B,70,80,generator=g)*2-6,speech_feat_len=fl,embedding=torch.randn(B,192,generator=g),cross_sample_mel=torch.randn(B,30,80,generator=g)*2-6,cross_sample_mel_len=torch.tensor([30,0,12]))
+        a.eval(); b.eval()
+        for trial in range(4):
+            ra,rb={},{}
+            a.decoder.compute_loss=cap(ra); b.decoder.compute_loss=cap(rb)
+            random.seed(trial); a(batch,torch.device('cpu')); random.seed(trial); b(batch,torch.device('cpu'))
+            assert ra['prompt_lens']==rb['prompt_lens'], (ra['prompt_lens'],rb['prompt_lens'])
+            for k in ('x1','mask','mu','spks','cond'): assert torch.equal(ra[k],rb[k]), k
+        print("training wrapper: prepared tensors identical over 4 seeds", ra['prompt_lens'])
+        for mode in ('full','mixed'):
+            for mod in (RC,):
+                mod.NO_PROMPT_TRAINING_CONFIG.update(enabled=True,mode=mode)
+            R.NO_PROMPT_TRAINING_CONFIG.update(enabled=True,mode=mode); O.NO_PROMPT_TRAINING_CONFIG.update(enabled=True,mode=mode)
+            ra,rb={},{}; a.decoder.compute_loss=cap(ra); b.decoder.compute_loss=cap(rb)
+            random.seed(5); a(batch,torch.device('cpu')); random.seed(5); b(batch,torch.device('cpu'))
+            assert ra['prompt_lens']==rb['prompt_lens']
+            for k in ('x1','mask','mu','spks','cond'): assert torch.equal(ra[k],rb[k]), k
+        print("no-prompt modes identical")
+        # inference arg capture
+        def capd(store):
+            def f(mu,mask,n_timesteps,temperature=1.0,spks=None,cond=None,prompt_len=0,cache=None):
+                store.update(mu=mu,mask=mask,n=n_timesteps,spks=spks,cond=cond,prompt_len=prompt_len); return torch.zeros(1,80,mu.shape[2]),torch.zeros(1,80,34,2)
+            return f
+        ra,rb={},{}
+        a.decoder.forward=capd(ra); b.decoder.forward=capd(rb)
+        tok=torch.randint(0,4096,(1,120),generator=g); ptok=torch.randint(0,4096,(1,30),generator=g); pf=torch.randn(1,52,80,generator=g); emb=torch.randn(1,192,generator=g)
+        a.inference(tok,torch.tensor([120]),ptok,torch.tensor([30]),pf,torch.tensor([52]),emb)
+        b.inference(tok,torch.tensor([120]),ptok,torch.tensor([30]),pf,torch.tensor([52]),emb)
+        assert ra['n']==rb['n'] and ra['prompt_len']==rb['prompt_len']
+        for k in ('mu','mask','spks','cond'): assert torch.allclose(ra[k],rb[k],atol=1e-6), k
+        print("inference wrapper identical; n_timesteps", ra['n'], "T", ra['mu'].shape)
+        ra.clear(); rb.clear()
+        a.inference_like_training(tok,torch.tensor([120]),400,emb,prompt_feat=pf,prompt_len=20)
+        b.inference_like_training(tok,torch.tensor([120]),400,emb,prompt_feat=pf,prompt_len=20)
+        assert ra['n']==rb['n']==15
+        for k in ('mu','mask','spks','cond'): assert torch.allclose(ra[k],rb[k],atol=1e-6), k
+        print("inference_like_training identical")
+    finally:
+        sys.path.remove(REF)
+        for k in ("flow_model", "utils", "config", "modules", "lora"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+        from cosyvoice_lora_finetune_framework_b200 import flow_model as O2
+        O2.NO_PROMPT_TRAINING_CONFIG.update(enabled=False, mode='full')
