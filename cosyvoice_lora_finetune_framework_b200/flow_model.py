@@ -190,6 +190,12 @@ class ConditionalCFM(nn.Module):
     def _loss_with_noise(self, x1, mask, mu, spks, cond, prompt_lens, t_step, z, keep):
         """compute_loss with the random draws supplied (t already warped): used by the parity tests."""
         est = self.estimator
+        for name, v in (("mu", mu), ("spks", spks), ("cond", cond), ("x1", x1)):
+            if torch.is_tensor(v) and v.requires_grad:
+                raise NotImplementedError(
+                    "compute_loss: %s requires grad, but the CUDA flow path does not produce dL/d%s yet (only the "
+                    "estimator's attn1 q/k/v LoRA gradients; SURVEY section 8f-3). Detach the prepared tensors or "
+                    "restrict LoRA to target_modules=['to_q','to_k','to_v']." % (name, name))
         ne = E.native_of(est)
         ne.check_trainable(est)
         dev = ne.device

@@ -1,0 +1,89 @@
+"""End-to-end through the reference-shaped Python API on the GPU: build_flow_model -> LoRA inject ->
+JointLLMFlowModel('flow_only') training steps with the DP trainer -> merged checkpoint -> strict load
+into a fresh stock-layout model -> Euler inference; plus the train_joint CLI on synthetic batches."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(seed=1234):
+    from cosyvoice_lora_finetune_framework_b200 import flow_model, lora, utils
+    from cosyvoice_lora_finetune_framework_b200.llm_flow_model import JointLLMFlowModel
+    utils.set_all_random_seed(seed)
+    flow = flow_model.build_flow_model(None, 'cpu', decoder_n_blocks=1, decoder_num_mid_blocks=2)
+    stats = lora.apply_lora_to_model(flow, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=['to_q', 'to_k', 'to_v'])
+    assert stats['replaced_layers'] == 18          # (2 + 2 + 2) stages x 1 block x q,k,v
+    return JointLLMFlowModel(None, flow.cuda(), 'flow_only', 1.0, 1.0, True)
+
+
+def test_flow_only_training_reduces_loss_and_merges(tmp_path):
+    from cosyvoice_lora_finetune_framework_b200 import flow_model, lora
+    from cosyvoice_lora_finetune_framework_b200.train_joint import synthetic_batches
+    from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer
+    model = _model()
+    model.eval()        # deterministic encoder (no dropout); the estimator itself has none
+    model.flow.decoder.estimator.train()
+    batch = next(synthetic_batches(1, 4, max_feat_len=96, seed=3))
+    trainer = FlowLoRATrainer(model.flow.decoder, lr=2e-3, max_grad_norm=1.0)
+    dev = torch.device('cuda')
+    losses = []
+    for step in range(12):
+        torch.manual_seed(0)                        # same (t, z) every step: a fixed objective to descend
+        out = model(batch, dev)
+        assert set(out) == {'flow_loss', 'loss'}
+        out['loss'].backward()
+        trainer.micro = 1
+        trainer.optimizer_step()
+        losses.append(float(out['loss']))
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0] * 0.97, losses
+    assert int(trainer.found_inf.item()) == 0
+    # merged checkpoint: stock key layout, loads strictly, reproduces the LoRA model's inference
+    flow = model.flow
+    flow.eval()
+    tok = batch['speech_token'][:1, :40].cuda()
+    emb = batch['embedding'][:1].cuda()
+    args = (tok, torch.tensor([40]).cuda(), torch.zeros(1, 0, dtype=torch.long).cuda(), torch.tensor([0]).cuda(),
+            torch.zeros(1, 0, 80).cuda(), torch.tensor([0]).cuda(), emb)
+    torch.manual_seed(5)
+    mel_lora, _ = flow.inference(*args)
+    merged = lora.get_merged_state_dict(flow)
+    path = str(tmp_path / 'flow_merged_flow_only.pt')
+    torch.save(merged, path)
+    fresh = flow_model.build_flow_model(None, 'cpu', decoder_n_blocks=1, decoder_num_mid_blocks=2)
+    assert list(fresh.state_dict().keys()) != [] and set(fresh.state_dict().keys()) == set(merged.keys())
+    fresh.load_state_dict(torch.load(path), strict=True)
+    fresh = fresh.cuda().eval()
+    torch.manual_seed(5)
+    mel_merged, _ = fresh.inference(*args)
+    assert mel_lora.shape == mel_merged.shape == (1, 80, int(40 / 50 * 22050 / 256))
+    assert (mel_lora - mel_merged).abs().max().item() <= 2e-2 * mel_lora.abs().max().item()
+
+
+def test_requires_grad_on_prepared_tensors_is_refused():
+    model = _model()
+    est = model.flow.decoder
+    x = torch.randn(1, 80, 16, device='cuda')
+    mu = torch.randn(1, 80, 16, device='cuda', requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        est.compute_loss(x, torch.ones(1, 1, 16, device='cuda'), mu, torch.randn(1, 80, device='cuda'),
+                         cond=torch.zeros(1, 80, 16, device='cuda'))
+
+
+def test_train_joint_cli_synthetic(tmp_path):
+    from cosyvoice_lora_finetune_framework_b200 import config, train_joint
+    old = dict(config.JOINT_TRAINING_CONFIG)
+    config.JOINT_TRAINING_CONFIG.update(accumulate_grad_batches=2, max_feat_len=64)
+    try:
+        train_joint.main(['--mode', 'flow_only', '--epochs', '1', '--batch-size', '2', '--synthetic', '4',
+                          '--output-dir', str(tmp_path)])
+    finally:
+        config.JOINT_TRAINING_CONFIG.clear()
+        config.JOINT_TRAINING_CONFIG.update(old)
+    ck = torch.load(os.path.join(str(tmp_path), 'joint_flow_only_last.ckpt'), map_location='cpu', weights_only=False)
+    assert any(k.startswith('model.flow.decoder.estimator.') and k.endswith('lora_A') for k in ck['state_dict'])
+    merged = torch.load(os.path.join(str(tmp_path), 'flow_merged_flow_only.pt'), map_location='cpu')
+    assert not any('lora_' in k or 'original_layer' in k for k in merged)
