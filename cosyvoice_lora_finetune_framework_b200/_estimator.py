@@ -52,7 +52,7 @@ def _lib():
         L.cvflow_cfm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f, f, i32, vp]
         L.cvflow_euler_update.argtypes = [vp, vp, vp, i32, f, i64, vp]
         L.cvflow_sumsq.argtypes = [vp, i64, vp, vp, vp]
-        L.cvflow_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, f, f, f, f, f, f, f, i32, vp, vp]
+        L.cvflow_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, f, f, f, f, f, f, f, i32, vp, vp, vp]
         _protos_done = True
     return L
 

@@ -150,10 +150,10 @@ extern "C" CVFLOW_API int cvflow_sumsq(const float* g, int64_t n, float* partial
 extern "C" CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
                                             float grad_unscale, float max_norm, float lr, float beta1, float beta2,
                                             float eps, float weight_decay, int32_t step, int32_t* found_inf,
-                                            void* stream) {
+                                            const float* hyper_dev, void* stream) {
   if (!p || !g || !m || !v || !sumsq) { set_error("cvflow_adamw_step: null argument"); return CVFLOW_ERR_ARG; }
   RET_LAUNCH(launch_adamw(p, g, m, v, (long)n, sumsq, grad_unscale, max_norm, lr, beta1, beta2, eps, weight_decay, step,
-                          found_inf, (cudaStream_t)stream), "cvflow_adamw_step");
+                          found_inf, hyper_dev, (cudaStream_t)stream), "cvflow_adamw_step");
 }
 
 extern "C" CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on) {

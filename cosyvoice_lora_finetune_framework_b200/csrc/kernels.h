@@ -103,6 +103,6 @@ int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float gr
 int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cudaStream_t st);
 int launch_adamw(float* p, const float* g, float* m, float* v, long n, const float* sumsq, float grad_unscale,
                  float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step,
-                 int* found_inf, cudaStream_t st);
+                 int* found_inf, const float* hyper_dev, cudaStream_t st);
 
 }  // namespace cvflow

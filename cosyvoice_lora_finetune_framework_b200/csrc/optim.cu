@@ -46,7 +46,11 @@ int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cuda
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long n, const float* __restrict__ sumsq,
                                                     float grad_unscale, float max_norm, float lr, float beta1, float beta2,
-                                                    float eps, float wd, float bc1, float bc2_sqrt, int* __restrict__ found_inf) {
+                                                    float eps, float wd, float bc1, float bc2_sqrt, int* __restrict__ found_inf,
+                                                    const float* __restrict__ hyper) {
+  if (hyper) {   // {lr, 1-beta1^t, sqrt(1-beta2^t)} refreshed by the host before each CUDA-graph replay
+    lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2];
+  }
   const float total = sqrtf(sumsq[0]) * grad_unscale;
   if (!isfinite(total)) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && found_inf) *found_inf = 1;
@@ -66,12 +70,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }
 int launch_adamw(float* p, const float* g, float* m, float* v, long n, const float* sumsq, float grad_unscale,
                  float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, int* found_inf,
-                 cudaStream_t st) {
+                 const float* hyper_dev, cudaStream_t st) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 4 ? (n + 255) / 256 : 148 * 4);
   adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, sumsq, grad_unscale, max_norm, lr, beta1, beta2, eps, wd, bc1,
-                                     bc2_sqrt, found_inf);
+                                     bc2_sqrt, found_inf, hyper_dev);
   LAUNCH_RET();
 }
 

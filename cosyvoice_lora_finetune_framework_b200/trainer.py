@@ -50,6 +50,11 @@ class FlowLoRATrainer:
         self.step_count = 0
         self.micro = 0
         self.kernel_launches_per_step = 0
+        # optimiser scalars that change every step live in device memory so that a captured CUDA graph
+        # of the whole step stays valid: the host refreshes them (pinned -> device) before each replay
+        self.hyper = torch.zeros(4, device=dev)
+        self.hyper_host = torch.zeros(4).pin_memory()
+        self._graph = None
 
     def current_lr(self):
         if self.total_steps <= 0:
@@ -63,19 +68,30 @@ class FlowLoRATrainer:
         self.micro += 1
         return loss
 
-    def optimizer_step(self):
+    def _advance_hyper(self):
+        """step counter, learning rate and Adam bias corrections -> device (async, pinned source)."""
+        self.step_count += 1
+        t = self.step_count
+        self.hyper_host[0] = self.current_lr()
+        self.hyper_host[1] = 1.0 - self.betas[0] ** t
+        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def optimizer_step(self, from_graph=False):
         ne = self.ne
         st = E._stream()
         g = ne.grad_bucket
         if self.world > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-        self.step_count += 1
+        if not from_graph:
+            self._advance_hyper()
         N.check(self.L.cvflow_sumsq(g.data_ptr(), ne.n_lora, self.partials.data_ptr(), self.sumsq.data_ptr(), st),
                 "cvflow_sumsq")
         N.check(self.L.cvflow_adamw_step(ne.param_bucket.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                          ne.n_lora, self.sumsq.data_ptr(), 1.0 / self.world, float(self.max_grad_norm),
                                          float(self.current_lr()), self.betas[0], self.betas[1], self.eps, self.wd,
-                                         self.step_count, self.found_inf.data_ptr(), st), "cvflow_adamw_step")
+                                         max(1, self.step_count), self.found_inf.data_ptr(),
+                                         C.c_void_p(self.hyper.data_ptr()), st), "cvflow_adamw_step")
         g.zero_()
         ne.mark_dirty()
         ne.sync_lora()
@@ -86,6 +102,52 @@ class FlowLoRATrainer:
         if self.micro >= self.accumulate:
             self.optimizer_step()
         return loss
+
+    # -- whole-step CUDA graph ------------------------------------------------------------------------
+    def train_step_graphed(self, x1, mask, mu, spks, cond):
+        """One full optimiser step (CFM prep, estimator fwd, loss, bwd, allreduce, clip+AdamW, W_eff
+        refresh: ~1,600 kernel launches) replayed as ONE CUDA graph. Shapes must stay fixed; the
+        inputs are copied into static buffers, the RNG advances per replay (graph-safe Philox), and
+        the per-step optimiser scalars come from device memory. Returns the (static) loss tensor."""
+        if self.accumulate != 1:
+            raise ValueError("train_step_graphed captures a whole optimiser step: accumulate must be 1")
+        key = (tuple(x1.shape), tuple(spks.shape))
+        if self._graph is None or self._graph["key"] != key:
+            dev = self.ne.device
+            mk = lambda t: torch.empty(t.shape, device=dev, dtype=torch.float32)
+            st = dict(key=key, x1=mk(x1), mask=mk(mask), mu=mk(mu), spks=mk(spks), cond=mk(cond))
+            for k in ("x1", "mask", "mu", "spks", "cond"):
+                st[k].copy_(locals()[k])
+
+            def body():
+                loss, _ = self.cfm.compute_loss(st["x1"], st["mask"], st["mu"], st["spks"], cond=st["cond"])
+                loss.backward()
+                self.optimizer_step(from_graph=True)
+                return loss.detach()
+
+            self.ne.attach_grads()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up off the capture stream (plans, workspace, NCCL)
+                for _ in range(2):
+                    self._advance_hyper()
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["loss"] = body()
+            st["graph"] = g
+            self._graph = st
+        st = self._graph
+        st["x1"].copy_(x1, non_blocking=True)
+        st["mask"].copy_(mask, non_blocking=True)
+        st["mu"].copy_(mu, non_blocking=True)
+        st["spks"].copy_(spks, non_blocking=True)
+        st["cond"].copy_(cond, non_blocking=True)
+        self._advance_hyper()
+        st["graph"].replay()
+        return st["loss"]
 
     def grad_norm(self):
         return float(self.sumsq.sqrt().item()) / self.world

@@ -164,7 +164,9 @@ CVFLOW_API int cvflow_euler_update(float* x, const float* d, const float* dt, in
 CVFLOW_API int cvflow_sumsq(const float* g, int64_t n, float* partials /* >= 296 */, float* out, void* stream);
 CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
                                  float grad_unscale, float max_norm, float lr, float beta1, float beta2, float eps,
-                                 float weight_decay, int32_t step, int32_t* found_inf, void* stream);
+                                 float weight_decay, int32_t step, int32_t* found_inf,
+                                 const float* hyper_dev /* optional {lr, 1-b1^t, sqrt(1-b2^t)} on device, NULL = use args */,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,6 @@ def test_euler_update_and_adamw():
         opt.step()
         N.check(L.cvflow_sumsq(g.data_ptr(), m, partials.data_ptr(), ss.data_ptr(), E._stream()))
         N.check(L.cvflow_adamw_step(ours.data_ptr(), g.data_ptr(), mm.data_ptr(), vv.data_ptr(), m, ss.data_ptr(), 1.0,
-                                    1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, found.data_ptr(), E._stream()))
+                                    1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, found.data_ptr(), None, E._stream()))
     assert torch.allclose(ours, pt.data, atol=1e-6, rtol=1e-5)
     assert found.item() == 0
