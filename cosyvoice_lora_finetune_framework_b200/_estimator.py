@@ -49,7 +49,8 @@ def _lib():
         L.cvflow_launch_count.argtypes = [vp]
         L.cvflow_launch_count.restype = i64
         L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
-        L.cvflow_cfm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f, f, i32, vp]
+        L.cvflow_cfm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f, f, i32, vp, vp]
+        L.cvflow_lora_prepare.argtypes = [vp, vp]
         L.cvflow_euler_update.argtypes = [vp, vp, vp, i32, f, i64, vp]
         L.cvflow_sumsq.argtypes = [vp, i64, vp, vp, vp]
         L.cvflow_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, f, f, f, f, f, f, f, i32, vp, vp, vp]
@@ -85,6 +86,9 @@ class NativeEstimator:
         if self.device.type != "cuda":
             raise RuntimeError("ConditionalDecoder parameters must live on a CUDA device (got %s)" % self.device)
         self.keep = []          # tensors the library holds raw pointers to
+        self.tensors = {}       # name -> bound tensor (shared with replicas)
+        self.grad_slots = {}    # '<...>.grad' name -> (offset, numel, shape) in the flat bucket
+        self.replicas = []
         self.handle = C.c_void_p()
         self.ws = None
         self.ws_key = None
@@ -106,6 +110,7 @@ class NativeEstimator:
         assert t.is_cuda and t.is_contiguous(), name
         code = _F32 if t.dtype == torch.float32 else N.dtype_code(t.dtype)
         self.keep.append(t)
+        self.tensors[name] = t
         N.check(self.L.cvflow_bind(self.handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), code), "cvflow_bind")
 
     def _h(self, t):
@@ -145,6 +150,7 @@ class NativeEstimator:
         self.lora_r = r
         gelu = m.down_blocks[0][1][0].ff.net[0].approximate
         cfg = Config(n_blocks, n_mid, N.dtype_code(self.dtype), 0 if gelu == "tanh" else 1, r, float(scaling))
+        self.cfg = cfg
         N.check(self.L.cvflow_create(C.byref(cfg), C.byref(self.handle)), "cvflow_create")
 
         def conv3_w(w):      # [Cout][Cin][3] -> [Cout][tap*Cin + c]
@@ -207,10 +213,10 @@ class NativeEstimator:
                         if lm is not None:
                             self._bind(Q + ".lora_%s.A" % short, lm.lora_A.data)
                             self._bind(Q + ".lora_%s.B" % short, lm.lora_B.data)
-                            ga = self._grad_view(lm.lora_A)
-                            gb = self._grad_view(lm.lora_B)
-                            self._bind(Q + ".lora_%s.A.grad" % short, ga)
-                            self._bind(Q + ".lora_%s.B.grad" % short, gb)
+                            for pname, p in ((".A.grad", lm.lora_A), (".B.grad", lm.lora_B)):
+                                gname = Q + ".lora_%s" % short + pname
+                                self._bind(gname, self._grad_view(p))
+                                self.grad_slots[gname] = self._grad_slot(p)
                     if r > 0 and all(_lin(getattr(tb.attn1, pn))[2] is not None for pn in ("to_q", "to_k", "to_v")):
                         self._bind(Q + ".acat16", torch.zeros(64, 256, device=self.device, dtype=self.dtype))
                         self._bind(Q + ".bblk16", torch.zeros(64, 1536, device=self.device, dtype=self.dtype))
@@ -269,7 +275,44 @@ class NativeEstimator:
                 return self.grad_bucket[off:off + n].view_as(p)
         raise KeyError
 
+    def _grad_slot(self, p):
+        for q, off, n in self.lora_views:
+            if q is p:
+                return off, n, tuple(p.shape)
+        raise KeyError
+
+    def make_replica(self):
+        """A second handle over the SAME weight images (frozen 16-bit operands, merged W_eff, LoRA
+        masters) with its own launch plans, workspace, dL/dpred buffer and gradient bucket, so that
+        shards of one batch can run concurrently on several CUDA streams."""
+        r = NativeEstimator.__new__(NativeEstimator)
+        r.L, r.module, r.dtype, r.device = self.L, self.module, self.dtype, self.device
+        r.keep, r.tensors, r.grad_slots, r.replicas = [], {}, self.grad_slots, []
+        r.handle = C.c_void_p()
+        r.ws, r.ws_key = None, None
+        r.loss_scale, r._dirty, r._merged_version = self.loss_scale, False, -1
+        r.cfg, r.lora_modules, r.lora_r, r.lora_views, r.n_lora = self.cfg, self.lora_modules, self.lora_r, [], self.n_lora
+        r.param_bucket = self.param_bucket
+        r.grad_bucket = torch.zeros_like(self.grad_bucket)
+        N.check(self.L.cvflow_create(C.byref(self.cfg), C.byref(r.handle)), "cvflow_create")
+        for name, t in self.tensors.items():
+            if name in self.grad_slots:
+                off, n, shape = self.grad_slots[name]
+                t = r.grad_bucket[off:off + n].view(shape)
+            r._bind(name, t)
+        N.check(self.L.cvflow_lora_prepare(r.handle, _stream()), "cvflow_lora_prepare")
+        r.is_replica = True
+        return r
+
+    def shard_handles(self, n):
+        """[self, replica_1, ...] of length n (replicas are created once and cached)."""
+        while len(self.replicas) < n - 1:
+            self.replicas.append(self.make_replica())
+        return [self] + self.replicas[: n - 1]
+
     def attach_grads(self):
+        if getattr(self, "is_replica", False):
+            return
         """Make every LoRA parameter's .grad a view of the flat bucket (zeroing it when a grad
         was dropped by zero_grad(set_to_none=True))."""
         fresh = any(p.grad is None or p.grad.data_ptr() != self.grad_bucket.data_ptr() + 4 * off

@@ -25,7 +25,10 @@ struct AttnPlan {
   CUtensorMap tm_qkv;   // 16-bit [B][L][1536], box {64, 128, 1}
   CUtensorMap tm_do;    // 16-bit [B][L][512],  box {64, 128, 1} (backward only)
   int B, L, bf16;
+  long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
 };
+static long long* g_attn_dbg = nullptr;
+void attn_set_debug_buffer(void* p) { g_attn_dbg = reinterpret_cast<long long*>(p); }
 int attn_plan_bytes() { return (int)sizeof(AttnPlan); }
 
 static constexpr int kAQ = 128;   // query rows per CTA
@@ -67,6 +70,11 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
   const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
   const int L = plan.L, bf = plan.bf16;
   const int nkb = (L + kAK - 1) / kAK;
+  long long* dbg = plan.dbg ? plan.dbg + ((long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  auto stamp = [&](int k) {
+    if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_k0, 1); mbar_init(bar_k1, 1); mbar_init(bar_v, 1);
@@ -81,8 +89,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+  if (threadIdx.x == 0) stamp(1);
   pdl_wait();
   pdl_launch();
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 16) {
     if (lane == 0) {
@@ -155,30 +165,46 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
         }
       }
       mbar_wait(bar_s, (uint32_t)(i & 1));
+      if (threadIdx.x == 0 && i < 2) stamp(3 + 4 * i);
       tc_fence_after();
       uint32_t v[32];
       __syncwarp();
       tmem_ld_32x32b_x32(tmem_S + lane_addr + g * 32, v);
       tmem_ld_wait();
       float m_loc = -INFINITY;
+      const bool all_valid = vw == 0xffffffffu;   // warp-uniform: no per-element masking on the common path
+      if (all_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if ((vw >> j) & 1u) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((vw >> j) & 1u) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
+      }
       float* mrow = mx + ((i & 1) * 128 + r) * 4;
       mrow[g] = m_loc;
       softmax_bar_sync();
+      if (threadIdx.x == 0 && i < 2) stamp(4 + 4 * i);
       const float4 m4 = *reinterpret_cast<const float4*>(mrow);
       const float m_blk = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2;
       const float m_new = fmaxf(m_run, m_blk);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);
+      const float alpha = exp2_fast(m_run - m_use);
       float p[32];
       float rowsum = 0.f;
+      if (all_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pv = ((vw >> j) & 1u) ? exp2f(__uint_as_float(v[j]) * kScaleLog2 - m_use) : 0.f;
-        p[j] = pv;
-        rowsum += pv;
+        for (int j = 0; j < 32; ++j) {
+          p[j] = exp2_fast(fmaf(__uint_as_float(v[j]), kScaleLog2, -m_use));
+          rowsum += p[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pv = ((vw >> j) & 1u) ? exp2_fast(fmaf(__uint_as_float(v[j]), kScaleLog2, -m_use)) : 0.f;
+          p[j] = pv;
+          rowsum += pv;
+        }
       }
       {
         uint8_t* chunk = sP + (g >> 1) * 16384 + r * 128;
@@ -193,8 +219,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_p);
+      if (threadIdx.x == 0 && i < 2) stamp(5 + 4 * i);
       // O' = P V of this block: this thread accumulates output columns [16g, 16g+16)
       mbar_wait(bar_o, (uint32_t)(i & 1));
+      if (threadIdx.x == 0 && i < 2) stamp(6 + 4 * i);
       tc_fence_after();
       uint32_t ov[16];
       __syncwarp();
@@ -220,15 +248,17 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
       if (lse_out && g == 0) lse_out[((long)b * 8 + h) * L + qi] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
     }
   }
+  if (threadIdx.x == 0) stamp(11);
   tc_fence_before();
   __syncthreads();
   if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (threadIdx.x == 0) stamp(12);
 }
 
 int attn_fwd_prepare(void* plan_, const void* qkv, int B, int L, int bf16, char* err, int errlen) {
   AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);
   memset(p, 0, sizeof(*p));
-  p->B = B; p->L = L; p->bf16 = bf16;
+  p->B = B; p->L = L; p->bf16 = bf16; p->dbg = g_attn_dbg;
   int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, 1536 * 2, (uint64_t)L * 1536 * 2, 64,
                         128, 1);
   if (r) { if (err) snprintf(err, errlen, "attn: cuTensorMapEncodeTiled(qkv) failed (%d)", r); return -1; }

@@ -21,6 +21,7 @@ struct AttnPlan {
   CUtensorMap tm_qkv;
   CUtensorMap tm_do;
   int B, L, bf16;
+  long long* dbg;
 };
 
 static constexpr float kScale = 0.125f;
@@ -193,10 +194,18 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restric
       tmem_ld_32x32b_x32(tmem_dP + lane_addr + g * 32, pv);
       tmem_ld_wait();
       float ds[32];
+      // ds = P (dP - delta) d^-1/2 with the scale folded into the exponent: 2^(s c - (lse - log2 d^-1/2))
+      const float lse_s = my_lse + 3.0f;   // -log2(0.125) = 3
+      if (vw == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pj = ((vw >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - my_lse) : 0.f;
-        ds[j] = pj * (__uint_as_float(pv[j]) - my_delta) * kScale;
+        for (int j = 0; j < 32; ++j)
+          ds[j] = exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_s)) * (__uint_as_float(pv[j]) - my_delta);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          ds[j] = ((vw >> j) & 1u)
+                      ? exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_s)) * (__uint_as_float(pv[j]) - my_delta)
+                      : 0.f;
       }
       store_row_chunk(sdS, r, g, ds, bf);
       tc_fence_before();
@@ -356,11 +365,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
       tmem_ld_32x32b_x32(tmem_dPT + lane_addr + g * 32, pv);
       tmem_ld_wait();
       float pp[32], ds[32];
+      if (col_ok == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pj = ((col_ok >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * kScaleLog2 - lse_i[j]) : 0.f;
-        pp[j] = pj;
-        ds[j] = pj * (__uint_as_float(pv[j]) - del_i[j]) * kScale;
+        for (int j = 0; j < 32; ++j) {
+          const float pj = exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_i[j]));
+          pp[j] = pj;
+          ds[j] = pj * ((__uint_as_float(pv[j]) - del_i[j]) * kScale);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pj = ((col_ok >> j) & 1u) ? exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_i[j])) : 0.f;
+          pp[j] = pj;
+          ds[j] = pj * ((__uint_as_float(pv[j]) - del_i[j]) * kScale);
+        }
       }
       store_row_chunk(sPT, r, g, pp, bf);
       store_row_chunk(sdST, r, g, ds, bf);

@@ -99,6 +99,10 @@ extern "C" CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream)
   if (!h) { set_error("cvflow_lora_refresh: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->lora_refresh((cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_lora_prepare(cvflow_estimator* h, void* stream) {
+  if (!h) { set_error("cvflow_lora_prepare: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->lora_refresh((cudaStream_t)stream, false) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int cvflow_estimator_forward(cvflow_estimator* h, const cvflow_estimator_io* io, void* stream) {
   if (!h || !io || !io->x || !io->mask || !io->mu || !io->t || !io->out || io->B < 1 || io->T < 1) {
     set_error("cvflow_estimator_forward: null/invalid argument");
@@ -133,10 +137,11 @@ extern "C" CVFLOW_API int cvflow_cfm_prep(const float* x1, const float* z, const
 }
 extern "C" CVFLOW_API int cvflow_cfm_loss(const float* pred, const float* x1, const float* z, const float* w,
                                           const float* mask, float* scal, float* partials, void* dpred16, int32_t B,
-                                          int32_t T, float sigma_min, float loss_scale, int32_t dtype, void* stream) {
+                                          int32_t T, float sigma_min, float loss_scale, int32_t dtype,
+                                          const float* wsum_dev, void* stream) {
   if (!pred || !x1 || !z || !w || !mask || !scal || !partials) { set_error("cvflow_cfm_loss: null argument"); return CVFLOW_ERR_ARG; }
   RET_LAUNCH(launch_cfm_loss(pred, x1, z, w, mask, scal, partials, dpred16, B, T, sigma_min, loss_scale,
-                             dtype == CVFLOW_DTYPE_BF16, (cudaStream_t)stream), "cvflow_cfm_loss");
+                             dtype == CVFLOW_DTYPE_BF16, wsum_dev, (cudaStream_t)stream), "cvflow_cfm_loss");
 }
 extern "C" CVFLOW_API int cvflow_euler_update(float* x, const float* d, const float* dt, int32_t step, float cfg_rate,
                                               int64_t n, void* stream) {
@@ -168,3 +173,5 @@ extern "C" CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, i
   for (int i = 0; i < n; ++i) counts[i] = c[i];
   return r ? CVFLOW_ERR_CUDA : CVFLOW_OK;
 }
+
+extern "C" CVFLOW_API int cvflow_debug_attention_stamps(void* buf) { attn_set_debug_buffer(buf); return CVFLOW_OK; }

@@ -81,6 +81,12 @@ __device__ __forceinline__ float mish_grad_f(float x) {
   float sig = e / (1.f + e);
   return tsp + x * sig * (1.f - tsp * tsp);
 }
+// 2^x on the SFU (MUFU.EX2, flush-to-zero): exact enough for probabilities that are rounded to 16 bits
+__device__ __forceinline__ float exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // hardware tanh (MUFU.TANH, rel. error ~2^-11: below the 16-bit rounding of the tensors it feeds)
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -242,7 +242,12 @@ int launch_cfm_prep(const float* x1, const float* z, const float* t, float* y, i
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) wsum_kernel(const float* __restrict__ w, long n, float* __restrict__ scal) {
+__global__ void __launch_bounds__(256) wsum_kernel(const float* __restrict__ w, long n, float* __restrict__ scal,
+                                                   const float* __restrict__ wsum_dev) {
+  if (wsum_dev) {   // this call covers one shard: the normaliser is the whole batch's sum(w)
+    if (threadIdx.x == 0) scal[0] = wsum_dev[0];
+    return;
+  }
   __shared__ float red[8];
   float s = 0.f;
   for (long i = threadIdx.x; i < n; i += 256) s += w[i];
@@ -322,8 +327,8 @@ __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict
 }
 int launch_cfm_loss(const float* pred, const float* x1, const float* z, const float* w, const float* mask,
                     float* scal, float* partials, void* dpred, int B, int T, float sigma_min, float loss_scale,
-                    int bf16, cudaStream_t st) {
-  wsum_kernel<<<1, 256, 0, st>>>(w, (long)B * T, scal);
+                    int bf16, const float* wsum_dev, cudaStream_t st) {
+  wsum_kernel<<<1, 256, 0, st>>>(w, (long)B * T, scal, wsum_dev);
   dim3 grid((T + 31) / 32, B);
   cfm_loss_kernel<<<grid, 256, 0, st>>>(pred, x1, z, w, mask, scal, partials, reinterpret_cast<uint32_t*>(dpred), T,
                                         1.f - sigma_min, loss_scale, bf16);

@@ -297,7 +297,7 @@ int Estimator::stage_fwd(const std::string& S, int res_idx, const void* xin, lon
 // ------------------------------------------------------------------------------------------
 // LoRA weight refresh
 // ------------------------------------------------------------------------------------------
-int Estimator::lora_refresh(cudaStream_t st) {
+int Estimator::lora_refresh(cudaStream_t st, bool merge) {
   stream_ = st;
   dry_ = false;
   missing_ = false;

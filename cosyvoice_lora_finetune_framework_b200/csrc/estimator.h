@@ -63,7 +63,7 @@ class Estimator {
   int bind(const char* name, void* ptr, long numel, int dtype);
   void set_workspace(void* p, long bytes) { ws_ = p; ws_bytes_ = bytes; plans_.clear(); }
   long workspace_bytes(int B, int T, int training);
-  int lora_refresh(cudaStream_t st);
+  int lora_refresh(cudaStream_t st, bool merge = true);
   int forward(const EstimatorIO& io, cudaStream_t st);
   int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
   long launches() const { return launches_; }

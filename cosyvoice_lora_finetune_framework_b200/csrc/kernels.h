@@ -36,7 +36,7 @@ int launch_cfm_prep(const float* x1, const float* z, const float* t, float* y, i
 // (cols 80..127 zero) scaled by loss_scale. scal[0]=sum w, scal[1]=loss numerator, scal[2]=loss.
 int launch_cfm_loss(const float* pred, const float* x1, const float* z, const float* w, const float* mask,
                     float* scal, float* partials, void* dpred, int B, int T, float sigma_min, float loss_scale,
-                    int bf16, cudaStream_t st);
+                    int bf16, const float* wsum_dev, cudaStream_t st);
 // x += dt * ((1+g) d[0] - g d[1])   (flow_model.py:117-119)
 int launch_euler_update(float* x, const float* d, const float* dt_arr, int step, float cfg_rate, long n,
                         cudaStream_t st);
@@ -65,6 +65,7 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
 // keymask fp32 [B][L]; iso_p: prompt-isolation boundary at this resolution (0 = off).
 struct AttnPlan;  // holds the encoded tensor maps
 int attn_plan_bytes();
+void attn_set_debug_buffer(void* p);   // profiling aid: 16 x int64 globaltimer stamps per CTA of the next forward plans
 int attn_fwd_prepare(void* plan, const void* qkv, int B, int L, int bf16, char* err, int errlen);
 int attn_fwd_launch(const void* plan, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st);
 int attn_bwd_prepare(void* plan, const void* qkv, const void* dout, int B, int L, int bf16, char* err, int errlen);

@@ -43,7 +43,7 @@ class _CFMLossFn(torch.autograd.Function):
         dpred = ne.dpred_buffer(B, T)
         N.check(L.cvflow_cfm_loss(pred.data_ptr(), x1.data_ptr(), z.data_ptr(), w.data_ptr(), mask.data_ptr(),
                                   scal.data_ptr(), partials.data_ptr(), dpred.data_ptr(), B, T, sigma_min,
-                                  ne.loss_scale, N.dtype_code(ne.dtype), st), "cvflow_cfm_loss")
+                                  ne.loss_scale, N.dtype_code(ne.dtype), None, st), "cvflow_cfm_loss")
         ctx.ne = ne
         ctx.dpred = dpred
         ctx.n_extra = len(lora_params)
@@ -57,6 +57,76 @@ class _CFMLossFn(torch.autograd.Function):
         g = gloss.detach().reshape(1).to(torch.float32).contiguous()
         ne.backward(ctx.dpred, grad_scale=1.0 / ne.loss_scale, grad_scale_dev=g)
         return (None,) * (12 + ctx.n_extra)
+
+
+class _CFMLossShardedFn(torch.autograd.Function):
+    """The same training step with the batch cut into contiguous shards that run CONCURRENTLY on
+    several CUDA streams (one estimator handle per shard over shared weights). Every op of the path
+    is per-utterance except the loss normaliser sum(w), which is computed once for the whole batch
+    and handed to each shard, so the result equals the single-stream step. At these sizes
+    (6,400-12,800 tokens x 256 channels per kernel) single kernels are latency-bound; concurrent
+    shards fill the 148 SMs."""
+
+    @staticmethod
+    def forward(ctx, nes, streams, x1, mask, mu, spks, cond, w, t, z, keep, iso_len, sigma_min, *lora_params):
+        from .parallel import shard_bounds
+        L = E._lib()
+        B, _, T = x1.shape
+        S = len(nes)
+        cur = torch.cuda.current_stream()
+        wsum = w.sum().reshape(1)
+        y = torch.empty_like(x1)
+        scal = torch.zeros(S, 4, device=x1.device, dtype=torch.float32)
+        shards = []
+        for s in range(S):
+            lo, hi = shard_bounds(B, s, S)
+            st = cur if s == 0 else streams[s - 1]
+            if s > 0:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                ne = nes[s]
+                cs = C.c_void_p(st.cuda_stream)
+                sl = slice(lo, hi)
+                N.check(L.cvflow_cfm_prep(x1[sl].data_ptr(), z[sl].data_ptr(), t[sl].data_ptr(), y[sl].data_ptr(), hi - lo,
+                                          T, sigma_min, cs), "cvflow_cfm_prep")
+                pred = ne.forward(y[sl], mask[sl], mu[sl], t[sl], spks[sl] if spks is not None else None,
+                                  cond[sl] if cond is not None else None, keep=keep[sl] if keep is not None else None,
+                                  iso_len=iso_len, training=True)
+                partials = torch.empty((hi - lo) * ((T + 31) // 32), device=x1.device, dtype=torch.float32)
+                dpred = ne.dpred_buffer(hi - lo, T)
+                N.check(L.cvflow_cfm_loss(pred.data_ptr(), x1[sl].data_ptr(), z[sl].data_ptr(), w[sl].data_ptr(),
+                                          mask[sl].data_ptr(), scal[s].data_ptr(), partials.data_ptr(), dpred.data_ptr(),
+                                          hi - lo, T, sigma_min, ne.loss_scale, N.dtype_code(ne.dtype), wsum.data_ptr(),
+                                          cs), "cvflow_cfm_loss")
+                shards.append((st, ne, dpred, pred, partials))
+        for s in range(1, S):
+            cur.wait_stream(streams[s - 1])
+        denom = wsum * 80.0
+        loss = torch.where(denom > 0, scal[:, 1].sum() / denom.clamp_min(1e-30), torch.zeros_like(denom)).reshape(())
+        ctx.shards = shards
+        ctx.streams = streams
+        ctx.n_extra = len(lora_params)
+        ctx.mark_non_differentiable(y)
+        return loss, y
+
+    @staticmethod
+    def backward(ctx, gloss, gy):
+        cur = torch.cuda.current_stream()
+        g = gloss.detach().reshape(1).to(torch.float32).contiguous()
+        primary = ctx.shards[0][1]
+        primary.attach_grads()
+        for s, (st, ne, dpred, _, _) in enumerate(ctx.shards):
+            if s > 0:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                ne.backward(dpred, grad_scale=1.0 / ne.loss_scale, grad_scale_dev=g)
+        for s in range(1, len(ctx.shards)):
+            cur.wait_stream(ctx.shards[s][0])
+        for s in range(1, len(ctx.shards)):        # deterministic, fixed-order sum of the shard buckets
+            rb = ctx.shards[s][1].grad_bucket
+            primary.grad_bucket.add_(rb)
+            rb.zero_()
+        return (None,) * (13 + ctx.n_extra)
 
 
 class ConditionalCFM(nn.Module):
@@ -76,6 +146,8 @@ class ConditionalCFM(nn.Module):
         self.estimator = estimator
         self.use_cuda_graph = True
         self._graphs = {}
+        self.num_streams = 1      # >1: training batch shards run concurrently on that many CUDA streams
+        self._streams = []
 
     # ------------------------------------------------------------------------------------------
     # inference
@@ -220,9 +292,17 @@ class ConditionalCFM(nn.Module):
         cond_ = f(cond) if cond is not None else None
         keep_ = keep.to(dev).float().contiguous() if keep is not None else None
         ne.sync_lora()
-        loss, y = _CFMLossFn.apply(ne, f(x1), f(mask).reshape(b, T), f(mu), spks_, cond_, f(w).reshape(b, T),
-                                   f(t_step).reshape(b), f(z), keep_, iso, float(self.sigma_min),
-                                   *[p for p, _, _ in ne.lora_views])
+        S = min(int(self.num_streams), b)
+        if S > 1:
+            while len(self._streams) < S - 1:
+                self._streams.append(torch.cuda.Stream(device=dev))
+            loss, y = _CFMLossShardedFn.apply(ne.shard_handles(S), self._streams[: S - 1], f(x1), f(mask).reshape(b, T),
+                                              f(mu), spks_, cond_, f(w).reshape(b, T), f(t_step).reshape(b), f(z),
+                                              keep_, iso, float(self.sigma_min), *[p for p, _, _ in ne.lora_views])
+        else:
+            loss, y = _CFMLossFn.apply(ne, f(x1), f(mask).reshape(b, T), f(mu), spks_, cond_, f(w).reshape(b, T),
+                                       f(t_step).reshape(b), f(z), keep_, iso, float(self.sigma_min),
+                                       *[p for p, _, _ in ne.lora_views])
         return loss, y.to(x1.dtype)
 
 

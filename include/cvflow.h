@@ -113,6 +113,9 @@ CVFLOW_API int cvflow_set_workspace(cvflow_estimator* h, void* ptr, int64_t byte
 /* Rebuild the merged 16-bit q/k/v operands W + (alpha/r) B A from the bound fp32 masters
  * (lora.py:64-76 folded into the GEMM operand). Call after binding and after every optimiser step. */
 CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream);
+/* Same pointer-table setup without the merge launch: for a second handle that shares the weight
+ * images of another one (batch shards running concurrently on several streams). */
+CVFLOW_API int cvflow_lora_prepare(cvflow_estimator* h, void* stream);
 
 typedef struct cvflow_estimator_io {
   const float* x;    int32_t x_nb;     /* [x_nb][80][T]; batch row b reads row b % x_nb */
@@ -140,6 +143,9 @@ CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
  * the launching stream. cvflow_profile_read synchronises the stream and sums per class
  * (0 gemm, 1 attention fwd, 2 attention bwd, 4 lora wgrad): milliseconds, launches, algorithmic FLOPs. */
 CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on);
+/* Profiling aid: attention-forward plans prepared after this call write 16 x int64 globaltimer phase
+ * stamps per CTA into buf (NULL switches it off). */
+CVFLOW_API int cvflow_debug_attention_stamps(void* buf);
 CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* counts, double* flops, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------
@@ -149,11 +155,14 @@ CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* cou
 CVFLOW_API int cvflow_cfm_prep(const float* x1, const float* z, const float* t, float* y, int32_t B, int32_t T,
                                float sigma_min, void* stream);
 /* loss = sum(((pred-u) w)^2) / (sum(w) 80), u = x1-(1-sigma_min) z   flow_model.py:155,197-200
- * scal[0] = sum w, scal[1] = numerator, scal[2] = loss; partials: >= B*ceil(T/32) floats scratch;
+ * scal[0] = sum w, scal[1] = numerator, scal[2] = numerator / (scal[0] 80); partials: >= B*ceil(T/32) floats scratch;
  * dpred16 (nullable): loss_scale * dL/dpred * mask, 16-bit token-major [B][T][128]. */
 CVFLOW_API int cvflow_cfm_loss(const float* pred, const float* x1, const float* z, const float* w, const float* mask,
                                float* scal, float* partials, void* dpred16, int32_t B, int32_t T, float sigma_min,
-                               float loss_scale, int32_t dtype, void* stream);
+                               float loss_scale, int32_t dtype,
+                               const float* wsum_dev /* optional: sum(w) of the WHOLE batch when this call covers one
+                                                        shard of it (scal[0] is then copied from it), else NULL */,
+                               void* stream);
 /* x += dt[step] * ((1+cfg) d[0] - cfg d[1]) over n = 80*T elements   flow_model.py:117-119 */
 CVFLOW_API int cvflow_euler_update(float* x, const float* d, const float* dt, int32_t step, float cfg_rate, int64_t n,
                                    void* stream);

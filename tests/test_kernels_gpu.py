@@ -27,7 +27,7 @@ def test_cfm_prep_and_loss():
     partials = torch.zeros(B * ((T + 31) // 32), device="cuda")
     dp = torch.zeros(B, T, 128, device="cuda", dtype=torch.float16)
     N.check(L.cvflow_cfm_loss(pred.data_ptr(), x1.data_ptr(), z.data_ptr(), w.data_ptr(), mask.data_ptr(),
-                              scal.data_ptr(), partials.data_ptr(), dp.data_ptr(), B, T, 1e-6, 1024.0, 0, E._stream()))
+                              scal.data_ptr(), partials.data_ptr(), dp.data_ptr(), B, T, 1e-6, 1024.0, 0, None, E._stream()))
     p = pred.clone().requires_grad_(True)
     u = x1 - (1 - 1e-6) * z
     loss = (((p - u) * w[:, None]) ** 2).sum() / (w.sum() * 80)

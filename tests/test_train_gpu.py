@@ -76,3 +76,29 @@ def test_grad_accumulation_and_generic_autograd():
     (out ** 2).mean().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in est.parameters() if p.requires_grad)
     assert sum(float(p.grad.abs().sum()) for p in est.parameters() if p.requires_grad) > 0
+
+
+@pytest.mark.parametrize("streams", [2, 3])
+def test_sharded_streams_match_single_stream(streams):
+    """Concurrent batch shards (one handle + stream per shard, global loss normaliser) == single stream."""
+    from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
+    fx = load_golden("train_tiny_prompt")          # B = 3, prompt isolation, boundary weights
+    ref_loss, _, ref_grads, _ = _step(fx, torch.float16)
+    est, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    est = est.cuda().train()
+    cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
+    cfm.num_streams = streams
+    c = lambda k: fx[k].cuda()
+    t = 1 - torch.cos(c("t_rand") * 0.5 * 3.14159265359)
+    loss, y = cfm._loss_with_noise(c("x1"), c("mask"), c("mu"), c("spks"), c("cond"), fx["prompt_lens"], t, c("z"),
+                                   c("cfg_rand") > 0.2)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert torch.allclose(y.cpu(), fx["y"], atol=1e-5)
+    for k, p in est.named_parameters():
+        if p.requires_grad:
+            g = p.grad.cpu()
+            assert torch.allclose(g, ref_grads[k], atol=1e-7 + 1e-3 * float(ref_grads[k].abs().max())), k
+    # golden tolerance as well
+    assert abs(loss.item() - float(fx["loss"])) <= 1e-2 * float(fx["loss"])
