@@ -21,12 +21,15 @@ static constexpr int BK = 64;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 2 : 3);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 8 * 4096;   // one 32x32 fp32 (or 16-bit) chunk per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 2048;   // per epilogue warp: 32 rows x 64 B (32 x 16-bit, or 16 x fp32 per pass)
+  // two CTAs per SM leave (228 KB - 2 x 1 KB reserved) / 2 = 115,712 B each: stages + staging + 128 B of
+  // barriers + 896 B of alignment slack (the dynamic window is at least 128-byte aligned; checked at run time)
+  static constexpr int kPayloadBytes = kStages * kStageBytes + kStagingBytes + 128;
+  static constexpr int kSmemBytes = kPayloadBytes + 896;
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
   static constexpr int kChunksPerWarp = BN / 64; // 8 epilogue warps: 2 per TMEM lane quadrant
@@ -49,6 +52,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (smem_base - smem_u32(smem_raw) + Cfg::kPayloadBytes > Cfg::kSmemBytes) __trap();   // alignment slack exceeded
   const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -154,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const bool is_gelu = p.act == ACT_GELU_TANH || p.act == ACT_GELU_ERF;
     const bool is_mul = p.act == ACT_MUL_GELU_TANH_GRAD || p.act == ACT_MUL_GELU_ERF_GRAD;
     // per-warp staging tile for TMA stores: [32 rows][64 B] (16-bit, 64B swizzle) or [32][128 B] (fp32, 128B swizzle)
-    const uint32_t stg = staging_base + (uint32_t)(warp - 2) * 4096u;
+    const uint32_t stg = staging_base + (uint32_t)(warp - 2) * 2048u;
     auto stage_h16 = [&](const float* x) {   // this lane's row: 32 x 16-bit = 4 x 16 B
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -163,10 +167,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
       }
     };
-    auto stage_f32 = [&](const float* x) {   // this lane's row: 32 x fp32 = 8 x 16 B
+    auto stage_f32_half = [&](const float* x) {   // 16 fp32 of this lane's row = 4 x 16 B (64-byte rows, 64B swizzle)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t addr = stg + (uint32_t)lane * 64u + (uint32_t)((u ^ ((lane >> 1) & 3)) << 4);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[4 * u]), "f"(x[4 * u + 1]),
                      "f"(x[4 * u + 2]), "f"(x[4 * u + 3]) : "memory");
       }
@@ -290,9 +294,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           }
           if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
           if (p.tma_out) {
-            stage_release();
-            if (p.out_f32) stage_f32(x); else stage_h16(x);
-            stage_store(&p.tmOut, p.col_off + nn, i0 + q * 32, b);
+            if (p.out_f32) {   // two passes of 16 columns through the 2 KB staging tile
+              stage_release();
+              stage_f32_half(x);
+              stage_store(&p.tmOut, p.col_off + nn, i0 + q * 32, b);
+              stage_release();
+              stage_f32_half(x + 16);
+              stage_store(&p.tmOut, p.col_off + nn + 16, i0 + q * 32, b);
+            } else {
+              stage_release();
+              stage_h16(x);
+              stage_store(&p.tmOut, p.col_off + nn, i0 + q * 32, b);
+            }
           } else if (p.transposed_out) {
             if (valid) {
               float* o = reinterpret_cast<float*>(p.out);
@@ -458,11 +471,11 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.out) + (long)a.roff * a.ldc * esz;
     const bool ok = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((a.ldc * esz) % 16 == 0);
     if (ok) {
-      int r2 = tma_encode_3d_ex(&p->tmOut, base, p->out_f32 ? 2 : (a.bf16 ? 1 : 0), p->out_f32 ? 128 : 64,
+      int r2 = tma_encode_3d_ex(&p->tmOut, base, p->out_f32 ? 2 : (a.bf16 ? 1 : 0), 64,
                                 (uint64_t)(a.col_off + a.n_valid), (uint64_t)rows_view, (uint64_t)a.nbatch,
                                 (uint64_t)a.rmul * a.ldc * esz,
                                 (uint64_t)(a.nbatch > 1 ? (long)a.out_rows * a.ldc * esz : (long)a.rmul * a.ldc * esz * rows_view),
-                                32, 32, 1);
+                                p->out_f32 ? 16 : 32, 32, 1);
       if (r2) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(out) failed (%d)", r2);
       p->tma_out = 1;
       if (a.aux_out) {
