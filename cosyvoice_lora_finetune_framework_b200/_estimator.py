@@ -218,12 +218,21 @@ class NativeEstimator:
                                 self._bind(gname, self._grad_view(p))
                                 self.grad_slots[gname] = self._grad_slot(p)
                     if r > 0 and all(_lin(getattr(tb.attn1, pn))[2] is not None for pn in ("to_q", "to_k", "to_v")):
-                        self._bind(Q + ".acat16", torch.zeros(64, 256, device=self.device, dtype=self.dtype))
-                        self._bind(Q + ".bblk16", torch.zeros(64, 1536, device=self.device, dtype=self.dtype))
+                        # [W_eff ; A_cat] and [W_eff^T ; B_blk]: the LoRA factor images ride along as 64 extra
+                        # operand rows, so u = x A_cat^T and v = dY B_blk^T fall out of the q/k/v GEMMs
+                        wext = torch.zeros(1600, 256, device=self.device, dtype=self.dtype)
+                        wtext = torch.zeros(320, 1536, device=self.device, dtype=self.dtype)
+                        self._bind(Q + ".weff_ext", wext)
+                        self._bind(Q + ".weff_t_ext", wtext)
+                        self._bind(Q + ".weff", wext[:1536])
+                        self._bind(Q + ".acat16", wext[1536:])
+                        self._bind(Q + ".weff_t", wtext[:256])
+                        self._bind(Q + ".bblk16", wtext[256:])
                     elif r > 0:
                         raise NotImplementedError("LoRA must wrap to_q, to_k and to_v of every attention block")
-                    self._bind(Q + ".weff", torch.empty(1536, 256, device=self.device, dtype=self.dtype))
-                    self._bind(Q + ".weff_t", torch.empty(256, 1536, device=self.device, dtype=self.dtype))
+                    else:
+                        self._bind(Q + ".weff", torch.empty(1536, 256, device=self.device, dtype=self.dtype))
+                        self._bind(Q + ".weff_t", torch.empty(256, 1536, device=self.device, dtype=self.dtype))
                     wo, bo, _ = _lin(tb.attn1.to_out[0])
                     self._bind(Q + ".wo", self._h(wo))
                     self._bind(Q + ".wo_t", self._h(wo.t()))

@@ -255,12 +255,12 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__
   if (threadIdx.x == 0) stamp(12);
 }
 
-int attn_fwd_prepare(void* plan_, const void* qkv, int B, int L, int bf16, char* err, int errlen) {
+int attn_fwd_prepare(void* plan_, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen) {
   AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);
   memset(p, 0, sizeof(*p));
   p->B = B; p->L = L; p->bf16 = bf16; p->dbg = g_attn_dbg;
-  int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, 1536 * 2, (uint64_t)L * 1536 * 2, 64,
-                        128, 1);
+  int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, (uint64_t)ldq * 2,
+                        (uint64_t)L * ldq * 2, 64, 128, 1);
   if (r) { if (err) snprintf(err, errlen, "attn: cuTensorMapEncodeTiled(qkv) failed (%d)", r); return -1; }
   return 0;
 }

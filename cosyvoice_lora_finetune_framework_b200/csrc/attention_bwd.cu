@@ -410,12 +410,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-int attn_bwd_prepare(void* plan_, const void* qkv, const void* dout, int B, int L, int bf16, char* err, int errlen) {
+int attn_bwd_prepare(void* plan_, const void* qkv, long ldq, const void* dout, int B, int L, int bf16, char* err,
+                     int errlen) {
   AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);
   memset(p, 0, sizeof(*p));
   p->B = B; p->L = L; p->bf16 = bf16;
-  int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, 1536 * 2, (uint64_t)L * 1536 * 2, 64,
-                        128, 1);
+  int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, (uint64_t)ldq * 2,
+                        (uint64_t)L * ldq * 2, 64, 128, 1);
   if (!r) r = tma_encode_3d(&p->tm_do, dout, bf16, 512, (uint64_t)L, (uint64_t)B, 512 * 2, (uint64_t)L * 512 * 2, 64, 128, 1);
   if (r) { if (err) snprintf(err, errlen, "attn bwd: cuTensorMapEncodeTiled failed (%d)", r); return -1; }
   return 0;

@@ -215,8 +215,12 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
 int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, int iso_p,
                       float** h_out, TBRec* rec) {
   const long M = (long)B * L;
+  // with LoRA in training the q/k/v GEMM also emits u = x1 A_cat^T as 64 extra output columns
+  // (operand rows 1536..1599 of weff_ext), which the wgrad kernel consumes in the backward pass
+  const bool ext = cfg.lora_r > 0 && training_;
+  const long ldq = ext ? 1600 : 1536;
   void* x1 = alloc(M * 256 * 2);
-  void* qkv = alloc(M * 1536 * 2);
+  void* qkv = alloc(M * ldq * 2);
   void* o = alloc(M * 512 * 2);
   float* lse = (float*)alloc((long)B * 8 * L * 4);
   float* h1 = (float*)alloc(M * 256 * 4);
@@ -230,14 +234,15 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     ++launches_;
   }
   {
-    GemmArgs g = linear_args(x1, M, 256, get(Q + ".weff", cfg.bf16, 1536L * 256), 1536, qkv, 0);
+    GemmArgs g = ext ? linear_args(x1, M, 256, get(Q + ".weff_ext", cfg.bf16, 1600L * 256), 1600, qkv, 0)
+                     : linear_args(x1, M, 256, get(Q + ".weff", cfg.bf16, 1536L * 256), 1536, qkv, 0);
     CK(run_gemm(g));
   }
   if (!dry_) {
     Plan& pl = *plan_;
     if ((size_t)attn_idx_ >= pl.attn.size()) {
       pl.attn.emplace_back(attn_plan_bytes());
-      if (attn_fwd_prepare(pl.attn.back().data(), qkv, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
+      if (attn_fwd_prepare(pl.attn.back().data(), qkv, ldq, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
     }
     prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
     CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), mask, iso_p, o, lse, stream_));
@@ -269,7 +274,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     CK(run_gemm(g));
   }
   *h_out = h2;
-  if (rec) *rec = TBRec{Q, lora_idx, B, L, h0, x1, qkv, o, lse, h1, pre, mask, iso_p};
+  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, iso_p};
   return 0;
 }
 
@@ -393,6 +398,7 @@ int Estimator::forward(const EstimatorIO& io, cudaStream_t st) {
 
 int Estimator::forward_impl(const EstimatorIO& io) {
   const int B = io.B, T = io.T, T2 = (T + 1) / 2;
+  training_ = io.training != 0;
   gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0; wg_idx_ = 0;
   stages_.clear();
   const int nres = n_resnets();
@@ -541,8 +547,8 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_layernorm_bwd(tmp.dx, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
-                            stream_));
+    CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+                             stream_));
     ++launches_;
   }
   {
@@ -553,7 +559,7 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     Plan& pl = *plan_;
     if ((size_t)attn_idx_ >= pl.attn.size()) {
       pl.attn.emplace_back(attn_plan_bytes());
-      if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
+      if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, t.ldq, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
     }
     prof_begin(2, 10.0 * t.B * 8.0 * (double)t.L * t.L * 64);
@@ -561,36 +567,34 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     prof_end();
     launches_ += 3;
   }
-  if (cfg.lora_r > 0) {
-    {  // u = x1 A_cat^T, v = dqkv B_blk^T  ([M][64] each, columns p*r+j)
-      GemmArgs g = linear_args(t.x1, M, 256, get(Q + ".acat16", cfg.bf16, 64L * 256), 64, tmp.u16, 0);
-      CK(run_gemm(g));
-      GemmArgs g2 = linear_args(tmp.dqkv, M, 1536, get(Q + ".bblk16", cfg.bf16, 64L * 1536), 64, tmp.v16, 0);
-      CK(run_gemm(g2));
-    }
-    if (!dry_) {
-      Plan& pl = *plan_;
-      if ((size_t)wg_idx_ >= pl.wgrads.size()) {
-        pl.wgrads.emplace_back(lora_wgrad_plan_bytes());
-        if (lora_wgrad_prepare(pl.wgrads.back().data(), tmp.dqkv, t.x1, tmp.u16, tmp.v16, M, cfg.lora_r, tmp.wg_scratch,
-                               cfg.bf16, error_buf(), error_buf_len()))
-          return -1;
-      }
-      prof_begin(4, 2.0 * M * 64.0 * (1536 + 256));
-      CKL(lora_wgrad_launch(pl.wgrads[wg_idx_++].data(), lora_table_dev_ + t.lora_idx, grad_scale, grad_scale_dev_,
-                            stream_));
-      prof_end();
-      launches_ += 2;
-    }
-  }
-  if (need_input_grad) {
-    GemmArgs g = linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, tmp.dx, 0);
+  // dx1 = dqkv W_eff and, with LoRA, v = dqkv B_blk^T as 64 extra output columns of the same GEMM
+  const bool lora = cfg.lora_r > 0;
+  const long ldx = lora ? 320 : 256;
+  if (lora || need_input_grad) {
+    GemmArgs g = lora ? linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t_ext", cfg.bf16, 320L * 1536), 320, tmp.dxe, 0)
+                      : linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, tmp.dxe, 0);
     CK(run_gemm(g));
-    if (!dry_) {
-      CKL(launch_layernorm_bwd(tmp.dx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
-                              stream_));
-      ++launches_;
+  }
+  if (lora && !dry_) {
+    Plan& pl = *plan_;
+    if ((size_t)wg_idx_ >= pl.wgrads.size()) {
+      pl.wgrads.emplace_back(lora_wgrad_plan_bytes());
+      const uint16_t* u = reinterpret_cast<const uint16_t*>(t.qkv) + 1536;
+      const uint16_t* v = reinterpret_cast<const uint16_t*>(tmp.dxe) + 256;
+      if (lora_wgrad_prepare(pl.wgrads.back().data(), tmp.dqkv, t.x1, u, t.ldq, v, ldx, M, cfg.lora_r, tmp.wg_scratch,
+                             cfg.bf16, error_buf(), error_buf_len()))
+        return -1;
     }
+    prof_begin(4, 2.0 * M * 64.0 * (1536 + 256));
+    CKL(lora_wgrad_launch(pl.wgrads[wg_idx_++].data(), lora_table_dev_ + t.lora_idx, grad_scale, grad_scale_dev_,
+                          stream_));
+    prof_end();
+    launches_ += 2;
+  }
+  if (need_input_grad && !dry_) {
+    CKL(launch_layernorm_bwd(tmp.dxe, ldx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+                             stream_));
+    ++launches_;
   }
   return 0;
 }
@@ -648,8 +652,7 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   tmp.dc = alloc(MT * 256 * 2);
   tmp.da = alloc(MT * 256 * 2);
   tmp.wg_scratch = (float*)alloc(lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1) * 4);
-  tmp.u16 = alloc(MT * 64 * 2);
-  tmp.v16 = alloc(MT * 64 * 2);
+  tmp.dxe = alloc(MT * 320 * 2);
   float* dh32 = (float*)alloc(MT * 256 * 4);
   void* dh16 = alloc(MT * 256 * 2);
   void* g16a = alloc(MT * 256 * 2);

@@ -38,12 +38,12 @@ struct BoundTensor { void* ptr; long numel; int dtype; };  // dtype: 0 f16, 1 bf
 
 struct ResnetRec { std::string prefix; int cin, B, L; void *c1, *c2; float *st1, *st2; const float* mask; };
 struct TBRec {
-  std::string prefix; int lora_idx, B, L; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
+  std::string prefix; int lora_idx, B, L; long ldq; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
   const float* mask; int iso_p;
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
-struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; void *u16, *v16; };
+struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; void* dxe; };
 
 struct PlanKey {
   int B, T, training; uintptr_t ws;
@@ -99,6 +99,7 @@ class Estimator {
   Plan* plan_ = nullptr;
   void* ws_ = nullptr;
   long ws_bytes_ = 0, ws_off_ = 0, fwd_ws_end_ = 0;
+  bool training_ = false;
   bool dry_ = false, missing_ = false, oom_ = false, have_fwd_ = false, lora_table_ready_ = false;
   int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0, wg_idx_ = 0;
   long launches_ = 0;

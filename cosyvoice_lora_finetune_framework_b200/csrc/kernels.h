@@ -45,7 +45,7 @@ int launch_euler_update(float* x, const float* d, const float* dt_arr, int step,
 int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, void* out, long M, int bf16,
                          cudaStream_t st);
 // dh = dres + LN'(dxn16; h_in); also writes the 16-bit copy dh16 (nullable)
-int launch_layernorm_bwd(const void* dxn16, const float* h_in, const float* gamma, const float* dres, float* dh,
+int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, const float* gamma, const float* dres, float* dh,
                          void* dh16, long M, int bf16, cudaStream_t st);
 // GroupNorm(8 groups of 32 channels, C=256) over the padded extent L of [B][L][256]
 int gn_num_splits(int B, int L);
@@ -66,9 +66,10 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
 struct AttnPlan;  // holds the encoded tensor maps
 int attn_plan_bytes();
 void attn_set_debug_buffer(void* p);   // profiling aid: 16 x int64 globaltimer stamps per CTA of the next forward plans
-int attn_fwd_prepare(void* plan, const void* qkv, int B, int L, int bf16, char* err, int errlen);
+int attn_fwd_prepare(void* plan, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen);
 int attn_fwd_launch(const void* plan, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st);
-int attn_bwd_prepare(void* plan, const void* qkv, const void* dout, int B, int L, int bf16, char* err, int errlen);
+int attn_bwd_prepare(void* plan, const void* qkv, long ldq, const void* dout, int B, int L, int bf16, char* err,
+                     int errlen);
 int attn_bwd_launch(const void* plan, const void* dout, const float* keymask, int iso_p, const void* o,
                     const float* lse, float* delta, void* dqkv, cudaStream_t st);
 
@@ -94,8 +95,8 @@ int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int b
 // dY^T u and x^T v (u = x A_cat^T, v = dY B_blk^T are produced by two engine GEMMs, [M][64] each).
 int lora_wgrad_plan_bytes();
 long lora_wgrad_scratch_floats(long M, int r);
-int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, const void* v16, long M, int r,
-                       float* scratch, int bf16, char* err, int errlen);
+int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, long ld_u, const void* v16,
+                       long ld_v, long M, int r, float* scratch, int bf16, char* err, int errlen);
 int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float grad_scale, const float* grad_scale_dev,
                       cudaStream_t st);
 

@@ -231,8 +231,8 @@ long lora_wgrad_scratch_floats(long M, int r) {
 }
 int lora_wgrad_plan_bytes() { return (int)sizeof(WgradParams); }
 
-int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, const void* v16, long M, int r,
-                       float* scratch, int bf16, char* err, int errlen) {
+int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, long ld_u, const void* v16,
+                       long ld_v, long M, int r, float* scratch, int bf16, char* err, int errlen) {
   WgradParams* p = reinterpret_cast<WgradParams*>(plan);
   memset(p, 0, sizeof(*p));
   p->M = M; p->r = r; p->bf16 = bf16;
@@ -244,8 +244,8 @@ int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void*
   int rc = 0;
   rc |= tma_encode_3d(&p->tmA[0], dqkv, bf16, 1536, (uint64_t)M, 1, 1536 * 2, (uint64_t)M * 1536 * 2, 64, 64, 1);
   rc |= tma_encode_3d(&p->tmA[1], xn, bf16, 256, (uint64_t)M, 1, 256 * 2, (uint64_t)M * 256 * 2, 64, 64, 1);
-  rc |= tma_encode_3d(&p->tmW[0], u16, bf16, 64, (uint64_t)M, 1, 64 * 2, (uint64_t)M * 64 * 2, 64, 64, 1);
-  rc |= tma_encode_3d(&p->tmW[1], v16, bf16, 64, (uint64_t)M, 1, 64 * 2, (uint64_t)M * 64 * 2, 64, 64, 1);
+  rc |= tma_encode_3d(&p->tmW[0], u16, bf16, 64, (uint64_t)M, 1, (uint64_t)ld_u * 2, (uint64_t)M * ld_u * 2, 64, 64, 1);
+  rc |= tma_encode_3d(&p->tmW[1], v16, bf16, 64, (uint64_t)M, 1, (uint64_t)ld_v * 2, (uint64_t)M * ld_v * 2, 64, 64, 1);
   if (rc) { if (err) snprintf(err, errlen, "lora wgrad: cuTensorMapEncodeTiled failed"); return -1; }
   return 0;
 }

@@ -69,7 +69,7 @@ int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, 
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __restrict__ dxn, const float* __restrict__ h_in,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __restrict__ dxn, long ld_dxn, const float* __restrict__ h_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres,
                                                             float* __restrict__ dh, uint16_t* __restrict__ dh16, long M,
                                                             int bf) {
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
   float x[8], g[8], d[8];
   load8_f32(h_in + row * 256 + lane * 8, x);
   load8_f32(gamma + lane * 8, g);
-  load8_h16(dxn + row * 256 + lane * 8, bf, d);
+  load8_h16(dxn + row * ld_dxn + lane * 8, bf, d);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += x[i];
@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
   if (dh) store8_f32(dh + row * 256 + lane * 8, d);
   if (dh16) store8_h16(dh16 + row * 256 + lane * 8, bf, d);
 }
-int launch_layernorm_bwd(const void* dxn16, const float* h_in, const float* gamma, const float* dres, float* dh,
+int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, const float* gamma, const float* dres, float* dh,
                          void* dh16, long M, int bf16, cudaStream_t st) {
-  launch_pdl(layernorm_bwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dxn16), h_in, gamma,
+  launch_pdl(layernorm_bwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dxn16), ld_dxn, h_in, gamma,
                                                                dres, dh, reinterpret_cast<uint16_t*>(dh16), M, bf16);
   LAUNCH_RET();
 }
