@@ -102,3 +102,35 @@ def test_sharded_streams_match_single_stream(streams):
             assert torch.allclose(g, ref_grads[k], atol=1e-7 + 1e-3 * float(ref_grads[k].abs().max())), k
     # golden tolerance as well
     assert abs(loss.item() - float(fx["loss"])) <= 1e-2 * float(fx["loss"])
+
+
+def test_long_ragged_utterances_T1500():
+    """BASELINE configs[4] shape class: T = 1500 padded frames with ragged lengths (L = 1500 / 750
+    attention, 12 / 6 key blocks), tiny estimator so the CPU oracle finishes in seconds."""
+    from oracle import flow_oracle as O
+    from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
+    from tests.helpers import lora_scaling_of
+    B, T = 2, 1500
+    est, sd, _ = build_estimator(1, 1, lora_r=8)
+    g = torch.Generator().manual_seed(42)
+    x1, mu = torch.randn(B, 80, T, generator=g), torch.randn(B, 80, T, generator=g)
+    spks, cond = torch.randn(B, 80, generator=g), torch.zeros(B, 80, T)
+    lengths = torch.tensor([1500, 611])
+    mask = (~O.make_pad_mask(lengths, T)).float().unsqueeze(1)
+    t_rand, z, cfg = torch.rand(B, 1, 1, generator=g), torch.randn(B, 80, T, generator=g), torch.tensor([0.9, 0.5])
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    ref_loss, _, _ = O.cfm_compute_loss(P, x1, mask, mu, spks, cond, None, t_rand, z, cfg, lora_scaling=lora_scaling_of(sd))
+    ref_loss.backward()
+    est = est.cuda().train()
+    cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
+    t = 1 - torch.cos(t_rand * 0.5 * 3.14159265359)
+    loss, _ = cfm._loss_with_noise(x1.cuda(), mask.cuda(), mu.cuda(), spks.cuda(), cond.cuda(), None, t.cuda(), z.cuda(),
+                                   (cfg > 0.2).cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
+    num = den = 0.0
+    for k, p in est.named_parameters():
+        if p.requires_grad:
+            num += float((p.grad.cpu() - P[k].grad).double().pow(2).sum())
+            den += float(P[k].grad.double().pow(2).sum())
+    assert (num / den) ** 0.5 <= 1e-2, (num / den) ** 0.5
