@@ -1,4 +1,4 @@
-// Flash-style attn1 self-attention on tcgen05 (sm_100a), forward and backward.
+// Flash-style attn1 self-attention forward on tcgen05 (sm_100a).
 //
 // Reference: Attention.forward, modules.py:253-293 -- softmax(q k^T * d^-1/2 + bias) v with
 // 8 heads x 64, bias = -1e10 on padded keys (utils.py:103-109) plus the optional prompt-isolation
@@ -6,253 +6,425 @@
 // materialised: the key mask comes from the [B,L] float mask and the isolation boundary from one
 // integer.
 //
-// Layout of one CTA (forward and dQ kernels): 128 query rows of one (batch, head); sixteen softmax
-// warps (warp w: TMEM lane quadrant w & 3 = 32 query rows, column group w >> 2), one MMA/TMA warp.
-//   S  = Q K^T   : A = Q [128 x 64] K-major, B = K block [128 keys x 64] K-major  -> TMEM cols [0,128)
-//   P  = softmax : tcgen05.ld row -> registers -> 16-bit, written to smem in the K-major
-//                  128B-swizzled operand layout (row = query, K = key)
-//   O' = P V     : A = P, B = V block [128 keys x 64] as MN-major operand            -> TMEM cols [128,192)
-// The running max / sum / output row live in registers of the row's thread (no cross-lane
-// shuffles: one thread sees its whole score row).
+// Structure (see attention.h): persistent CTAs over (batch, head, query-tile pair) items; per
+// warpgroup
+//   S  = Q K^T   : A = Q tile [128 x 64] (smem, K-major), B = key block [<=256 x 64] (smem, K-major)
+//                  -> TMEM columns [0, keys) of the warpgroup's 256-column region
+//   P  = softmax : thread = query row; two passes over the TMEM row (max, then exp2 / sum); P is
+//                  rounded to 16 bits and written back over S with tcgen05.st (A operand of P V)
+//   O' = P V     : A = P (TMEM), B = V block as MN-major smem operand -> TMEM columns [128, 192)
+// With L <= 256 there is one key block and the softmax is single-pass; longer sequences use the
+// online rescaling with the running max / sum / output row in registers of the row's thread.
 #include "kernels.h"
 #include "gemm.h"
-#include "common.cuh"
+#include "attention.h"
 #include <string.h>
 
 namespace cvflow {
 
-struct AttnPlan {
-  CUtensorMap tm_qkv;   // 16-bit [B][L][1536], box {64, 128, 1}
-  CUtensorMap tm_do;    // 16-bit [B][L][512],  box {64, 128, 1} (backward only)
-  int B, L, bf16;
-  long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
-};
 static long long* g_attn_dbg = nullptr;
 void attn_set_debug_buffer(void* p) { g_attn_dbg = reinterpret_cast<long long*>(p); }
 int attn_plan_bytes() { return (int)sizeof(AttnPlan); }
-
-static constexpr int kAQ = 128;   // query rows per CTA
-static constexpr int kAK = 128;   // keys per block
-static constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
-
-// named barrier among the 512 softmax threads only
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+int attn_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
 
 // ------------------------------------------------------------------------------------------
-// forward. 16 softmax warps: warp w owns TMEM lane quadrant w & 3 (query rows) and column group
-// w >> 2 (32 of the 128 keys of a block / 16 of the 64 output columns), so every scheduler has
-// four warps to interleave; warp 16 drives TMA and issues the MMAs.
+// kinfo[b] = kmax[b] = 1 + last index with mask != 0 (0 when the row is empty); behind the B extents
+// (rounded up to 4), kinfo[Bp + b*nw + i] = validity bits of keys [32 i, 32 i + 32) of sample b (nw = attn_kinfo_words(L))
 // ------------------------------------------------------------------------------------------
-struct AttnFwdSmem {
-  static constexpr int kQ = 0;
-  static constexpr int kK0 = 16384;
-  static constexpr int kK1 = 32768;
-  static constexpr int kV = 49152;
-  static constexpr int kP = 65536;          // 2 x 16 KB
-  static constexpr int kBar = 98304;        // barriers, then row-max / row-sum exchange
-  static constexpr int kMx = kBar + 128;    // float [2][128][4]
-  static constexpr int kBytes = kMx + 4096 + 1024;
+int attn_kinfo_words(int L) { return 8 * ((L + 255) / 256); }
+static int kinfo_bits_off(int B) { return (B + 3) & ~3; }   // bit words start 16-byte aligned
+long attn_kinfo_ints(int B, int L) { return kinfo_bits_off(B) + (long)B * attn_kinfo_words(L); }
+
+__global__ void __launch_bounds__(256) attn_kinfo_kernel(const float* __restrict__ mask, int Bp, int L, int nw,
+                                                         int* __restrict__ kinfo) {
+  __shared__ int s_max[8];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  int m = 0;
+  for (int i0 = 0; i0 < nw * 32; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    const bool ok = i < L && mask[(long)b * L + i] != 0.f;
+    if (ok) m = i + 1;   // i increases per thread: the last hit is the largest
+    const uint32_t word = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) kinfo[Bp + b * nw + (i >> 5)] = (int)word;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = max(m, s_max[i]);
+    kinfo[b] = m;
+  }
+}
+int launch_attn_kinfo(const float* mask, int B, int L, int* kinfo, cudaStream_t st) {
+  attn_kinfo_kernel<<<B, 256, 0, st>>>(mask, kinfo_bits_off(B), L, attn_kinfo_words(L), kinfo);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+struct FwdSmem {
+  static constexpr int kQ = 0;               // [2 stages][2 tiles][16 KB]
+  static constexpr int kKV = 65536;          // [2 slots][K 32 KB | V 32 KB]
+  static constexpr int kSlot = 65536;
+  static constexpr int kO = 196608;          // [2 warpgroups][16 KB] output staging for the TMA store
+  static constexpr int kBar = 229376;
+  static constexpr int kBytes = kBar + 256 + 1024;
 };
-static constexpr int kFwdThreads = 544;
+static constexpr int kFwdKB = 256;   // keys per block
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
-attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
+// one 32- (or 16-) column chunk of the softmax's second pass: P = 2^(s c - m) on the valid keys, row sum,
+// 16-bit P stored back into TMEM as the A operand of P V
+template <int NC>
+__device__ __forceinline__ void fwd_softmax_chunk(uint32_t t_s, uint32_t t_p, uint32_t vw, float m_use, float& rs0, float& rs1,
+                                                  int bf) {
+  uint32_t v[32];
+  if (NC == 32) {
+    tmem_ld_32x32b_x32(t_s, v);
+  } else {
+    uint32_t v16[16];
+    tmem_ld_32x32b_x16(t_s, v16);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v16[j];
+  }
+  tmem_ld_wait();
+  float p[NC];
+  const uint32_t full = NC == 32 ? 0xffffffffu : 0xffffu;
+  if ((vw & full) == full) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 2) {
+      float a0, a1;
+      ffma2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), kAttnScaleLog2, -m_use);
+      p[j] = exp2_fast(a0);
+      p[j + 1] = exp2_fast(a1);
+      fadd2(rs0, rs1, p[j], p[j + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      p[j] = ((vw >> j) & 1u) ? exp2_fast(fmaf(__uint_as_float(v[j]), kAttnScaleLog2, -m_use)) : 0.f;
+      rs0 += p[j];
+    }
+  }
+  if (NC == 32) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack2_h16(p[2 * j], p[2 * j + 1], bf);
+    tmem_st_32x32b_x16(t_p, pk);
+  } else {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack2_h16(p[2 * j], p[2 * j + 1], bf);
+    tmem_st_32x32b_x8(t_p, pk);
+  }
+}
+template <int NC>
+__device__ __forceinline__ float fwd_max_chunk(uint32_t t_s, uint32_t vw, float m_loc) {
+  uint32_t v[32];
+  if (NC == 32) {
+    tmem_ld_32x32b_x32(t_s, v);
+  } else {
+    uint32_t v16[16];
+    tmem_ld_32x32b_x16(t_s, v16);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v16[j];
+  }
+  tmem_ld_wait();
+  const uint32_t full = NC == 32 ? 0xffffffffu : 0xffffu;
+  if ((vw & full) == full) {   // four independent FMNMX3 chains
+    float m1 = m_loc, m2 = m_loc, m3 = m_loc;
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+      m_loc = fmax3(m_loc, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+      m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+    }
+    m_loc = fmaxf(fmaxf(m_loc, m1), fmaxf(m2, m3));
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if ((vw >> j) & 1u) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
+  }
+  return m_loc;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ kmax_arr, int iso_p,
                 uint16_t* __restrict__ o_out, float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar = base + AttnFwdSmem::kBar;
-  const uint32_t bar_q = bar, bar_k0 = bar + 8, bar_k1 = bar + 16, bar_v = bar + 24, bar_s = bar + 32,
-                 bar_p = bar + 40, bar_o = bar + 48, tmem_slot = bar + 56;
-  float* mx = reinterpret_cast<float*>(gbase + AttnFwdSmem::kMx);
+  const uint32_t bar = base + FwdSmem::kBar;
+  auto q_full = [&](int s) { return bar + 8u * s; };
+  auto q_empty = [&](int s) { return bar + 16u + 8u * s; };
+  auto kv_full = [&](int s) { return bar + 32u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 48u + 8u * s; };
+  auto s_full = [&](int w) { return bar + 64u + 8u * w; };
+  auto p_full = [&](int w) { return bar + 80u + 8u * w; };
+  auto o_full = [&](int w) { return bar + 96u + 8u * w; };
+  auto o_free = [&](int w) { return bar + 112u + 8u * w; };
+  const uint32_t skew_bar = bar + 128u;
+  const uint32_t tmem_slot = bar + 136u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
   const int L = plan.L, bf = plan.bf16;
-  const int nkb = (L + kAK - 1) / kAK;
-  long long* dbg = plan.dbg ? plan.dbg + ((long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  const int npairs = (L + 255) / 256;
+  const int n_items = plan.B * 8 * npairs;
+  long long* dbg = plan.dbg ? plan.dbg + (long)blockIdx.x * 32 : nullptr;
   auto stamp = [&](int k) {
     if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
   };
-  if (threadIdx.x == 0) stamp(0);
+  if (threadIdx.x == 0) { stamp(0); if (dbg) dbg[30] = clock64(); }
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_k0, 1); mbar_init(bar_k1, 1); mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 512); mbar_init(bar_o, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1); mbar_init(q_empty(s), 2);
+      mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 128);
+      mbar_init(o_full(s), 1); mbar_init(o_free(s), 128);
+    }
+    mbar_init(skew_bar, 128);
     fence_barrier_init();
     tma_prefetch_desc(&plan.tm_qkv);
+    tma_prefetch_desc(&plan.tm_o);
   }
-  if (warp == 16) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
   if (threadIdx.x == 0) stamp(1);
   pdl_wait();
   pdl_launch();
   if (threadIdx.x == 0) stamp(2);
 
-  if (warp == 16) {
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
+      int qs = 0, ring = 0;
+      uint32_t qph = 0, rph = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);   // extent of the next item: load issued early
+        if (!a.act[0]) continue;
+        mbar_wait(q_empty(qs), qph ^ 1u);
+        const int ntile = a.act[1] ? 2 : 1;
+        mbar_expect_tx(q_full(qs), (uint32_t)ntile * 16384u);
+        for (int t = 0; t < ntile; ++t)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(base + FwdSmem::kQ + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, q_full(qs), a.h * 64,
+                        (2 * a.pair + t) * 128 + hf * 64, a.b);
+        const int nkb = (a.ext + kFwdKB - 1) / kFwdKB;
+        for (int blk = 0; blk < nkb; ++blk) {
+          const int k0 = blk * kFwdKB;
+          const int keb = min(kFwdKB, a.ext - k0);
+          const int nbox = (keb + 63) >> 6;
+          mbar_wait(kv_empty(ring), rph ^ 1u);
+          mbar_expect_tx(kv_full(ring), (uint32_t)nbox * 16384u);
+          const uint32_t slot = base + FwdSmem::kKV + ring * FwdSmem::kSlot;
+          for (int x = 0; x < nbox; ++x) {
+            tma_load_3d(slot + x * 8192, &plan.tm_qkv, kv_full(ring), 512 + a.h * 64, k0 + x * 64, a.b);
+            tma_load_3d(slot + 32768 + x * 8192, &plan.tm_qkv, kv_full(ring), 1024 + a.h * 64, k0 + x * 64, a.b);
+          }
+          if (++ring == 2) { ring = 0; rph ^= 1u; }
+        }
+        if (++qs == 2) { qs = 0; qph ^= 1u; }
+      }
+    }
+  } else if (warp >= 9) {
+    // ---------------- MMA issuer of warpgroup w ----------------
+    if (lane == 0) {
+      const int w = warp - 9;
+      const uint32_t treg = tmem + (uint32_t)(w * 256);
       const uint32_t idesc_o = umma_idesc_f16(bf, 128, 64, 0, 1);
-      mbar_expect_tx(bar_q, 16384);
-      tma_load_3d(base + AttnFwdSmem::kQ, &plan.tm_qkv, bar_q, h * 64, q0, b);
-      mbar_expect_tx(bar_k0, 16384);
-      tma_load_3d(base + AttnFwdSmem::kK0, &plan.tm_qkv, bar_k0, 512 + h * 64, 0, b);
-      mbar_expect_tx(bar_v, 16384);
-      tma_load_3d(base + AttnFwdSmem::kV, &plan.tm_qkv, bar_v, 1024 + h * 64, 0, b);
-      mbar_wait(bar_q, 0);
-      for (int i = 0; i < nkb; ++i) {
-        const uint32_t sK = base + ((i & 1) ? AttnFwdSmem::kK1 : AttnFwdSmem::kK0);
-        if (i + 1 < nkb) {  // prefetch next K block (its buffer was last read by S(i-1), long complete)
-          const uint32_t bk = ((i + 1) & 1) ? bar_k1 : bar_k0;
-          mbar_expect_tx(bk, 16384);
-          tma_load_3d(base + (((i + 1) & 1) ? AttnFwdSmem::kK1 : AttnFwdSmem::kK0), &plan.tm_qkv, bk,
-                      512 + h * 64, (i + 1) * kAK, b);
-        }
-        mbar_wait((i & 1) ? bar_k1 : bar_k0, (uint32_t)((i >> 1) & 1));
-        tc_fence_after();
-        {
-          const uint64_t dq = umma_desc_kmajor_sw128(base + AttnFwdSmem::kQ);
-          const uint64_t dk = umma_desc_kmajor_sw128(sK);
+      int qs = 0, ring = 0;
+      uint32_t qph = 0, rph = 0, n = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);
+        if (!a.act[0]) continue;
+        mbar_wait(q_full(qs), qph);
+        if (w == 0 && n == 0) stamp(17);
+        const int nkb = (a.ext + kFwdKB - 1) / kFwdKB;
+        const uint32_t sQ = base + FwdSmem::kQ + qs * 32768 + w * 16384;
+        for (int blk = 0; blk < nkb; ++blk) {
+          const int keb = min(kFwdKB, a.ext - blk * kFwdKB);
+          const uint32_t slot = base + FwdSmem::kKV + ring * FwdSmem::kSlot;
+          mbar_wait(kv_full(ring), rph);
+          if (w == 0 && n == 0) stamp(18);
+          if (a.act[w]) {
+            mbar_wait(o_free(w), (n & 1u) ^ 1u);   // the warpgroup has drained O' (and S / P) of its previous block
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_f16(bf, 128, keb, 0, 0);
+            const uint64_t dq = umma_desc_kmajor_sw128(sQ);
+            const uint64_t dk = umma_desc_kmajor_sw128(slot);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(treg, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            umma_commit(s_full(w));
+            if (blk == nkb - 1) umma_commit(q_empty(qs));
+            mbar_wait(p_full(w), n & 1u);
+            tc_fence_after();
+            const int nk = keb >> 4;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t dv = umma_desc_mnmajor_sw128(slot + 32768 + k * 2048, 1024);
+              umma_f16_ts(treg + 128, treg + (uint32_t)(k * 8), dv, idesc_o, k > 0);
+            }
+            umma_commit(o_full(w));
+            umma_commit(kv_empty(ring));
+            ++n;
+          } else {
+            if (blk == nkb - 1) mbar_arrive(q_empty(qs));
+            mbar_arrive(kv_empty(ring));
+          }
+          if (++ring == 2) { ring = 0; rph ^= 1u; }
         }
-        umma_commit(bar_s);
-        mbar_wait(bar_p, (uint32_t)(i & 1));
-        mbar_wait(bar_v, (uint32_t)(i & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t dp = umma_desc_kmajor_sw128(base + AttnFwdSmem::kP + (k >> 2) * 16384) + 2 * (k & 3);
-          const uint64_t dv = umma_desc_mnmajor_sw128(base + AttnFwdSmem::kV + k * 2048, 1024);
-          umma_f16_ss(tmem_O, dp, dv, idesc_o, k > 0);
-        }
-        umma_commit(bar_o);
-        if (i + 1 < nkb) {
-          mbar_wait(bar_o, (uint32_t)(i & 1));  // V buffer is free once P V has completed
-          mbar_expect_tx(bar_v, 16384);
-          tma_load_3d(base + AttnFwdSmem::kV, &plan.tm_qkv, bar_v, 1024 + h * 64, (i + 1) * kAK, b);
-        }
+        if (++qs == 2) { qs = 0; qph ^= 1u; }
       }
     }
   } else {
-    const int qd = warp & 3, g = warp >> 2;
-    const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
-    const int qi = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[16];
+    // ---------------- row warpgroups: thread = query row ----------------
+    const int w = warp >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const int wtid = threadIdx.x & 127;
+    const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
+    uint32_t n = 0;
+    const int nwords = 8 * npairs;
+    const int* bits_base = kmax_arr + ((plan.B + 3) & ~3);
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+    uint4 nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
+    uint4 nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const AttnItem a = nxt;
+      const uint4 fb0 = nb0, fb1 = nb1;   // validity words of the item's first key block
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);
+      nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
+      nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
+      const int qi = (2 * a.pair + w) * 128 + r;
+      uint16_t* dst = o_out + ((long)a.b * L + qi) * 512 + a.h * 64;
+      if (!a.act[w]) {   // tile of padding rows only: defined zeros instead of the reference's masked garbage
+        if (qi < L) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = 0.f;
-    const bool q_side = qi < iso_p;
-    uint8_t* sP = gbase + AttnFwdSmem::kP;
-
-    for (int i = 0; i < nkb; ++i) {
-      const int k0 = i * kAK;
-      uint32_t vw;
-      {  // validity bits of this warp's 32 keys
-        const int key = k0 + g * 32 + lane;
-        const bool ok = key < L && keymask[(long)b * L + key] != 0.f;
-        vw = __ballot_sync(0xffffffffu, ok);
-        if (iso_p > 0) {
-          const int nb = iso_p - (k0 + g * 32);
-          const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          vw &= q_side ? below : ~below;
+          for (int u = 0; u < 8; ++u) reinterpret_cast<uint4*>(dst)[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (lse_out) lse_out[((long)a.b * 8 + a.h) * L + qi] = INFINITY;
         }
+        continue;
       }
-      mbar_wait(bar_s, (uint32_t)(i & 1));
-      if (threadIdx.x == 0 && i < 2) stamp(3 + 4 * i);
-      tc_fence_after();
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(tmem_S + lane_addr + g * 32, v);
-      tmem_ld_wait();
-      float m_loc = -INFINITY;
-      const bool all_valid = vw == 0xffffffffu;   // warp-uniform: no per-element masking on the common path
-      if (all_valid) {
+      const uint4* bits = reinterpret_cast<const uint4*>(bits_base + (long)a.b * nwords);
+      const bool q_below = qi < iso_p;
+      float m_run = -INFINITY, l_run = 0.f;
+      float o[64];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if ((vw >> j) & 1u) m_loc = fmaxf(m_loc, __uint_as_float(v[j]));
-      }
-      float* mrow = mx + ((i & 1) * 128 + r) * 4;
-      mrow[g] = m_loc;
-      softmax_bar_sync();
-      if (threadIdx.x == 0 && i < 2) stamp(4 + 4 * i);
-      const float4 m4 = *reinterpret_cast<const float4*>(mrow);
-      const float m_blk = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2;
-      const float m_new = fmaxf(m_run, m_blk);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2_fast(m_run - m_use);
-      float p[32];
-      float rowsum = 0.f;
-      if (all_valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          p[j] = exp2_fast(fmaf(__uint_as_float(v[j]), kScaleLog2, -m_use));
-          rowsum += p[j];
+      for (int j = 0; j < 64; ++j) o[j] = 0.f;
+      const int nkb = (a.ext + kFwdKB - 1) / kFwdKB;
+      for (int blk = 0; blk < nkb; ++blk) {
+        const int k0 = blk * kFwdKB;
+        const int keb = min(kFwdKB, a.ext - k0);
+        const int nfull = keb >> 5;
+        const bool tail = (keb & 16) != 0;
+        uint32_t vw[8];
+        {
+          const uint4 b0 = blk == 0 ? fb0 : __ldg(bits + 2 * blk), b1 = blk == 0 ? fb1 : __ldg(bits + 2 * blk + 1);
+          vw[0] = b0.x; vw[1] = b0.y; vw[2] = b0.z; vw[3] = b0.w; vw[4] = b1.x; vw[5] = b1.y; vw[6] = b1.z; vw[7] = b1.w;
         }
-      } else {
+        uint32_t vt = 0u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pv = ((vw >> j) & 1u) ? exp2_fast(fmaf(__uint_as_float(v[j]), kScaleLog2, -m_use)) : 0.f;
-          p[j] = pv;
-          rowsum += pv;
+        for (int c = 0; c < 8; ++c) {
+          vw[c] = attn_iso_word(vw[c], k0 + 32 * c, iso_p, q_below);
+          if (c == nfull) vt = vw[c];
         }
+        mbar_wait(s_full(w), n & 1u);
+        const bool st_on = threadIdx.x == 0 && n < 2;
+        if (st_on) stamp(3 + 6 * n);
+        tc_fence_after();
+        // pass 1: row maximum over the valid keys of the block
+        float m_loc = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nfull) m_loc = fwd_max_chunk<32>(treg + (uint32_t)(c * 32), vw[c], m_loc);
+        if (tail) m_loc = fwd_max_chunk<16>(treg + (uint32_t)(nfull * 32), vt, m_loc);
+        if (st_on) stamp(4 + 6 * n);
+        const float m_new = fmaxf(m_run, m_loc * kAttnScaleLog2);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = exp2_fast(m_run - m_use);
+        // pass 2: P = 2^(s c - m), row sum, 16-bit P written over S
+        float rs0 = 0.f, rs1 = 0.f;
+        if (w == 1 && n == 0) mbar_wait(skew_bar, 0);   // one-shot stagger: the two warpgroups' exp phases alternate
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nfull) fwd_softmax_chunk<32>(treg + (uint32_t)(c * 32), treg + (uint32_t)(c * 16), vw[c], m_use, rs0, rs1, bf);
+        if (tail) fwd_softmax_chunk<16>(treg + (uint32_t)(nfull * 32), treg + (uint32_t)(nfull * 16), vt, m_use, rs0, rs1, bf);
+        if (w == 0 && n == 0) mbar_arrive(skew_bar);
+        const float rowsum = rs0 + rs1;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(w));
+        if (st_on) stamp(5 + 6 * n);
+        l_run = l_run * alpha + rowsum;
+        m_run = m_new;
+        // O' = P V of this block
+        mbar_wait(o_full(w), n & 1u);
+        if (st_on) stamp(6 + 6 * n);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(treg + 128u + (uint32_t)(hf * 32), ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[hf * 32 + j] = o[hf * 32 + j] * alpha + __uint_as_float(ov[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(o_free(w));
+        if (st_on) stamp(7 + 6 * n);
+        ++n;
       }
       {
-        uint8_t* chunk = sP + (g >> 1) * 16384 + r * 128;
+        // normalised output row -> 128B-swizzled staging tile -> TMA store (rows >= L are clipped by the tensor map)
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (g & 1) * 4 + u;
-          *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = pack8_h16(p + 8 * u, bf);
+        for (int j = 0; j < 64; ++j) o[j] *= inv;
+        const uint32_t stg = base + FwdSmem::kO + w * 16384;
+        if (wtid == 0) tma_store_wait_read();   // the previous item's store has finished reading the tile
+        wg_bar_sync(w);
+        const uint32_t rowaddr = stg + (uint32_t)r * 128u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 pk = pack8_h16(o + 8 * u, bf);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((u ^ (r & 7)) << 4)), "r"(pk.x),
+                       "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
         }
+        fence_proxy_async_smem();
+        wg_bar_sync(w);
+        if (wtid == 0) {
+          const int q0 = (2 * a.pair + w) * 128;
+          tma_store_3d(&plan.tm_o, stg, a.h * 64, q0, a.b);
+          if (q0 + 64 < L) tma_store_3d(&plan.tm_o, stg + 8192, a.h * 64, q0 + 64, a.b);
+          tma_store_commit();
+        }
+        if (lse_out && qi < L) lse_out[((long)a.b * 8 + a.h) * L + qi] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
       }
-      l_run = l_run * alpha + rowsum;   // partial sum over this thread's key group
-      m_run = m_new;
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(bar_p);
-      if (threadIdx.x == 0 && i < 2) stamp(5 + 4 * i);
-      // O' = P V of this block: this thread accumulates output columns [16g, 16g+16)
-      mbar_wait(bar_o, (uint32_t)(i & 1));
-      if (threadIdx.x == 0 && i < 2) stamp(6 + 4 * i);
-      tc_fence_after();
-      uint32_t ov[16];
-      __syncwarp();
-      tmem_ld_32x32b_x16(tmem_O + lane_addr + g * 16, ov);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = o[j] * alpha + __uint_as_float(ov[j]);
+      if (threadIdx.x == 0 && n <= 2) stamp(8 + 6 * (n - 1));
     }
-    // total row sum = sum of the four groups' partial sums (same running max in all four)
-    float* lrow = mx + ((nkb & 1) * 128 + r) * 4;
-    softmax_bar_sync();
-    lrow[g] = l_run;
-    softmax_bar_sync();
-    const float4 l4 = *reinterpret_cast<const float4*>(lrow);
-    const float l_tot = (l4.x + l4.y) + (l4.z + l4.w);
-    if (qi < L) {
-      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] *= inv;
-      uint16_t* dst = o_out + ((long)b * L + qi) * 512 + h * 64 + g * 16;
-      reinterpret_cast<uint4*>(dst)[0] = pack8_h16(o, bf);
-      reinterpret_cast<uint4*>(dst)[1] = pack8_h16(o + 8, bf);
-      if (lse_out && g == 0) lse_out[((long)b * 8 + h) * L + qi] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
-    }
+    if (wtid == 0) tma_store_wait_all();   // the staging tile must outlive the bulk stores
   }
-  if (threadIdx.x == 0) stamp(11);
+  if (threadIdx.x == 0) { stamp(15); if (dbg) dbg[31] = clock64(); }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 256); }
-  if (threadIdx.x == 0) stamp(12);
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 int attn_fwd_prepare(void* plan_, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen) {
@@ -260,20 +432,28 @@ int attn_fwd_prepare(void* plan_, const void* qkv, long ldq, int B, int L, int b
   memset(p, 0, sizeof(*p));
   p->B = B; p->L = L; p->bf16 = bf16; p->dbg = g_attn_dbg;
   int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, (uint64_t)ldq * 2,
-                        (uint64_t)L * ldq * 2, 64, 128, 1);
+                        (uint64_t)L * ldq * 2, 64, 64, 1);
   if (r) { if (err) snprintf(err, errlen, "attn: cuTensorMapEncodeTiled(qkv) failed (%d)", r); return -1; }
+  p->o_ptr = nullptr;
   return 0;
 }
 
-int attn_fwd_launch(const void* plan_, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st) {
-  const AttnPlan* p = reinterpret_cast<const AttnPlan*>(plan_);
+int attn_fwd_launch(void* plan_, const int* kinfo, int iso_p, void* o, float* lse, cudaStream_t st) {
+  AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);
+  if (p->o_ptr != o) {   // (re-)encode the output map when the destination moves
+    int r = tma_encode_3d(&p->tm_o, o, p->bf16, 512, (uint64_t)p->L, (uint64_t)p->B, 512 * 2, (uint64_t)p->L * 512 * 2, 64, 64, 1);
+    if (r) return -(int)cudaErrorInvalidValue;
+    p->o_ptr = o;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kBytes);
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kBytes);
     attr_done = true;
   }
-  dim3 grid((p->L + kAQ - 1) / kAQ, 8, p->B);
-  launch_pdl(attn_fwd_kernel, grid, kFwdThreads, AttnFwdSmem::kBytes, st, *p, keymask, iso_p, reinterpret_cast<uint16_t*>(o), lse);
+  const int n_items = p->B * 8 * ((p->L + 255) / 256);
+  const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
+  launch_pdl(attn_fwd_kernel, dim3((unsigned)grid), kAttnThreads, FwdSmem::kBytes, st, *p, kinfo, iso_p,
+             reinterpret_cast<uint16_t*>(o), lse);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -1,0 +1,122 @@
+// Shared pieces of the attn1 kernels (attention.cu forward, attention_bwd.cu backward).
+//
+// Work decomposition (all three tensor-core kernels): an *item* is one (batch b, head h, pair of
+// adjacent 128-row tiles). A persistent CTA walks items; its two row warpgroups (WG0 / WG1, 128
+// threads each, thread = row = TMEM lane) own the two row tiles of the item and share the column
+// blocks that a producer warp streams through a shared-memory ring with TMA. One MMA-issuing warp
+// per warpgroup drives that warpgroup's chain (score MMA -> row math -> output MMA), so while one
+// warpgroup is in its exp-heavy phase the tensor core runs the other one's MMAs.
+//
+// Padding is skipped, not computed: kmax[b] = 1 + (last index with mask != 0) bounds both the rows
+// and the columns that are touched. Rows >= kmax[b] are written as zeros (the reference computes
+// garbage there and masks it downstream, modules.py:1046-1049,1104-1106), columns >= kmax[b] carry
+// the -1e10 bias in the reference (utils.py:103-109), i.e. probability exactly 0 in fp32.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace cvflow {
+
+struct AttnPlan {
+  CUtensorMap tm_qkv;   // 16-bit [B][L][ldq] (q | k | v column ranges), box {64 cols, 64 rows, 1}
+  CUtensorMap tm_do;    // 16-bit [B][L][512], same box (backward only)
+  CUtensorMap tm_o;     // forward output [B][L][512], same box (TMA store)
+  const void* o_ptr;    // destination tm_o was encoded for
+  int B, L, bf16;
+  long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
+};
+
+static constexpr float kAttnScale = 0.125f;                               // d^-1/2, d = 64
+static constexpr float kAttnScaleLog2 = 0.125f * 1.4426950408889634f;     // d^-1/2 * log2(e)
+
+// thread layout shared by the kernels: warps 0-3 = WG0, 4-7 = WG1, 8 = TMA producer, 9 / 10 = MMA issuers
+static constexpr int kAttnThreads = 352;
+
+struct AttnItem {
+  int b, h, pair;       // pair of 128-row tiles: tiles 2*pair, 2*pair+1
+  int kmax;             // valid extent of sample b (0 = nothing valid)
+  int ext;              // kmax rounded up to 16 (MMA granularity), <= round16(L)
+  bool act[2];          // does tile (2*pair + w) contain a valid row?
+};
+__device__ __forceinline__ AttnItem attn_item(int it, int npairs, const int* __restrict__ kmax_arr) {
+  AttnItem a;
+  a.pair = it % npairs;
+  const int bh = it / npairs;
+  a.h = bh & 7;
+  a.b = bh >> 3;
+  a.kmax = kmax_arr[a.b];
+  a.ext = (a.kmax + 15) & ~15;
+  a.act[0] = (2 * a.pair) * 128 < a.kmax;
+  a.act[1] = (2 * a.pair + 1) * 128 < a.kmax;
+  return a;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit, two K elements per 32-bit column, lane = row)
+// was written with tcgen05.st by the row threads, so P / dS never travel through shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// named barrier of one 128-thread row warpgroup (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, 128;" ::"r"(w + 1) : "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// validity bits of the 32 columns [c0, c0+32) for this warp: mask != 0 and below the valid extent
+__device__ __forceinline__ uint32_t attn_valid_word(const float* __restrict__ maskrow, int c0, int lane, int kmax) {
+  const int c = c0 + lane;
+  const bool ok = c < kmax && maskrow[c] != 0.f;
+  return __ballot_sync(0xffffffffu, ok);
+}
+// prompt-isolation (modules.py:844-879): a row on one side of the boundary p only sees columns on the same side
+__device__ __forceinline__ uint32_t attn_iso_word(uint32_t vw, int c0, int iso_p, bool row_below) {
+  if (iso_p <= 0) return vw;
+  const int nb = iso_p - c0;
+  const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
+  return vw & (row_below ? below : ~below);
+}
+
+// 3-input max (FMNMX3) and packed fp32x2 arithmetic (FFMA2 / FADD2): halve the issue slots of the row math
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (x0, x1) * s + t for both lanes of a packed pair
+__device__ __forceinline__ void ffma2(float& y0, float& y1, float x0, float x1, float s, float t) {
+  asm("{\n\t.reg .b64 rx, rs, rt, ry;\n\t"
+      "mov.b64 rx, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rt, {%5, %5};\n\t"
+      "fma.rn.f32x2 ry, rx, rs, rt;\n\tmov.b64 {%0, %1}, ry;\n\t}"
+      : "=f"(y0), "=f"(y1)
+      : "f"(x0), "f"(x1), "f"(s), "f"(t));
+}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
+int attn_num_sms();
+
+}  // namespace cvflow

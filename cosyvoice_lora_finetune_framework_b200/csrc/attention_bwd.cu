@@ -12,17 +12,10 @@
 // prompt-isolation boundary give P = 0 (reference modules.py:275-288 under autograd).
 #include "kernels.h"
 #include "gemm.h"
-#include "common.cuh"
+#include "attention.h"
 #include <string.h>
 
 namespace cvflow {
-
-struct AttnPlan {
-  CUtensorMap tm_qkv;
-  CUtensorMap tm_do;
-  int B, L, bf16;
-  long long* dbg;
-};
 
 static constexpr float kScale = 0.125f;
 static constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;

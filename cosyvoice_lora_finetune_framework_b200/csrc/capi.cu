@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 namespace cvflow {
 static thread_local char g_err[512] = "";
@@ -175,3 +176,37 @@ extern "C" CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, i
 }
 
 extern "C" CVFLOW_API int cvflow_debug_attention_stamps(void* buf) { attn_set_debug_buffer(buf); return CVFLOW_OK; }
+
+// ---------------------------------------------------------------------------------------------
+extern "C" CVFLOW_API int64_t cvflow_attention_scratch_ints(int32_t B, int32_t L) { return attn_kinfo_ints(B, L); }
+extern "C" CVFLOW_API int cvflow_attention_forward(const void* qkv, int64_t ldq, int32_t B, int32_t L, int32_t dtype,
+                                                   const float* keymask, int32_t* kmax_scratch, int32_t iso_p, void* o,
+                                                   float* lse, void* stream) {
+  if (!qkv || !keymask || !kmax_scratch || !o || B < 1 || L < 1 || ldq < 1536) {
+    set_error("cvflow_attention_forward: null/invalid argument");
+    return CVFLOW_ERR_ARG;
+  }
+  std::vector<uint8_t> plan(attn_plan_bytes());
+  if (attn_fwd_prepare(plan.data(), qkv, (long)ldq, B, L, dtype == CVFLOW_DTYPE_BF16, error_buf(), error_buf_len()))
+    return CVFLOW_ERR_ARG;
+  int r = launch_attn_kinfo(keymask, B, L, kmax_scratch, (cudaStream_t)stream);
+  if (!r) r = attn_fwd_launch(plan.data(), kmax_scratch, iso_p, o, lse, (cudaStream_t)stream);
+  if (r) { set_error("cvflow_attention_forward: %s", cudaGetErrorString((cudaError_t)(-r))); return CVFLOW_ERR_CUDA; }
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_attention_backward(const void* qkv, int64_t ldq, int32_t B, int32_t L, int32_t dtype,
+                                                    const float* keymask, int32_t* kmax_scratch, int32_t iso_p,
+                                                    const void* o, const float* lse, const void* dout,
+                                                    float* delta_scratch, void* dqkv, void* stream) {
+  if (!qkv || !keymask || !kmax_scratch || !o || !lse || !dout || !delta_scratch || !dqkv || B < 1 || L < 1 || ldq < 1536) {
+    set_error("cvflow_attention_backward: null/invalid argument");
+    return CVFLOW_ERR_ARG;
+  }
+  std::vector<uint8_t> plan(attn_plan_bytes());
+  if (attn_bwd_prepare(plan.data(), qkv, (long)ldq, dout, B, L, dtype == CVFLOW_DTYPE_BF16, error_buf(), error_buf_len()))
+    return CVFLOW_ERR_ARG;
+  int r = launch_attn_kinfo(keymask, B, L, kmax_scratch, (cudaStream_t)stream);
+  if (!r) r = attn_bwd_launch(plan.data(), dout, keymask, iso_p, o, lse, delta_scratch, dqkv, (cudaStream_t)stream);
+  if (r) { set_error("cvflow_attention_backward: %s", cudaGetErrorString((cudaError_t)(-r))); return CVFLOW_ERR_CUDA; }
+  return CVFLOW_OK;
+}

@@ -145,24 +145,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint
+// expires) instead of returning at once, so a waiting warp does not compete for issue slots with the warps
+// doing the math on its scheduler (a plain try_wait poll loop slowed the row warps of the attention kernel 4x).
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok;
 }
-// Bounded spin: a wrong descriptor / byte count must fault loudly rather than hang the box
-// (a hung GPU box is a strike). ~2^28 polls of a HW-sleeping try_wait is seconds, far beyond
-// any legitimate wait in these kernels.
+// Bounded wait: a wrong descriptor / byte count must fault loudly rather than hang the box
+// (a hung GPU box is a strike). Each try may park the thread for up to ~10 ms, so 2^9 tries is
+// seconds, far beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 9)) {
       printf("cvflow: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x,
              blockIdx.y, threadIdx.x, bar, parity);
       __trap();

@@ -212,8 +212,8 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   return 0;
 }
 
-int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, int iso_p,
-                      float** h_out, TBRec* rec) {
+int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, const int* kmax,
+                      int iso_p, float** h_out, TBRec* rec) {
   const long M = (long)B * L;
   // with LoRA in training the q/k/v GEMM also emits u = x1 A_cat^T as 64 extra output columns
   // (operand rows 1536..1599 of weff_ext), which the wgrad kernel consumes in the backward pass
@@ -245,7 +245,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       if (attn_fwd_prepare(pl.attn.back().data(), qkv, ldq, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
     }
     prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
-    CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), mask, iso_p, o, lse, stream_));
+    CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), kmax, iso_p, o, lse, stream_));
     prof_end();
     ++launches_;
   }
@@ -274,7 +274,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     CK(run_gemm(g));
   }
   *h_out = h2;
-  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, iso_p};
+  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p};
   return 0;
 }
 
@@ -290,7 +290,7 @@ int Estimator::stage_fwd(const std::string& S, int res_idx, const void* xin, lon
   for (int j = 0; j < cfg.n_blocks; ++j) {
     TBRec tr;
     const std::string Q = S + ".1." + std::to_string(j);
-    CK(tb_fwd(Q, tb_counter_++, h, B, L, mask, iso_p, &h, &tr));
+    CK(tb_fwd(Q, tb_counter_++, h, B, L, mask, mask == mask1_ ? kmax1_ : kmax2_, iso_p, &h, &tr));
     st.tbs.push_back(tr);
   }
   st.h_out = h;
@@ -413,9 +413,14 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   void* cat1 = alloc((long)B * T * 512 * 2);
   void* cat0 = alloc((long)B * T2 * 512 * 2);
   void* xd1 = alloc((long)B * T2 * 256 * 2);
+  kmax1_ = (int*)alloc(attn_kinfo_ints(B, T) * 4);
+  kmax2_ = (int*)alloc(attn_kinfo_ints(B, T2) * 4);
   mask1_ = mask1; mask2_ = mask2; cat1_ = cat1; cat0_ = cat0;
   if (!dry_) {
     CKL(launch_mask_down(io.mask, io.mask_nb, mask1, mask2, B, T, T2, stream_));
+    CKL(launch_attn_kinfo(mask1, B, T, kmax1_, stream_));
+    CKL(launch_attn_kinfo(mask2, B, T2, kmax2_, stream_));
+    launches_ += 2;
     CKL(launch_sinus_embed(io.t, io.t_nb, emb, B, stream_));
     CKL(launch_small_linear(emb, (const float*)get("time.w1", 2, 1024L * 320), (const float*)get("time.b1", 2, 1024), te1,
                            B, 320, 1024, 0, 1, stream_));

@@ -39,7 +39,7 @@ struct BoundTensor { void* ptr; long numel; int dtype; };  // dtype: 0 f16, 1 bf
 struct ResnetRec { std::string prefix; int cin, B, L; void *c1, *c2; float *st1, *st2; const float* mask; };
 struct TBRec {
   std::string prefix; int lora_idx, B, L; long ldq; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
-  const float* mask; int iso_p;
+  const float* mask; const int* kmax; int iso_p;
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
@@ -85,8 +85,8 @@ class Estimator {
   int backward_impl(const void* dpred16, float grad_scale);
   int resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L, const float* mask,
                  const float* tb, long tb_stride, float** h_out, ResnetRec* rec);
-  int tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, int iso_p, float** h_out,
-             TBRec* rec);
+  int tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, const int* kmax, int iso_p,
+             float** h_out, TBRec* rec);
   int stage_fwd(const std::string& S, int res_idx, const void* xin, long ld_in, int col0, int cin, int B, int L, int T,
                 const float* mask, int iso_len, float** h_out);
   int tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp);
@@ -119,6 +119,7 @@ class Estimator {
   void prof_begin(int cls, double flops);
   void prof_end();
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
+  int *kmax1_ = nullptr, *kmax2_ = nullptr;
   void *cat0_ = nullptr, *cat1_ = nullptr;
 };
 

@@ -67,7 +67,11 @@ struct AttnPlan;  // holds the encoded tensor maps
 int attn_plan_bytes();
 void attn_set_debug_buffer(void* p);   // profiling aid: 16 x int64 globaltimer stamps per CTA of the next forward plans
 int attn_fwd_prepare(void* plan, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen);
-int attn_fwd_launch(const void* plan, const float* keymask, int iso_p, void* o, float* lse, cudaStream_t st);
+// kinfo (attn_kinfo_ints(B, L) ints): [b] = kmax[b] = 1 + last index with keymask[b][.] != 0 -- rows and keys beyond
+// it are skipped (rows written as zeros) -- followed by the per-sample key validity bit words.
+long attn_kinfo_ints(int B, int L);
+int launch_attn_kinfo(const float* keymask, int B, int L, int* kinfo, cudaStream_t st);
+int attn_fwd_launch(void* plan, const int* kinfo, int iso_p, void* o, float* lse, cudaStream_t st);
 int attn_bwd_prepare(void* plan, const void* qkv, long ldq, const void* dout, int B, int L, int bf16, char* err,
                      int errlen);
 int attn_bwd_launch(const void* plan, const void* dout, const float* keymask, int iso_p, const void* o,

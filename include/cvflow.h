@@ -149,6 +149,25 @@ CVFLOW_API int cvflow_debug_attention_stamps(void* buf);
 CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* counts, double* flops, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------
+ * attn1 self-attention on its own (reference Attention.forward, modules.py:253-293): the kernels the
+ * estimator runs per transformer block, exposed for parity tests and reuse.
+ *   qkv   16-bit [B][L][ldq], columns [0,512) q | [512,1024) k | [1024,1536) v, 8 heads x 64
+ *   keymask fp32 [B][L] (0 = padded key, utils.py:103-109); iso_p = prompt-isolation boundary (0 = off)
+ *   kmax_scratch int32 [cvflow_attention_scratch_ints(B, L)] (written: per sample 1 + last valid index, then key
+ *   validity bit words)
+ *   o 16-bit [B][L][512]; lse fp32 [B][8][L] (base-2 log-sum-exp of the scaled scores, +inf on empty rows)
+ * backward: dout 16-bit [B][L][512]; delta_scratch fp32 [B][8][L]; dqkv 16-bit [B][L][1536].
+ * ------------------------------------------------------------------------------------------- */
+CVFLOW_API int64_t cvflow_attention_scratch_ints(int32_t B, int32_t L);
+CVFLOW_API int cvflow_attention_forward(const void* qkv, int64_t ldq, int32_t B, int32_t L, int32_t dtype,
+                                        const float* keymask, int32_t* kmax_scratch, int32_t iso_p, void* o, float* lse,
+                                        void* stream);
+CVFLOW_API int cvflow_attention_backward(const void* qkv, int64_t ldq, int32_t B, int32_t L, int32_t dtype,
+                                         const float* keymask, int32_t* kmax_scratch, int32_t iso_p, const void* o,
+                                         const float* lse, const void* dout, float* delta_scratch, void* dqkv,
+                                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * CFM passes (reference flow_model.py:94-204)
  * ------------------------------------------------------------------------------------------- */
 /* y = (1-(1-sigma_min) t) z + t x1            flow_model.py:154 */
