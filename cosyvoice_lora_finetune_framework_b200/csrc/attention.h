@@ -23,7 +23,9 @@ struct AttnPlan {
   CUtensorMap tm_qkv;   // 16-bit [B][L][ldq] (q | k | v column ranges), box {64 cols, 64 rows, 1}
   CUtensorMap tm_do;    // 16-bit [B][L][512], same box (backward only)
   CUtensorMap tm_o;     // forward output [B][L][512], same box (TMA store)
-  const void* o_ptr;    // destination tm_o was encoded for
+  CUtensorMap tm_qkv32; // as tm_qkv with box {64 cols, 32 rows, 1} (96-key blocks of the dQ kernel)
+  CUtensorMap tm_dqkv;  // backward output [B][L][1536], box {64, 64, 1} (TMA store)
+  const void* o_ptr;    // destination tm_o / tm_dqkv was encoded for
   int B, L, bf16;
   long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
 };

@@ -1,15 +1,21 @@
-// attn1 backward on tcgen05 (sm_100a): three launches per attention layer.
+// attn1 backward on tcgen05 (sm_100a): two launches per attention layer, both with the persistent
+// two-warpgroup structure of the forward kernel (attention.h).
 //
-//   delta[b,h,q] = sum_d dO*O                                   (HBM-bound prep pass)
-//   dQ kernel   : CTA = 128 queries, loops over key blocks      (rows = queries)
-//        S = Q K^T, dP = dO V^T  -> TMEM;  dS = P o (dP - delta) * d^-1/2  -> smem (16-bit)
-//        dQ += dS K                (A = dS K-major, B = K block as MN-major operand) in TMEM
-//   dK/dV kernel: CTA = 128 keys, loops over query blocks       (rows = keys)
-//        S^T = K Q^T, dP^T = V dO^T -> TMEM;  P^T, dS^T -> smem (16-bit)
-//        dV += P^T dO, dK += dS^T Q (B = dO / Q blocks as MN-major operands) in TMEM
+//   dQ kernel   : item = (b, h, pair of 128-query tiles); thread = query row; key blocks of <= 96
+//        delta = rowsum(dO o O) (fused here, also written out for the dK/dV kernel)
+//        S = Q K^T, dP = dO V^T                        -> TMEM [0,96) / [96,192)
+//        dS = P o (dP - delta) d^-1/2, P = 2^(s c - lse) -> 16-bit, stored over S with tcgen05.st
+//        dQ += dS K   (A = dS from TMEM, B = K block as MN-major smem operand) -> TMEM [192,256),
+//        accumulated in TMEM over the key blocks
+//   dK/dV kernel: item = (b, h, pair of 128-key tiles); thread = key row; query blocks of <= 64
+//        S^T = K Q^T, dP^T = V dO^T                    -> TMEM [0,64) / [64,128)
+//        P^T, dS^T -> 16-bit over S^T / dP^T
+//        dV += P^T dO, dK += dS^T Q (A from TMEM, B = dO / Q blocks as MN-major operands) -> [128,192) / [192,256)
 // P is recomputed from the stored base-2 log-sum-exp of the forward pass. Both kernels are
 // deterministic (no atomics). Masking matches the forward kernel: padded keys and the
-// prompt-isolation boundary give P = 0 (reference modules.py:275-288 under autograd).
+// prompt-isolation boundary give P = 0 (reference modules.py:275-288 under autograd). Rows at or
+// beyond the sample's valid extent are skipped: their dQ/dK/dV are written as zeros and their dO is
+// taken as zero (in the estimator every consumer of those rows is masked, so it is).
 #include "kernels.h"
 #include "gemm.h"
 #include "attention.h"
@@ -17,389 +23,566 @@
 
 namespace cvflow {
 
-static constexpr float kScale = 0.125f;
-static constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
-
-__device__ __forceinline__ void rows_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-static constexpr int kBwdThreads = 544;   // 16 row warps (quadrant = w & 3, column group = w >> 2) + 1 MMA/TMA warp
-
-// write 32 consecutive K-elements (columns c*32 .. c*32+31) of row r into a [128 x 128] 16-bit
-// K-major SW128 operand made of two 16 KB column chunks
-__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int r, int c, const float (&v)[32], int bf) {
-  uint8_t* chunk = tile + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int unit = (c & 1) * 4 + u;
-    *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = pack8_h16(v + 8 * u, bf);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// delta = rowsum(dO * O) per head
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, const uint16_t* __restrict__ O,
-                                                         float* __restrict__ delta, int L, long M, int bf) {
-  pdl_wait();
-  pdl_launch();
-  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float s = 0.f;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint4 a = *reinterpret_cast<const uint4*>(dO + row * 512 + lane * 16 + half * 8);
-    const uint4 b = *reinterpret_cast<const uint4*>(O + row * 512 + lane * 16 + half * 8);
-    float x[8], y[8];
-    unpack2_h16(a.x, bf, x[0], x[1]); unpack2_h16(a.y, bf, x[2], x[3]);
-    unpack2_h16(a.z, bf, x[4], x[5]); unpack2_h16(a.w, bf, x[6], x[7]);
-    unpack2_h16(b.x, bf, y[0], y[1]); unpack2_h16(b.y, bf, y[2], y[3]);
-    unpack2_h16(b.z, bf, y[4], y[5]); unpack2_h16(b.w, bf, y[6], y[7]);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s += x[e] * y[e];
-  }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  if ((lane & 3) == 0) {
-    const int h = lane >> 2;
-    const long b = row / L;
-    const int q = (int)(row - b * L);
-    delta[(b * 8 + h) * L + q] = s;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // dQ kernel
 // ------------------------------------------------------------------------------------------
+static constexpr int kDqKB = 96;    // keys per block
 struct DqSmem {
-  static constexpr int kQ = 0, kdO = 16384;
-  static constexpr int kK0 = 32768, kK1 = 49152, kV0 = 65536, kV1 = 81920;
-  static constexpr int kdS = 98304;   // 32 KB
-  static constexpr int kBar = 131072;
+  static constexpr int kQ = 0;                 // [2 stages][2 tiles][16 KB]
+  static constexpr int kdO = 65536;            // [2 stages][2 tiles][16 KB]
+  static constexpr int kKV = 131072;           // [2 slots][K 12 KB | V 12 KB]
+  static constexpr int kSlot = 24576;
+  static constexpr int kStg = 180224;          // [2 warpgroups][16 KB] output staging
+  static constexpr int kBar = 212992;
   static constexpr int kBytes = kBar + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
-                   const float* __restrict__ lse, const float* __restrict__ delta, uint16_t* __restrict__ dqkv) {
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ kinfo, int iso_p,
+                   const uint16_t* __restrict__ o_in, const uint16_t* __restrict__ do_in, const float* __restrict__ lse,
+                   float* __restrict__ delta_out, uint16_t* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar = base + DqSmem::kBar;
-  const uint32_t bar_q = bar, bar_kv0 = bar + 8, bar_kv1 = bar + 16, bar_sp = bar + 24, bar_ds = bar + 32,
-                 bar_dq = bar + 40, tmem_slot = bar + 48;
-  uint32_t* kvalid = reinterpret_cast<uint32_t*>(gbase + DqSmem::kBar + 64);
+  auto q_full = [&](int s) { return bar + 8u * s; };
+  auto q_empty = [&](int s) { return bar + 16u + 8u * s; };
+  auto kv_full = [&](int s) { return bar + 32u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 48u + 8u * s; };
+  auto s_full = [&](int w) { return bar + 64u + 8u * w; };
+  auto p_full = [&](int w) { return bar + 80u + 8u * w; };
+  auto acc_full = [&](int w) { return bar + 96u + 8u * w; };
+  auto acc_free = [&](int w) { return bar + 112u + 8u * w; };
+  const uint32_t tmem_slot = bar + 128u;
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int L = plan.L, bf = plan.bf16;
-  const int nkb = (L + 127) / 128;
+  const int npairs = (L + 255) / 256;
+  const int n_items = plan.B * 8 * npairs;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv1, 1); mbar_init(bar_sp, 1);
-    mbar_init(bar_ds, 512); mbar_init(bar_dq, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1); mbar_init(q_empty(s), 2);
+      mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 128);
+      mbar_init(acc_full(s), 1); mbar_init(acc_free(s), 128);
+    }
     fence_barrier_init();
+    tma_prefetch_desc(&plan.tm_qkv);
+    tma_prefetch_desc(&plan.tm_qkv32);
+    tma_prefetch_desc(&plan.tm_do);
+    tma_prefetch_desc(&plan.tm_dqkv);
   }
-  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dQ = tmem + 256;
   pdl_wait();
   pdl_launch();
 
-  if (warp == 16) {
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
+      int qs = 0, ring = 0;
+      uint32_t qph = 0, rph = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        if (!a.act[0]) continue;
+        mbar_wait(q_empty(qs), qph ^ 1u);
+        const int ntile = a.act[1] ? 2 : 1;
+        mbar_expect_tx(q_full(qs), (uint32_t)ntile * 32768u);
+        for (int t = 0; t < ntile; ++t)
+          for (int hf = 0; hf < 2; ++hf) {
+            const int row = (2 * a.pair + t) * 128 + hf * 64;
+            tma_load_3d(base + DqSmem::kQ + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, q_full(qs), a.h * 64, row, a.b);
+            tma_load_3d(base + DqSmem::kdO + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_do, q_full(qs), a.h * 64, row, a.b);
+          }
+        const int nkb = (a.ext + kDqKB - 1) / kDqKB;
+        for (int blk = 0; blk < nkb; ++blk) {
+          const int k0 = blk * kDqKB;
+          const int keb = min(kDqKB, a.ext - k0);
+          const int nbox = (keb + 31) >> 5;
+          mbar_wait(kv_empty(ring), rph ^ 1u);
+          mbar_expect_tx(kv_full(ring), (uint32_t)nbox * 8192u);
+          const uint32_t slot = base + DqSmem::kKV + ring * DqSmem::kSlot;
+          for (int x = 0; x < nbox; ++x) {
+            tma_load_3d(slot + x * 4096, &plan.tm_qkv32, kv_full(ring), 512 + a.h * 64, k0 + x * 32, a.b);
+            tma_load_3d(slot + 12288 + x * 4096, &plan.tm_qkv32, kv_full(ring), 1024 + a.h * 64, k0 + x * 32, a.b);
+          }
+          if (++ring == 2) { ring = 0; rph ^= 1u; }
+        }
+        if (++qs == 2) { qs = 0; qph ^= 1u; }
+      }
+    }
+  } else if (warp >= 9) {
+    // ---------------- MMA issuer of warpgroup w ----------------
+    if (lane == 0) {
+      const int w = warp - 9;
+      const uint32_t treg = tmem + (uint32_t)(w * 256);
       const uint32_t idesc_q = umma_idesc_f16(bf, 128, 64, 0, 1);
-      mbar_expect_tx(bar_q, 32768);
-      tma_load_3d(base + DqSmem::kQ, &plan.tm_qkv, bar_q, h * 64, q0, b);
-      tma_load_3d(base + DqSmem::kdO, &plan.tm_do, bar_q, h * 64, q0, b);
-      mbar_expect_tx(bar_kv0, 32768);
-      tma_load_3d(base + DqSmem::kK0, &plan.tm_qkv, bar_kv0, 512 + h * 64, 0, b);
-      tma_load_3d(base + DqSmem::kV0, &plan.tm_qkv, bar_kv0, 1024 + h * 64, 0, b);
-      mbar_wait(bar_q, 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i & 1;
-        const uint32_t sK = base + (s ? DqSmem::kK1 : DqSmem::kK0);
-        const uint32_t sV = base + (s ? DqSmem::kV1 : DqSmem::kV0);
-        mbar_wait(s ? bar_kv1 : bar_kv0, (uint32_t)((i >> 1) & 1));
-        tc_fence_after();
-        {
-          const uint64_t dq = umma_desc_kmajor_sw128(base + DqSmem::kQ);
-          const uint64_t dk = umma_desc_kmajor_sw128(sK);
-          const uint64_t ddo = umma_desc_kmajor_sw128(base + DqSmem::kdO);
-          const uint64_t dv = umma_desc_kmajor_sw128(sV);
+      int qs = 0, ring = 0;
+      uint32_t qph = 0, rph = 0, n = 0, m = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        if (!a.act[0]) continue;
+        mbar_wait(q_full(qs), qph);
+        const int nkb = (a.ext + kDqKB - 1) / kDqKB;
+        const uint32_t sQ = base + DqSmem::kQ + qs * 32768 + w * 16384;
+        const uint32_t sdO = base + DqSmem::kdO + qs * 32768 + w * 16384;
+        for (int blk = 0; blk < nkb; ++blk) {
+          const int keb = min(kDqKB, a.ext - blk * kDqKB);
+          const uint32_t sK = base + DqSmem::kKV + ring * DqSmem::kSlot;
+          const uint32_t sV = sK + 12288;
+          mbar_wait(kv_full(ring), rph);
+          if (a.act[w]) {
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_f16(bf, 128, keb, 0, 0);
+            const uint64_t dq = umma_desc_kmajor_sw128(sQ), dk = umma_desc_kmajor_sw128(sK);
+            const uint64_t ddo = umma_desc_kmajor_sw128(sdO), dv = umma_desc_kmajor_sw128(sV);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(treg, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_dP, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(treg + 96, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
+            umma_commit(s_full(w));
+            if (blk == nkb - 1) umma_commit(q_empty(qs));
+            mbar_wait(p_full(w), n & 1u);
+            if (blk == 0) mbar_wait(acc_free(w), (m & 1u) ^ 1u);   // the previous item's dQ has been read out
+            tc_fence_after();
+            const int nk = keb >> 4;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t db = umma_desc_mnmajor_sw128(sK + k * 2048, 1024);
+              umma_f16_ts(treg + 192, treg + (uint32_t)(k * 8), db, idesc_q, (blk > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(kv_empty(ring));
+            if (blk == nkb - 1) { umma_commit(acc_full(w)); ++m; }
+            ++n;
+          } else {
+            if (blk == nkb - 1) mbar_arrive(q_empty(qs));
+            mbar_arrive(kv_empty(ring));
+          }
+          if (++ring == 2) { ring = 0; rph ^= 1u; }
         }
-        umma_commit(bar_sp);
-        if (i + 1 < nkb) {
-          if (i >= 1) mbar_wait(bar_dq, (uint32_t)((i - 1) & 1));  // buffers of block i-1 are free
-          const int s2 = (i + 1) & 1;
-          const uint32_t bk = s2 ? bar_kv1 : bar_kv0;
-          mbar_expect_tx(bk, 32768);
-          tma_load_3d(base + (s2 ? DqSmem::kK1 : DqSmem::kK0), &plan.tm_qkv, bk, 512 + h * 64, (i + 1) * 128, b);
-          tma_load_3d(base + (s2 ? DqSmem::kV1 : DqSmem::kV0), &plan.tm_qkv, bk, 1024 + h * 64, (i + 1) * 128, b);
-        }
-        mbar_wait(bar_ds, (uint32_t)(i & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_desc_kmajor_sw128(base + DqSmem::kdS + (k >> 2) * 16384) + 2 * (k & 3);
-          const uint64_t db = umma_desc_mnmajor_sw128(sK + k * 2048, 1024);
-          umma_f16_ss(tmem_dQ, da, db, idesc_q, (i > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_dq);
+        if (++qs == 2) { qs = 0; qph ^= 1u; }
       }
     }
   } else {
-    const int qd = warp & 3, g = warp >> 2;
+    // ---------------- row warpgroups: thread = query row ----------------
+    const int w = warp >> 2, qd = warp & 3;
     const int r = qd * 32 + lane;
-    const int qi = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const bool q_side = qi < iso_p;
-    const long stat_idx = ((long)b * 8 + h) * L + qi;
-    const float my_lse = qi < L ? lse[stat_idx] : INFINITY;
-    const float my_delta = qi < L ? delta[stat_idx] : 0.f;
-    uint8_t* sdS = gbase + DqSmem::kdS;
-    for (int i = 0; i < nkb; ++i) {
-      const int k0 = i * 128;
-      uint32_t vw;
-      {
-        const int key = k0 + g * 32 + lane;
-        const bool ok = key < L && keymask[(long)b * L + key] != 0.f;
-        vw = __ballot_sync(0xffffffffu, ok);
-        if (iso_p > 0) {
-          const int nb = iso_p - (k0 + 32 * g);
-          const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          vw &= q_side ? below : ~below;
+    const int wtid = threadIdx.x & 127;
+    const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
+    const int nwords = 8 * npairs;
+    const int* bits_base = kinfo + ((plan.B + 3) & ~3);
+    uint32_t n = 0, m = 0;
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const AttnItem a = nxt;
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+      const int q0 = (2 * a.pair + w) * 128;
+      const int qi = q0 + r;
+      const long stat_idx = ((long)a.b * 8 + a.h) * L + qi;
+      if (!a.act[w]) {   // tile of padding rows only
+        if (qi < L) {
+          uint16_t* dst = dqkv + ((long)a.b * L + qi) * 1536 + a.h * 64;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) reinterpret_cast<uint4*>(dst)[u] = make_uint4(0u, 0u, 0u, 0u);
+          delta_out[stat_idx] = 0.f;
         }
+        continue;
       }
-      mbar_wait(bar_sp, (uint32_t)(i & 1));
-      if (i >= 1) mbar_wait(bar_dq, (uint32_t)((i - 1) & 1));  // dS tile no longer read by dQ MMA(i-1)
-      tc_fence_after();
-      uint32_t sv[32], pv[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(tmem_S + lane_addr + g * 32, sv);
-      tmem_ld_32x32b_x32(tmem_dP + lane_addr + g * 32, pv);
-      tmem_ld_wait();
-      float ds[32];
-      // ds = P (dP - delta) d^-1/2 with the scale folded into the exponent: 2^(s c - (lse - log2 d^-1/2))
-      const float lse_s = my_lse + 3.0f;   // -log2(0.125) = 3
-      if (vw == 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          ds[j] = exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_s)) * (__uint_as_float(pv[j]) - my_delta);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          ds[j] = ((vw >> j) & 1u)
-                      ? exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_s)) * (__uint_as_float(pv[j]) - my_delta)
-                      : 0.f;
-      }
-      store_row_chunk(sdS, r, g, ds, bf);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(bar_ds);
-    }
-    mbar_wait(bar_dq, (uint32_t)((nkb - 1) & 1));
-    tc_fence_after();
-    {
-      uint32_t v[16];
-      __syncwarp();
-      tmem_ld_32x32b_x16(tmem_dQ + lane_addr + g * 16, v);
-      tmem_ld_wait();
+      // delta = rowsum(dO o O) and the row's log-sum-exp
+      float my_delta = 0.f, my_lse = INFINITY;
       if (qi < L) {
-        float f[16];
+        if (qi < a.kmax) {
+          my_lse = lse[stat_idx];
+          const uint4* po = reinterpret_cast<const uint4*>(o_in + ((long)a.b * L + qi) * 512 + a.h * 64);
+          const uint4* pd = reinterpret_cast<const uint4*>(do_in + ((long)a.b * L + qi) * 512 + a.h * 64);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        uint16_t* dst = dqkv + ((long)b * L + qi) * 1536 + h * 64 + g * 16;
-        reinterpret_cast<uint4*>(dst)[0] = pack8_h16(f, bf);
-        reinterpret_cast<uint4*>(dst)[1] = pack8_h16(f + 8, bf);
+          for (int u = 0; u < 8; ++u) {
+            const uint4 x = __ldg(po + u), y = __ldg(pd + u);
+            float xa, xb, ya, yb;
+            unpack2_h16(x.x, bf, xa, xb); unpack2_h16(y.x, bf, ya, yb); my_delta = fmaf(xa, ya, fmaf(xb, yb, my_delta));
+            unpack2_h16(x.y, bf, xa, xb); unpack2_h16(y.y, bf, ya, yb); my_delta = fmaf(xa, ya, fmaf(xb, yb, my_delta));
+            unpack2_h16(x.z, bf, xa, xb); unpack2_h16(y.z, bf, ya, yb); my_delta = fmaf(xa, ya, fmaf(xb, yb, my_delta));
+            unpack2_h16(x.w, bf, xa, xb); unpack2_h16(y.w, bf, ya, yb); my_delta = fmaf(xa, ya, fmaf(xb, yb, my_delta));
+          }
+        }   // else: padding row inside an active tile: P = 0 (lse = +inf), so dS = 0
+        delta_out[stat_idx] = my_delta;
+      }
+      const bool q_below = qi < iso_p;
+      const float lse_s = my_lse + 3.0f;   // d^-1/2 folded into the exponent: -log2(0.125) = 3
+      const int nkb = (a.ext + kDqKB - 1) / kDqKB;
+      const int* bits = bits_base + (long)a.b * nwords;
+      for (int blk = 0; blk < nkb; ++blk) {
+        const int k0 = blk * kDqKB;
+        const int keb = min(kDqKB, a.ext - k0);
+        uint32_t vw[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          vw[c] = (3 * blk + c < nwords) ? attn_iso_word((uint32_t)__ldg(bits + 3 * blk + c), k0 + 32 * c, iso_p, q_below) : 0u;
+        mbar_wait(s_full(w), n & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c * 32 < keb) {   // the last chunk of a block may hold only 16 live columns; the rest is masked by vw
+            uint32_t sv[32], pv[32];
+            tmem_ld_32x32b_x32(treg + (uint32_t)(c * 32), sv);
+            tmem_ld_32x32b_x32(treg + 96u + (uint32_t)(c * 32), pv);
+            tmem_ld_wait();
+            float ds[32];
+            if (vw[c] == 0xffffffffu) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float a0, a1;
+                ffma2(a0, a1, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]), kAttnScaleLog2, -lse_s);
+                ds[j] = exp2_fast(a0) * (__uint_as_float(pv[j]) - my_delta);
+                ds[j + 1] = exp2_fast(a1) * (__uint_as_float(pv[j + 1]) - my_delta);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                ds[j] = ((vw[c] >> j) & 1u)
+                            ? exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, -lse_s)) * (__uint_as_float(pv[j]) - my_delta)
+                            : 0.f;
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack2_h16(ds[2 * j], ds[2 * j + 1], bf);
+            tmem_st_32x32b_x16(treg + (uint32_t)(c * 16), pk);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(w));
+        ++n;
+      }
+      // dQ of the tile: TMEM -> 16-bit -> swizzled staging tile -> TMA store
+      mbar_wait(acc_full(w), m & 1u);
+      tc_fence_after();
+      float dqv[64];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(treg + 192u + (uint32_t)(hf * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dqv[hf * 32 + j] = __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(acc_free(w));
+      ++m;
+      const uint32_t stg = base + DqSmem::kStg + w * 16384;
+      if (wtid == 0) tma_store_wait_read();
+      wg_bar_sync(w);
+      const uint32_t rowaddr = stg + (uint32_t)r * 128u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 pk = pack8_h16(dqv + 8 * u, bf);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((u ^ (r & 7)) << 4)), "r"(pk.x),
+                     "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      wg_bar_sync(w);
+      if (wtid == 0) {
+        tma_store_3d(&plan.tm_dqkv, stg, a.h * 64, q0, a.b);
+        if (q0 + 64 < L) tma_store_3d(&plan.tm_dqkv, stg + 8192, a.h * 64, q0 + 64, a.b);
+        tma_store_commit();
       }
     }
+    if (wtid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
 // dK / dV kernel
 // ------------------------------------------------------------------------------------------
+static constexpr int kDkvQB = 64;   // queries per block
 struct DkvSmem {
-  static constexpr int kK = 0, kV = 16384;
-  static constexpr int kQ0 = 32768, kQ1 = 49152, kdO0 = 65536, kdO1 = 81920;
-  static constexpr int kPT = 98304;    // 32 KB
-  static constexpr int kdST = 131072;  // 32 KB
-  static constexpr int kBar = 163840;
-  static constexpr int kBytes = kBar + 2304 + 1024;   // barriers + 2 x (lse, delta)[128]
+  static constexpr int kK = 0;                 // [2 stages][2 tiles][16 KB]
+  static constexpr int kV = 65536;             // [2 stages][2 tiles][16 KB]
+  static constexpr int kQdO = 131072;          // [3 slots][Q 8 KB | dO 8 KB]
+  static constexpr int kSlot = 16384;
+  static constexpr int kNumSlots = 3;
+  static constexpr int kStg = 180224;          // [2 warpgroups][16 KB] output staging
+  static constexpr int kStat = 212992;         // float [2 warpgroups][2 buffers][lse 64 | delta 64]
+  static constexpr int kBar = 215040;
+  static constexpr int kBytes = kBar + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const float* __restrict__ keymask, int iso_p,
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ kinfo, int iso_p,
                     const float* __restrict__ lse, const float* __restrict__ delta, uint16_t* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar = base + DkvSmem::kBar;
-  const uint32_t bar_kv = bar, bar_q0 = bar + 8, bar_q1 = bar + 16, bar_sp = bar + 24, bar_pd = bar + 32,
-                 bar_acc = bar + 40, tmem_slot = bar + 48;
-  float* s_lse = reinterpret_cast<float*>(gbase + DkvSmem::kBar + 256);    // [2][128]
-  float* s_delta = s_lse + 256;                                            // [2][128]
+  auto kv_full = [&](int s) { return bar + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 16u + 8u * s; };
+  auto c_full = [&](int s) { return bar + 32u + 8u * s; };     // 3 slots
+  auto c_empty = [&](int s) { return bar + 56u + 8u * s; };    // 3 slots
+  auto s_full = [&](int w) { return bar + 80u + 8u * w; };
+  auto p_full = [&](int w) { return bar + 96u + 8u * w; };
+  auto acc_full = [&](int w) { return bar + 112u + 8u * w; };
+  auto acc_free = [&](int w) { return bar + 128u + 8u * w; };
+  const uint32_t tmem_slot = bar + 144u;
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int L = plan.L, bf = plan.bf16;
-  const int nqb = (L + 127) / 128;
+  const int npairs = (L + 255) / 256;
+  const int n_items = plan.B * 8 * npairs;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q1, 1); mbar_init(bar_sp, 1);
-    mbar_init(bar_pd, 512); mbar_init(bar_acc, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 128);
+      mbar_init(acc_full(s), 1); mbar_init(acc_free(s), 128);
+    }
+    for (int s = 0; s < DkvSmem::kNumSlots; ++s) { mbar_init(c_full(s), 1); mbar_init(c_empty(s), 2); }
     fence_barrier_init();
+    tma_prefetch_desc(&plan.tm_qkv);
+    tma_prefetch_desc(&plan.tm_do);
+    tma_prefetch_desc(&plan.tm_dqkv);
   }
-  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const uint32_t tmem_ST = tmem, tmem_dPT = tmem + 128, tmem_dV = tmem + 256, tmem_dK = tmem + 320;
   pdl_wait();
   pdl_launch();
 
-  if (warp == 16) {
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(bf, 128, 128, 0, 0);
+      int ks = 0, ring = 0;
+      uint32_t kph = 0, rph = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        if (!a.act[0]) continue;
+        mbar_wait(kv_empty(ks), kph ^ 1u);
+        const int ntile = a.act[1] ? 2 : 1;
+        mbar_expect_tx(kv_full(ks), (uint32_t)ntile * 32768u);
+        for (int t = 0; t < ntile; ++t)
+          for (int hf = 0; hf < 2; ++hf) {
+            const int row = (2 * a.pair + t) * 128 + hf * 64;
+            tma_load_3d(base + DkvSmem::kK + ks * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, kv_full(ks), 512 + a.h * 64, row, a.b);
+            tma_load_3d(base + DkvSmem::kV + ks * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, kv_full(ks), 1024 + a.h * 64, row, a.b);
+          }
+        const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
+        for (int blk = 0; blk < nqb; ++blk) {
+          mbar_wait(c_empty(ring), rph ^ 1u);
+          mbar_expect_tx(c_full(ring), 16384u);
+          const uint32_t slot = base + DkvSmem::kQdO + ring * DkvSmem::kSlot;
+          tma_load_3d(slot, &plan.tm_qkv, c_full(ring), a.h * 64, blk * kDkvQB, a.b);
+          tma_load_3d(slot + 8192, &plan.tm_do, c_full(ring), a.h * 64, blk * kDkvQB, a.b);
+          if (++ring == DkvSmem::kNumSlots) { ring = 0; rph ^= 1u; }
+        }
+        if (++ks == 2) { ks = 0; kph ^= 1u; }
+      }
+    }
+  } else if (warp >= 9) {
+    // ---------------- MMA issuer of warpgroup w ----------------
+    if (lane == 0) {
+      const int w = warp - 9;
+      const uint32_t treg = tmem + (uint32_t)(w * 256);
       const uint32_t idesc_a = umma_idesc_f16(bf, 128, 64, 0, 1);
-      mbar_expect_tx(bar_kv, 32768);
-      tma_load_3d(base + DkvSmem::kK, &plan.tm_qkv, bar_kv, 512 + h * 64, k0, b);
-      tma_load_3d(base + DkvSmem::kV, &plan.tm_qkv, bar_kv, 1024 + h * 64, k0, b);
-      mbar_expect_tx(bar_q0, 32768);
-      tma_load_3d(base + DkvSmem::kQ0, &plan.tm_qkv, bar_q0, h * 64, 0, b);
-      tma_load_3d(base + DkvSmem::kdO0, &plan.tm_do, bar_q0, h * 64, 0, b);
-      mbar_wait(bar_kv, 0);
-      for (int i = 0; i < nqb; ++i) {
-        const int s = i & 1;
-        const uint32_t sQ = base + (s ? DkvSmem::kQ1 : DkvSmem::kQ0);
-        const uint32_t sdO = base + (s ? DkvSmem::kdO1 : DkvSmem::kdO0);
-        mbar_wait(s ? bar_q1 : bar_q0, (uint32_t)((i >> 1) & 1));
-        tc_fence_after();
-        {
-          const uint64_t dk = umma_desc_kmajor_sw128(base + DkvSmem::kK);
-          const uint64_t dq = umma_desc_kmajor_sw128(sQ);
-          const uint64_t dv = umma_desc_kmajor_sw128(base + DkvSmem::kV);
-          const uint64_t ddo = umma_desc_kmajor_sw128(sdO);
+      int ks = 0, ring = 0;
+      uint32_t kph = 0, rph = 0, n = 0, m = 0;
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const AttnItem a = nxt;
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        if (!a.act[0]) continue;
+        mbar_wait(kv_full(ks), kph);
+        const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
+        const uint32_t sK = base + DkvSmem::kK + ks * 32768 + w * 16384;
+        const uint32_t sV = base + DkvSmem::kV + ks * 32768 + w * 16384;
+        for (int blk = 0; blk < nqb; ++blk) {
+          const int qeb = min(kDkvQB, a.ext - blk * kDkvQB);
+          const uint32_t sQ = base + DkvSmem::kQdO + ring * DkvSmem::kSlot;
+          const uint32_t sdO = sQ + 8192;
+          mbar_wait(c_full(ring), rph);
+          if (a.act[w]) {
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_f16(bf, 128, qeb, 0, 0);
+            const uint64_t dk = umma_desc_kmajor_sw128(sK), dq = umma_desc_kmajor_sw128(sQ);
+            const uint64_t dv = umma_desc_kmajor_sw128(sV), ddo = umma_desc_kmajor_sw128(sdO);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_ST, dk + 2 * k, dq + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(treg, dk + 2 * k, dq + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_dPT, dv + 2 * k, ddo + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(treg + 64, dv + 2 * k, ddo + 2 * k, idesc_s, k > 0);
+            umma_commit(s_full(w));
+            if (blk == nqb - 1) umma_commit(kv_empty(ks));
+            mbar_wait(p_full(w), n & 1u);
+            if (blk == 0) mbar_wait(acc_free(w), (m & 1u) ^ 1u);
+            tc_fence_after();
+            const int nk = qeb >> 4;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t db = umma_desc_mnmajor_sw128(sdO + k * 2048, 1024);
+              umma_f16_ts(treg + 128, treg + (uint32_t)(k * 8), db, idesc_a, (blk > 0 || k > 0) ? 1u : 0u);
+            }
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t db = umma_desc_mnmajor_sw128(sQ + k * 2048, 1024);
+              umma_f16_ts(treg + 192, treg + 64u + (uint32_t)(k * 8), db, idesc_a, (blk > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(c_empty(ring));
+            if (blk == nqb - 1) { umma_commit(acc_full(w)); ++m; }
+            ++n;
+          } else {
+            if (blk == nqb - 1) mbar_arrive(kv_empty(ks));
+            mbar_arrive(c_empty(ring));
+          }
+          if (++ring == DkvSmem::kNumSlots) { ring = 0; rph ^= 1u; }
         }
-        umma_commit(bar_sp);
-        if (i + 1 < nqb) {
-          if (i >= 1) mbar_wait(bar_acc, (uint32_t)((i - 1) & 1));
-          const int s2 = (i + 1) & 1;
-          const uint32_t bq = s2 ? bar_q1 : bar_q0;
-          mbar_expect_tx(bq, 32768);
-          tma_load_3d(base + (s2 ? DkvSmem::kQ1 : DkvSmem::kQ0), &plan.tm_qkv, bq, h * 64, (i + 1) * 128, b);
-          tma_load_3d(base + (s2 ? DkvSmem::kdO1 : DkvSmem::kdO0), &plan.tm_do, bq, h * 64, (i + 1) * 128, b);
-        }
-        mbar_wait(bar_pd, (uint32_t)(i & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t dp = umma_desc_kmajor_sw128(base + DkvSmem::kPT + (k >> 2) * 16384) + 2 * (k & 3);
-          const uint64_t db = umma_desc_mnmajor_sw128(sdO + k * 2048, 1024);
-          umma_f16_ss(tmem_dV, dp, db, idesc_a, (i > 0 || k > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t ds = umma_desc_kmajor_sw128(base + DkvSmem::kdST + (k >> 2) * 16384) + 2 * (k & 3);
-          const uint64_t db = umma_desc_mnmajor_sw128(sQ + k * 2048, 1024);
-          umma_f16_ss(tmem_dK, ds, db, idesc_a, (i > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_acc);
+        if (++ks == 2) { ks = 0; kph ^= 1u; }
       }
     }
   } else {
-    const int qd = warp & 3, g = warp >> 2;
-    const int r = qd * 32 + lane;   // key row
-    const int kj = k0 + r;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const bool key_ok = kj < L && keymask[(long)b * L + kj] != 0.f;
-    const bool k_side = kj < iso_p;
-    uint8_t* sPT = gbase + DkvSmem::kPT;
-    uint8_t* sdST = gbase + DkvSmem::kdST;
-    for (int i = 0; i < nqb; ++i) {
-      const int q0 = i * 128;
-      if (threadIdx.x < 128) {
-        const int q = q0 + threadIdx.x;
-        const long idx = ((long)b * 8 + h) * L + q;
-        s_lse[(i & 1) * 128 + threadIdx.x] = q < L ? lse[idx] : INFINITY;
-        s_delta[(i & 1) * 128 + threadIdx.x] = q < L ? delta[idx] : 0.f;
+    // ---------------- row warpgroups: thread = key row ----------------
+    const int w = warp >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const int wtid = threadIdx.x & 127;
+    const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
+    const int nwords = 8 * npairs;
+    const int* bits_base = kinfo + ((plan.B + 3) & ~3);
+    float* stat = reinterpret_cast<float*>(gbase + DkvSmem::kStat) + w * 256;   // [2 buffers][lse 64 | delta 64]
+    uint32_t n = 0, m = 0;
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const AttnItem a = nxt;
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+      const int k0 = (2 * a.pair + w) * 128;
+      const int kj = k0 + r;
+      if (!a.act[w]) {   // tile of padding keys only
+        if (kj < L) {
+          uint16_t* dst = dqkv + ((long)a.b * L + kj) * 1536 + 512 + a.h * 64;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            reinterpret_cast<uint4*>(dst)[u] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4*>(dst + 512)[u] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        continue;
       }
-      rows_bar_sync();
-      const float* lse_i = s_lse + (i & 1) * 128 + g * 32;
-      const float* del_i = s_delta + (i & 1) * 128 + g * 32;
-      mbar_wait(bar_sp, (uint32_t)(i & 1));
-      if (i >= 1) mbar_wait(bar_acc, (uint32_t)((i - 1) & 1));
+      const bool key_ok = kj < a.kmax && ((__ldg(bits_base + (long)a.b * nwords + (kj >> 5)) >> (kj & 31)) & 1);
+      const bool k_below = kj < iso_p;
+      const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
+      const float* lse_row = lse + ((long)a.b * 8 + a.h) * L;
+      const float* del_row = delta + ((long)a.b * 8 + a.h) * L;
+      for (int blk = 0; blk < nqb; ++blk) {
+        const int q0 = blk * kDkvQB;
+        const int qeb = min(kDkvQB, a.ext - q0);
+        float* sb = stat + (n & 1u) * 128;
+        {   // per-column statistics of the block: lse and delta of its queries (dead queries: P = 0)
+          const int q = q0 + (wtid & 63);
+          const bool live = q < a.kmax;
+          sb[wtid] = wtid < 64 ? (live ? lse_row[q] : INFINITY) : (live ? del_row[q] : 0.f);
+        }
+        wg_bar_sync(w);
+        mbar_wait(s_full(w), n & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c * 32 < qeb) {
+            const int nlive = a.kmax - (q0 + 32 * c);   // live query columns of this chunk
+            uint32_t col_ok = !key_ok || nlive <= 0 ? 0u : (nlive >= 32 ? 0xffffffffu : ((1u << nlive) - 1u));
+            col_ok = attn_iso_word(col_ok, q0 + 32 * c, iso_p, k_below);
+            uint32_t sv[32], pv[32];
+            tmem_ld_32x32b_x32(treg + (uint32_t)(c * 32), sv);
+            tmem_ld_32x32b_x32(treg + 64u + (uint32_t)(c * 32), pv);
+            tmem_ld_wait();
+            uint32_t pk[16], dk[16];
+            const float4* l4 = reinterpret_cast<const float4*>(sb + c * 32);
+            const float4* d4 = reinterpret_cast<const float4*>(sb + 64 + c * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 lv = l4[g], dv = d4[g];
+              const float ls[4] = {lv.x, lv.y, lv.z, lv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w};
+              float pp[4], dd[4];
+              if (col_ok == 0xffffffffu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * g + e;
+                  pp[e] = exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, -ls[e]));
+                  dd[e] = pp[e] * ((__uint_as_float(pv[j]) - de[e]) * kAttnScale);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * g + e;
+                  const bool on = (col_ok >> j) & 1u;
+                  pp[e] = on ? exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, -ls[e])) : 0.f;
+                  dd[e] = on ? pp[e] * ((__uint_as_float(pv[j]) - de[e]) * kAttnScale) : 0.f;
+                }
+              }
+              pk[2 * g] = pack2_h16(pp[0], pp[1], bf); pk[2 * g + 1] = pack2_h16(pp[2], pp[3], bf);
+              dk[2 * g] = pack2_h16(dd[0], dd[1], bf); dk[2 * g + 1] = pack2_h16(dd[2], dd[3], bf);
+            }
+            __syncwarp();
+            tmem_st_32x32b_x16(treg + (uint32_t)(c * 16), pk);
+            tmem_st_32x32b_x16(treg + 64u + (uint32_t)(c * 16), dk);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(w));
+        ++n;
+      }
+      // dV, dK of the tile: TMEM -> 16-bit -> swizzled staging tile -> TMA stores (dV first, then dK through the same tile)
+      mbar_wait(acc_full(w), m & 1u);
       tc_fence_after();
-      uint32_t col_ok = key_ok ? 0xffffffffu : 0u;
-      if (iso_p > 0) {
-        const int nb = iso_p - (q0 + 32 * g);
-        const uint32_t below = nb <= 0 ? 0u : (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u));
-        col_ok &= k_side ? below : ~below;
-      }
-      uint32_t sv[32], pv[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(tmem_ST + lane_addr + g * 32, sv);
-      tmem_ld_32x32b_x32(tmem_dPT + lane_addr + g * 32, pv);
-      tmem_ld_wait();
-      float pp[32], ds[32];
-      if (col_ok == 0xffffffffu) {
+      const uint32_t stg = base + DkvSmem::kStg + w * 16384;
+      const uint32_t rowaddr = stg + (uint32_t)r * 128u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pj = exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_i[j]));
-          pp[j] = pj;
-          ds[j] = pj * ((__uint_as_float(pv[j]) - del_i[j]) * kScale);
+      for (int which = 0; which < 2; ++which) {   // 0: dV -> columns 1024.., 1: dK -> columns 512..
+        float f[64];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(treg + (which == 0 ? 128u : 192u) + (uint32_t)(hf * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[hf * 32 + j] = __uint_as_float(v[j]);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pj = ((col_ok >> j) & 1u) ? exp2_fast(fmaf(__uint_as_float(sv[j]), kScaleLog2, -lse_i[j])) : 0.f;
-          pp[j] = pj;
-          ds[j] = pj * ((__uint_as_float(pv[j]) - del_i[j]) * kScale);
+        if (which == 1) {
+          tc_fence_before();
+          mbar_arrive(acc_free(w));
+          ++m;
         }
-      }
-      store_row_chunk(sPT, r, g, pp, bf);
-      store_row_chunk(sdST, r, g, ds, bf);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(bar_pd);
-    }
-    mbar_wait(bar_acc, (uint32_t)((nqb - 1) & 1));
-    tc_fence_after();
+        if (wtid == 0) tma_store_wait_read();
+        wg_bar_sync(w);
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {   // 0: dK -> cols 512.., 1: dV -> cols 1024..
-      uint32_t v[16];
-      __syncwarp();
-      tmem_ld_32x32b_x16((which == 0 ? tmem_dK : tmem_dV) + lane_addr + g * 16, v);
-      tmem_ld_wait();
-      if (kj < L) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        uint16_t* dst = dqkv + ((long)b * L + kj) * 1536 + (which == 0 ? 512 : 1024) + h * 64 + g * 16;
-        reinterpret_cast<uint4*>(dst)[0] = pack8_h16(f, bf);
-        reinterpret_cast<uint4*>(dst)[1] = pack8_h16(f + 8, bf);
+        for (int u = 0; u < 8; ++u) {
+          const uint4 pk = pack8_h16(f + 8 * u, bf);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((u ^ (r & 7)) << 4)), "r"(pk.x),
+                       "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+        }
+        fence_proxy_async_smem();
+        wg_bar_sync(w);
+        if (wtid == 0) {
+          const int col = (which == 0 ? 1024 : 512) + a.h * 64;
+          tma_store_3d(&plan.tm_dqkv, stg, col, k0, a.b);
+          if (k0 + 64 < L) tma_store_3d(&plan.tm_dqkv, stg + 8192, col, k0 + 64, a.b);
+          tma_store_commit();
+        }
       }
     }
+    if (wtid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -409,28 +592,37 @@ int attn_bwd_prepare(void* plan_, const void* qkv, long ldq, const void* dout, i
   memset(p, 0, sizeof(*p));
   p->B = B; p->L = L; p->bf16 = bf16;
   int r = tma_encode_3d(&p->tm_qkv, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, (uint64_t)ldq * 2,
-                        (uint64_t)L * ldq * 2, 64, 128, 1);
-  if (!r) r = tma_encode_3d(&p->tm_do, dout, bf16, 512, (uint64_t)L, (uint64_t)B, 512 * 2, (uint64_t)L * 512 * 2, 64, 128, 1);
+                        (uint64_t)L * ldq * 2, 64, 64, 1);
+  if (!r) r = tma_encode_3d(&p->tm_qkv32, qkv, bf16, 1536, (uint64_t)L, (uint64_t)B, (uint64_t)ldq * 2,
+                            (uint64_t)L * ldq * 2, 64, 32, 1);
+  if (!r) r = tma_encode_3d(&p->tm_do, dout, bf16, 512, (uint64_t)L, (uint64_t)B, 512 * 2, (uint64_t)L * 512 * 2, 64, 64, 1);
   if (r) { if (err) snprintf(err, errlen, "attn bwd: cuTensorMapEncodeTiled failed (%d)", r); return -1; }
+  p->o_ptr = nullptr;
   return 0;
 }
 
-int attn_bwd_launch(const void* plan_, const void* dout, const float* keymask, int iso_p, const void* o, const float* lse,
+int attn_bwd_launch(void* plan_, const void* dout, const int* kinfo, int iso_p, const void* o, const float* lse,
                     float* delta, void* dqkv, cudaStream_t st) {
-  const AttnPlan* p = reinterpret_cast<const AttnPlan*>(plan_);
+  AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::kBytes);
     cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::kBytes);
     attr_done = true;
   }
-  const long M = (long)p->B * p->L;
-  launch_pdl(attn_delta_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dout),
-                                                             reinterpret_cast<const uint16_t*>(o), delta, p->L, M, p->bf16);
-  dim3 grid((p->L + 127) / 128, 8, p->B);
-  launch_pdl(attn_bwd_dq_kernel, grid, kBwdThreads, DqSmem::kBytes, st, *p, keymask, iso_p, lse, delta, reinterpret_cast<uint16_t*>(dqkv));
-  launch_pdl(attn_bwd_dkv_kernel, grid, kBwdThreads, DkvSmem::kBytes, st, *p, keymask, iso_p, lse, delta,
-                                                          reinterpret_cast<uint16_t*>(dqkv));
+  if (p->o_ptr != dqkv) {
+    int r = tma_encode_3d(&p->tm_dqkv, dqkv, p->bf16, 1536, (uint64_t)p->L, (uint64_t)p->B, 1536 * 2,
+                          (uint64_t)p->L * 1536 * 2, 64, 64, 1);
+    if (r) return -(int)cudaErrorInvalidValue;
+    p->o_ptr = dqkv;
+  }
+  const int n_items = p->B * 8 * ((p->L + 255) / 256);
+  const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
+  launch_pdl(attn_bwd_dq_kernel, dim3((unsigned)grid), kAttnThreads, DqSmem::kBytes, st, *p, kinfo, iso_p,
+             reinterpret_cast<const uint16_t*>(o), reinterpret_cast<const uint16_t*>(dout), lse, delta,
+             reinterpret_cast<uint16_t*>(dqkv));
+  launch_pdl(attn_bwd_dkv_kernel, dim3((unsigned)grid), kAttnThreads, DkvSmem::kBytes, st, *p, kinfo, iso_p, lse, delta,
+             reinterpret_cast<uint16_t*>(dqkv));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

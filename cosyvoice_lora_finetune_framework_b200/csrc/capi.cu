@@ -206,7 +206,7 @@ extern "C" CVFLOW_API int cvflow_attention_backward(const void* qkv, int64_t ldq
   if (attn_bwd_prepare(plan.data(), qkv, (long)ldq, dout, B, L, dtype == CVFLOW_DTYPE_BF16, error_buf(), error_buf_len()))
     return CVFLOW_ERR_ARG;
   int r = launch_attn_kinfo(keymask, B, L, kmax_scratch, (cudaStream_t)stream);
-  if (!r) r = attn_bwd_launch(plan.data(), dout, keymask, iso_p, o, lse, delta_scratch, dqkv, (cudaStream_t)stream);
+  if (!r) r = attn_bwd_launch(plan.data(), dout, kmax_scratch, iso_p, o, lse, delta_scratch, dqkv, (cudaStream_t)stream);
   if (r) { set_error("cvflow_attention_backward: %s", cudaGetErrorString((cudaError_t)(-r))); return CVFLOW_ERR_CUDA; }
   return CVFLOW_OK;
 }

@@ -568,9 +568,9 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
         return -1;
     }
     prof_begin(2, 10.0 * t.B * 8.0 * (double)t.L * t.L * 64);
-    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.mask, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
+    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.kmax, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
     prof_end();
-    launches_ += 3;
+    launches_ += 2;
   }
   // dx1 = dqkv W_eff and, with LoRA, v = dqkv B_blk^T as 64 extra output columns of the same GEMM
   const bool lora = cfg.lora_r > 0;

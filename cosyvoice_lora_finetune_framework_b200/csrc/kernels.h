@@ -74,8 +74,9 @@ int launch_attn_kinfo(const float* keymask, int B, int L, int* kinfo, cudaStream
 int attn_fwd_launch(void* plan, const int* kinfo, int iso_p, void* o, float* lse, cudaStream_t st);
 int attn_bwd_prepare(void* plan, const void* qkv, long ldq, const void* dout, int B, int L, int bf16, char* err,
                      int errlen);
-int attn_bwd_launch(const void* plan, const void* dout, const float* keymask, int iso_p, const void* o,
-                    const float* lse, float* delta, void* dqkv, cudaStream_t st);
+// dout rows at or beyond kinfo[b] are taken as zero (padding rows; every consumer of them is masked in the estimator)
+int attn_bwd_launch(void* plan, const void* dout, const int* kinfo, int iso_p, const void* o, const float* lse,
+                    float* delta, void* dqkv, cudaStream_t st);
 
 // ---- lora.cu -------------------------------------------------------------------------------
 struct LoraLayerPtrs {       // one q/k/v projection of one attention block

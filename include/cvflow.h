@@ -156,7 +156,9 @@ CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* cou
  *   kmax_scratch int32 [cvflow_attention_scratch_ints(B, L)] (written: per sample 1 + last valid index, then key
  *   validity bit words)
  *   o 16-bit [B][L][512]; lse fp32 [B][8][L] (base-2 log-sum-exp of the scaled scores, +inf on empty rows)
- * backward: dout 16-bit [B][L][512]; delta_scratch fp32 [B][8][L]; dqkv 16-bit [B][L][1536].
+ * backward: dout 16-bit [B][L][512] (rows at or beyond a sample's last valid index are taken as zero, as they are
+ * in the estimator where every consumer of padded rows is masked); delta_scratch fp32 [B][8][L];
+ * dqkv 16-bit [B][L][1536].
  * ------------------------------------------------------------------------------------------- */
 CVFLOW_API int64_t cvflow_attention_scratch_ints(int32_t B, int32_t L);
 CVFLOW_API int cvflow_attention_forward(const void* qkv, int64_t ldq, int32_t B, int32_t L, int32_t dtype,
