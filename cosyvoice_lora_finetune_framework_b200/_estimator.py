@@ -54,6 +54,8 @@ def _lib():
         L.cvflow_euler_update.argtypes = [vp, vp, vp, i32, f, i64, vp]
         L.cvflow_sumsq.argtypes = [vp, i64, vp, vp, vp]
         L.cvflow_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, f, f, f, f, f, f, f, i32, vp, vp, vp]
+        L.cvflow_mlp_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+        L.cvflow_mlp_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp]
         L.cvflow_attention_scratch_ints.argtypes = [i32, i32]
         L.cvflow_attention_scratch_ints.restype = i64
         L.cvflow_attention_forward.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp, vp]

@@ -176,6 +176,7 @@ extern "C" CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, i
 }
 
 extern "C" CVFLOW_API int cvflow_debug_attention_stamps(void* buf) { attn_set_debug_buffer(buf); return CVFLOW_OK; }
+extern "C" CVFLOW_API int cvflow_debug_mlp_stamps(void* buf) { mlp_set_debug_buffer(buf); return CVFLOW_OK; }
 
 // ---------------------------------------------------------------------------------------------
 extern "C" CVFLOW_API int64_t cvflow_attention_scratch_ints(int32_t B, int32_t L) { return attn_kinfo_ints(B, L); }
@@ -209,4 +210,25 @@ extern "C" CVFLOW_API int cvflow_attention_backward(const void* qkv, int64_t ldq
   if (!r) r = attn_bwd_launch(plan.data(), dout, kmax_scratch, iso_p, o, lse, delta_scratch, dqkv, (cudaStream_t)stream);
   if (r) { set_error("cvflow_attention_backward: %s", cudaGetErrorString((cudaError_t)(-r))); return CVFLOW_ERR_CUDA; }
   return CVFLOW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" CVFLOW_API int cvflow_mlp_forward(const void* x16, const void* w1, const float* b1, const void* w2,
+                                             const float* b2, const float* resid32, float* out32, void* pre16, int64_t M,
+                                             int32_t dtype, int32_t gelu_erf, void* stream) {
+  if (!x16 || !w1 || !w2 || !out32 || !pre16 || M < 1) { set_error("cvflow_mlp_forward: null/invalid argument"); return CVFLOW_ERR_ARG; }
+  std::vector<uint8_t> plan(mlp_plan_bytes());
+  if (mlp_prepare(plan.data(), 0, x16, w1, b1, w2, b2, resid32, out32, pre16, (long)M, dtype == CVFLOW_DTYPE_BF16, gelu_erf,
+                  error_buf(), error_buf_len()))
+    return CVFLOW_ERR_ARG;
+  RET_LAUNCH(mlp_launch(plan.data(), (cudaStream_t)stream), "cvflow_mlp_forward");
+}
+extern "C" CVFLOW_API int cvflow_mlp_backward(const void* dy16, const void* w2_t, const void* pre16, const void* w1_t,
+                                              void* dx16, int64_t M, int32_t dtype, int32_t gelu_erf, void* stream) {
+  if (!dy16 || !w2_t || !pre16 || !w1_t || !dx16 || M < 1) { set_error("cvflow_mlp_backward: null/invalid argument"); return CVFLOW_ERR_ARG; }
+  std::vector<uint8_t> plan(mlp_plan_bytes());
+  if (mlp_prepare(plan.data(), 1, dy16, w2_t, nullptr, w1_t, nullptr, nullptr, dx16, const_cast<void*>(pre16), (long)M,
+                  dtype == CVFLOW_DTYPE_BF16, gelu_erf, error_buf(), error_buf_len()))
+    return CVFLOW_ERR_ARG;
+  RET_LAUNCH(mlp_launch(plan.data(), (cudaStream_t)stream), "cvflow_mlp_backward");
 }

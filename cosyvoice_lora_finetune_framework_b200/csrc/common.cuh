@@ -116,6 +116,62 @@ __device__ __forceinline__ float gelu_erf_grad_f(float x) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue one instruction for two lanes): the
+// epilogues that run an activation over a whole hidden tile on one SM are issue-bound otherwise.
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// GELU(tanh) of a pair; 5 packed ops + 2 MUFU.TANH
+__device__ __forceinline__ f32x2 gelu_tanh_f2(f32x2 x) {
+  const f32x2 c0 = f2_pack(0.7978845608028654f, 0.7978845608028654f);
+  const f32x2 c1 = f2_pack(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const f32x2 half = f2_pack(0.5f, 0.5f);
+  const f32x2 u = f2_mul(x, f2_fma(f2_mul(x, x), c1, c0));
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  const f32x2 th = f2_pack(tanh_fast(u0), tanh_fast(u1));
+  const f32x2 hx = f2_mul(x, half);
+  return f2_fma(hx, th, hx);
+}
+// d * GELU'(x) of a pair (tanh form); 10 packed ops + 2 MUFU.TANH
+__device__ __forceinline__ f32x2 gelu_tanh_grad_mul_f2(f32x2 d, f32x2 x) {
+  const f32x2 c0 = f2_pack(0.7978845608028654f, 0.7978845608028654f);
+  const f32x2 c1 = f2_pack(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const f32x2 c3 = f2_pack(3.f * 0.7978845608028654f * 0.044715f, 3.f * 0.7978845608028654f * 0.044715f);
+  const f32x2 half = f2_pack(0.5f, 0.5f), one = f2_pack(1.f, 1.f), mone = f2_pack(-1.f, -1.f);
+  const f32x2 x2 = f2_mul(x, x);
+  const f32x2 u = f2_mul(x, f2_fma(x2, c1, c0));
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  const f32x2 th = f2_pack(tanh_fast(u0), tanh_fast(u1));
+  const f32x2 du = f2_fma(x2, c3, c0);
+  const f32x2 a = f2_fma(th, half, half);                  // 0.5 (1 + th)
+  const f32x2 s = f2_fma(f2_mul(th, mone), th, one);       // 1 - th^2
+  const f32x2 m = f2_mul(f2_mul(x, half), s);
+  return f2_mul(d, f2_fma(m, du, a));
+}
+
+// ------------------------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel launched with launch_pdl() may begin (barrier init,
 // TMEM allocation, descriptor prefetch) while its predecessor drains; it must execute pdl_wait()
 // before its first global-memory access. pdl_launch() lets the successor start early.
@@ -208,6 +264,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0),
+               "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -29,7 +29,10 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {}
+Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {
+  const char* e = getenv("CVFLOW_FUSED_MLP");
+  fused_mlp_ = e && e[0] == '1';   // opt-in: one SM per 128-row tile is L2->SM bandwidth-bound (~40 B/clk), see DESIGN.md
+}
 Estimator::~Estimator() {
   if (lora_table_dev_) cudaFree(lora_table_dev_);
 }
@@ -136,6 +139,25 @@ int Estimator::run_gemm(GemmArgs& a) {
   return 0;
 }
 
+int Estimator::run_mlp(int backward, const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                       const float* resid, void* out, void* pre, long M) {
+  if (dry_) { ++mlp_idx_; return 0; }
+  if (missing_ || oom_) return -1;
+  Plan& pl = *plan_;
+  if ((size_t)mlp_idx_ >= pl.mlps.size()) {
+    pl.mlps.emplace_back(mlp_plan_bytes());
+    if (mlp_prepare(pl.mlps.back().data(), backward, x, w1, b1, w2, b2, resid, out, pre, M, cfg.bf16, cfg.gelu_erf, error_buf(),
+                    error_buf_len()))
+      return -1;
+  }
+  prof_begin(0, 2.0 * (double)M * 256.0 * 1024.0 * 2.0);
+  int r = mlp_launch(pl.mlps[mlp_idx_++].data(), stream_);
+  prof_end();
+  if (r) { set_error("mlp launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return -1; }
+  ++launches_;
+  return 0;
+}
+
 static GemmArgs linear_args(const void* A, long M, int K, const void* W, int N, void* out, int out_f32) {
   GemmArgs a;
   a.A[0] = A; a.a_rows[0] = (int)M; a.a_cols[0] = K; a.a_ld[0] = K; a.a_bstride[0] = M * (long)K;
@@ -226,7 +248,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   float* h1 = (float*)alloc(M * 256 * 4);
   void* x3 = alloc(M * 256 * 2);
   void* pre = alloc(M * 1024 * 2);
-  void* g16 = alloc(M * 1024 * 2);
+  void* g16 = fused_mlp_ ? nullptr : alloc(M * 1024 * 2);
   float* h2 = (float*)alloc(M * 256 * 4);
   if (!dry_) {
     CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
@@ -260,18 +282,23 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
                             M, cfg.bf16, stream_));
     ++launches_;
   }
-  {
-    GemmArgs g = linear_args(x3, M, 256, get(Q + ".w1", cfg.bf16, 1024L * 256), 1024, g16, 0);
-    g.bias = (const float*)get(Q + ".b1", 2, 1024);
-    g.act = cfg.gelu_erf ? ACT_GELU_ERF : ACT_GELU_TANH;
-    g.aux_out = pre; g.ld_aux = 1024;
-    CK(run_gemm(g));
-  }
-  {
-    GemmArgs g = linear_args(g16, M, 1024, get(Q + ".w2", cfg.bf16, 256L * 1024), 256, h2, 1);
-    g.bias = (const float*)get(Q + ".b2", 2, 256);
-    g.resid = h1; g.ldr = 256;
-    CK(run_gemm(g));
+  if (fused_mlp_) {
+    CK(run_mlp(0, x3, get(Q + ".w1", cfg.bf16, 1024L * 256), (const float*)get(Q + ".b1", 2, 1024),
+               get(Q + ".w2", cfg.bf16, 256L * 1024), (const float*)get(Q + ".b2", 2, 256), h1, h2, pre, M));
+  } else {
+    {
+      GemmArgs g = linear_args(x3, M, 256, get(Q + ".w1", cfg.bf16, 1024L * 256), 1024, g16, 0);
+      g.bias = (const float*)get(Q + ".b1", 2, 1024);
+      g.act = cfg.gelu_erf ? ACT_GELU_ERF : ACT_GELU_TANH;
+      g.aux_out = pre; g.ld_aux = 1024;
+      CK(run_gemm(g));
+    }
+    {
+      GemmArgs g = linear_args(g16, M, 1024, get(Q + ".w2", cfg.bf16, 256L * 1024), 256, h2, 1);
+      g.bias = (const float*)get(Q + ".b2", 2, 256);
+      g.resid = h1; g.ldr = 256;
+      CK(run_gemm(g));
+    }
   }
   *h_out = h2;
   if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p};
@@ -399,7 +426,7 @@ int Estimator::forward(const EstimatorIO& io, cudaStream_t st) {
 int Estimator::forward_impl(const EstimatorIO& io) {
   const int B = io.B, T = io.T, T2 = (T + 1) / 2;
   training_ = io.training != 0;
-  gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0; wg_idx_ = 0;
+  gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0; wg_idx_ = 0; mlp_idx_ = 0;
   stages_.clear();
   const int nres = n_resnets();
   float* mask1 = (float*)alloc((long)B * T * 4);
@@ -541,15 +568,20 @@ int Estimator::backward(const void* dpred16, float grad_scale, const float* grad
 int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp) {
   const long M = (long)t.B * t.L;
   const std::string& Q = t.prefix;
-  {  // d pre = (dh2 W2) * gelu'(pre)
-    GemmArgs g = linear_args(dh16, M, 256, get(Q + ".w2_t", cfg.bf16, 1024L * 256), 1024, tmp.dpre, 0);
-    g.act = cfg.gelu_erf ? ACT_MUL_GELU_ERF_GRAD : ACT_MUL_GELU_TANH_GRAD;
-    g.mul_src = t.pre; g.ld_aux = 1024;
-    CK(run_gemm(g));
-  }
-  {
-    GemmArgs g = linear_args(tmp.dpre, M, 1024, get(Q + ".w1_t", cfg.bf16, 256L * 1024), 256, tmp.dx, 0);
-    CK(run_gemm(g));
+  if (fused_mlp_) {  // dx = ((dh2 W2) o gelu'(pre)) W1 in one launch
+    CK(run_mlp(1, dh16, get(Q + ".w2_t", cfg.bf16, 1024L * 256), nullptr, get(Q + ".w1_t", cfg.bf16, 256L * 1024), nullptr,
+               nullptr, tmp.dx, t.pre, M));
+  } else {
+    {  // d pre = (dh2 W2) * gelu'(pre)
+      GemmArgs g = linear_args(dh16, M, 256, get(Q + ".w2_t", cfg.bf16, 1024L * 256), 1024, tmp.dpre, 0);
+      g.act = cfg.gelu_erf ? ACT_MUL_GELU_ERF_GRAD : ACT_MUL_GELU_TANH_GRAD;
+      g.mul_src = t.pre; g.ld_aux = 1024;
+      CK(run_gemm(g));
+    }
+    {
+      GemmArgs g = linear_args(tmp.dpre, M, 1024, get(Q + ".w1_t", cfg.bf16, 256L * 1024), 256, tmp.dx, 0);
+      CK(run_gemm(g));
+    }
   }
   if (!dry_) {
     CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
@@ -649,7 +681,7 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   const int B = last_io_.B, T = last_io_.T, T2 = (T + 1) / 2;
   const long MT = (long)B * T, MH = (long)B * T2;
   BwdTemps tmp;
-  tmp.dpre = alloc(MT * 1024 * 2);
+  tmp.dpre = fused_mlp_ ? nullptr : alloc(MT * 1024 * 2);
   tmp.dx = alloc(MT * 256 * 2);
   tmp.dO = alloc(MT * 512 * 2);
   tmp.dqkv = alloc(MT * 1536 * 2);

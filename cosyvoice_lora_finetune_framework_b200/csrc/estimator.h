@@ -54,7 +54,10 @@ struct PlanKey {
     return ws < o.ws;
   }
 };
-struct Plan { std::vector<GemmParams> gemms; std::vector<std::vector<uint8_t>> attn; std::vector<std::vector<uint8_t>> wgrads; };
+struct Plan {
+  std::vector<GemmParams> gemms;
+  std::vector<std::vector<uint8_t>> attn, wgrads, mlps;
+};
 
 class Estimator {
  public:
@@ -79,6 +82,8 @@ class Estimator {
   bool has(const std::string& name) const;
   void* alloc(long bytes);
   int run_gemm(GemmArgs& a);
+  int run_mlp(int backward, const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+              const float* resid, void* out, void* pre, long M);
   int iso_at(int L, int T, int iso_len) const;
   void for_each_tb(const std::function<void(const std::string&)>& f);
   int forward_impl(const EstimatorIO& io);
@@ -101,7 +106,8 @@ class Estimator {
   long ws_bytes_ = 0, ws_off_ = 0, fwd_ws_end_ = 0;
   bool training_ = false;
   bool dry_ = false, missing_ = false, oom_ = false, have_fwd_ = false, lora_table_ready_ = false;
-  int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0, wg_idx_ = 0;
+  int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0, wg_idx_ = 0, mlp_idx_ = 0;
+  bool fused_mlp_ = false;  // CVFLOW_FUSED_MLP=1 runs the feed-forward as one fused launch (mlp.cu) instead of two engine GEMMs
   long launches_ = 0;
   cudaStream_t stream_ = nullptr;
   LoraBlockPtrs* lora_table_dev_ = nullptr;

@@ -383,6 +383,24 @@ int tma_encode_3d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint
   return tma_encode_3d_ex(tm, base, bf16 ? 1 : 0, 128, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, b2);
 }
 
+int tma_encode_2d_ex(CUtensorMap* tm, const void* base, int dtype, int swizzle_bytes, uint64_t d0, uint64_t d1,
+                     uint64_t stride1_bytes, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -100;
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dtc = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                             : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(tm, dtc, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
 static int encode_2d(CUtensorMap* tm, const void* base, int bf16, uint64_t d0, uint64_t d1,
                      uint64_t stride1_bytes, uint32_t b0, uint32_t b1) {
   EncodeTiledFn fn = get_encode_fn();

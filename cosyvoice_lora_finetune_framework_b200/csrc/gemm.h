@@ -94,4 +94,7 @@ int tma_encode_3d_ex(CUtensorMap* tm, const void* base, int dtype, int swizzle_b
                      uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
                      uint32_t b2);
 
+int tma_encode_2d_ex(CUtensorMap* tm, const void* base, int dtype, int swizzle_bytes, uint64_t d0, uint64_t d1,
+                     uint64_t stride1_bytes, uint32_t b0, uint32_t b1);
+
 }  // namespace cvflow

@@ -78,6 +78,16 @@ int attn_bwd_prepare(void* plan, const void* qkv, long ldq, const void* dout, in
 int attn_bwd_launch(void* plan, const void* dout, const int* kinfo, int iso_p, const void* o, const float* lse,
                     float* delta, void* dqkv, cudaStream_t st);
 
+// ---- mlp.cu --------------------------------------------------------------------------------
+// Fused FeedForward (modules.py:192-224) + residual, and its backward, for hidden 1024 / model 256:
+//   forward : out32[M][256] = resid + b2 + gelu(x16 W1^T + b1) W2^T; pre16[M][1024] = x16 W1^T + b1 (stash)
+//   backward: out16[M][256] = ((x16 W1'^T) o gelu'(pre16)) W2'^T with W1' = W2^T image [1024][256], W2' = W1^T image [256][1024]
+int mlp_plan_bytes();
+int mlp_prepare(void* plan, int backward, const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                const float* resid, void* out, void* pre, long M, int bf16, int gelu_erf, char* err, int errlen);
+int mlp_launch(const void* plan, cudaStream_t st);
+void mlp_set_debug_buffer(void* p);   // profiling aid: 64 clock64 stamps per CTA for plans prepared afterwards
+
 // ---- lora.cu -------------------------------------------------------------------------------
 struct LoraLayerPtrs {       // one q/k/v projection of one attention block
   const float* W;            // frozen [512][256] fp32

@@ -146,6 +146,8 @@ CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on);
 /* Profiling aid: attention-forward plans prepared after this call write 16 x int64 globaltimer phase
  * stamps per CTA into buf (NULL switches it off). */
 CVFLOW_API int cvflow_debug_attention_stamps(void* buf);
+/* Same for the fused feed-forward kernel: 64 x int64 clock stamps per CTA. */
+CVFLOW_API int cvflow_debug_mlp_stamps(void* buf);
 CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* counts, double* flops, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------
@@ -168,6 +170,19 @@ CVFLOW_API int cvflow_attention_backward(const void* qkv, int64_t ldq, int32_t B
                                          const float* keymask, int32_t* kmax_scratch, int32_t iso_p, const void* o,
                                          const float* lse, const void* dout, float* delta_scratch, void* dqkv,
                                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused FeedForward of a transformer block (reference modules.py:192-224,372-374), model 256 / hidden 1024:
+ *   forward : out32[M][256] = resid32 + b2 + gelu(x16 W1^T + b1) W2^T, pre16[M][1024] = x16 W1^T + b1 (stash)
+ *             W1 16-bit [1024][256], W2 16-bit [256][1024] (nn.Linear layouts)
+ *   backward: dx16[M][256] = ((dy16 W2) o gelu'(pre16)) W1, given the transposed images W2^T [1024][256] and
+ *             W1^T [256][1024]
+ * ------------------------------------------------------------------------------------------- */
+CVFLOW_API int cvflow_mlp_forward(const void* x16, const void* w1, const float* b1, const void* w2, const float* b2,
+                                  const float* resid32, float* out32, void* pre16, int64_t M, int32_t dtype,
+                                  int32_t gelu_erf, void* stream);
+CVFLOW_API int cvflow_mlp_backward(const void* dy16, const void* w2_t, const void* pre16, const void* w1_t, void* dx16,
+                                   int64_t M, int32_t dtype, int32_t gelu_erf, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CFM passes (reference flow_model.py:94-204)

@@ -71,3 +71,39 @@ for M in (6400, 12800):
     run("out-proj dgrad", M, 512, 256, "h16")
     run("qkv dgrad", M, 256, 1536, "h16")
     run("lora u / v", M, 64, 1536, "h16")
+
+
+def run_mlp(M):
+    """fused FeedForward (one launch) next to the two engine GEMMs it replaces"""
+    from cosyvoice_lora_finetune_framework_b200 import _estimator as E
+    Lm = E._lib()
+    ncopy = 6
+    xs = [torch.randn(M, 256, device="cuda").to(dt) for _ in range(ncopy)]
+    w1 = (torch.randn(1024, 256, device="cuda") * 0.08).to(dt)
+    w2 = (torch.randn(256, 1024, device="cuda") * 0.05).to(dt)
+    b1, b2 = torch.randn(1024, device="cuda"), torch.randn(256, device="cuda")
+    res = [torch.randn(M, 256, device="cuda") for _ in range(ncopy)]
+    outs = [torch.empty(M, 256, device="cuda") for _ in range(ncopy)]
+    pres = [torch.empty(M, 1024, device="cuda", dtype=dt) for _ in range(ncopy)]
+    dxs = [torch.empty(M, 256, device="cuda", dtype=dt) for _ in range(ncopy)]
+    st = E._stream()
+    code = N.dtype_code(dt)
+
+    def fwd(i):
+        j = i % ncopy
+        Lm.cvflow_mlp_forward(xs[j].data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), res[j].data_ptr(),
+                              outs[j].data_ptr(), pres[j].data_ptr(), M, code, 0, st)
+
+    def bwd(i):
+        j = i % ncopy
+        Lm.cvflow_mlp_backward(xs[j].data_ptr(), w1.data_ptr(), pres[j].data_ptr(), w2.data_ptr(), dxs[j].data_ptr(), M, code, 0, st)
+
+    for j in range(ncopy):
+        fwd(j)
+    fl = 2.0 * M * 256 * 1024 * 2
+    uf, ub = bench(fwd), bench(bwd)
+    print("fused mlp M=%6d  fwd %7.1f us %6.0f TF/s | bwd %7.1f us %6.0f TF/s" % (M, uf, fl / uf / 1e6, ub, fl / ub / 1e6))
+
+
+for M in (700, 1400, 6400, 12800, 24000):
+    run_mlp(M)

@@ -46,6 +46,33 @@ __global__ void mufu2_kernel(float* out, long long* cycles, int iters) {
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// MUFU throughput with loop-varying (non-CSE-able) inputs: op 0 ex2, 1 tanh, 2 rcp
+template <int OP>
+__global__ void mufu3_kernel(float* out, long long* cycles, int iters) {
+  float x[32], y[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { x[j] = -0.01f * ((threadIdx.x & 31) + j) - 0.5f; y[j] = 0.f; }
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float r;
+      if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x[j]));
+      if (OP == 1) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x[j]));
+      if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x[j]));
+      y[j] += r;
+      x[j] += 0.001f;
+    }
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += y[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 __global__ void cvt_kernel(float* out, long long* cycles, int iters) {
   float x[32];
   uint32_t acc = 0;
@@ -181,6 +208,17 @@ int main() {
     cudaDeviceSynchronize();
     long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     printf("MUFU.EX2 (normal inputs, + FADD each): %d warp(s)/scheduler: %.2f ex2 per clk per SM\n", w, (double)128 * w * iters * 32 / c);
+  }
+  for (int w = 1; w <= 4; w *= 2) {
+    long long c[3];
+    mufu3_kernel<0><<<1, 128 * w>>>(out, cyc, iters); mufu3_kernel<0><<<1, 128 * w>>>(out, cyc, iters);
+    cudaDeviceSynchronize(); cudaMemcpy(&c[0], cyc, 8, cudaMemcpyDeviceToHost);
+    mufu3_kernel<1><<<1, 128 * w>>>(out, cyc, iters); mufu3_kernel<1><<<1, 128 * w>>>(out, cyc, iters);
+    cudaDeviceSynchronize(); cudaMemcpy(&c[1], cyc, 8, cudaMemcpyDeviceToHost);
+    mufu3_kernel<2><<<1, 128 * w>>>(out, cyc, iters); mufu3_kernel<2><<<1, 128 * w>>>(out, cyc, iters);
+    cudaDeviceSynchronize(); cudaMemcpy(&c[2], cyc, 8, cudaMemcpyDeviceToHost);
+    const double ops = 128.0 * w * iters * 32;
+    printf("MUFU varying inputs, %d warp(s)/scheduler: ex2 %.1f, tanh %.1f, rcp %.1f per clk per SM\n", w, ops / c[0], ops / c[1], ops / c[2]);
   }
   for (int w = 1; w <= 2; ++w) {
     cvt_kernel<<<1, 128 * w>>>(out, cyc, iters); cvt_kernel<<<1, 128 * w>>>(out, cyc, iters);
