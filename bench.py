@@ -288,7 +288,7 @@ def run_cvflow(a):
         msa, cnt, fl = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)()
         L.cvflow_profile_read(ne.handle, msa, cnt, fl, n)
         L.cvflow_set_profile(ne.handle, 0)
-        names = ["gemm_tc (tcgen05 implicit GEMM)", "attn_fwd (tcgen05)", "attn_bwd (tcgen05, 3 launches)", "-",
+        names = ["gemm_tc (tcgen05 implicit GEMM)", "attn_fwd (tcgen05)", "attn_bwd (tcgen05, dQ + dK/dV launches)", "-",
                  "lora_wgrad"]
         kernels = {names[i]: {"ms_per_step": msa[i] / 2, "launches_per_step": cnt[i] // 2,
                               "tflops": (fl[i] / 2) / (msa[i] / 2 * 1e9) if msa[i] > 0 else None}

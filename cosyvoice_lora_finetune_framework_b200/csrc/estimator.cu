@@ -11,6 +11,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cvflow {
 
@@ -31,9 +32,22 @@ void set_error(const char* fmt, ...);
 // ------------------------------------------------------------------------------------------
 Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {
   const char* e = getenv("CVFLOW_FUSED_MLP");
-  fused_mlp_ = e && e[0] == '1';   // opt-in: one SM per 128-row tile is L2->SM bandwidth-bound (~40 B/clk), see DESIGN.md
+  fused_mlp_ = e && e[0] == '1';
+  const char* e2 = getenv("CVFLOW_WGRAD_SIDE");
+  wgrad_side_ = e2 && e2[0] == '1';
+  const char* e3 = getenv("CVFLOW_SKIP");
+  skip_ = e3 ? (unsigned)atoi(e3) : 0u;
+  if (wgrad_side_) {
+    if (cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking) != cudaSuccess) { side_ = nullptr; wgrad_side_ = false; }
+    else {
+      cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_done_[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_done_[1], cudaEventDisableTiming);
+    }
+  }   // opt-in: one SM per 128-row tile is L2->SM bandwidth-bound (~40 B/clk), see DESIGN.md
 }
 Estimator::~Estimator() {
+  if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_done_[0]); cudaEventDestroy(ev_done_[1]); }
   if (lora_table_dev_) cudaFree(lora_table_dev_);
 }
 
@@ -79,15 +93,15 @@ cudaEvent_t Estimator::ev_get() {
   }
   return ev_pool_[ev_used_++];
 }
-void Estimator::prof_begin(int cls, double flops) {
+void Estimator::prof_begin(int cls, double flops, cudaStream_t st) {
   if (!profile_ || dry_) return;
   ProfRec r{cls, flops, ev_get(), ev_get()};
-  cudaEventRecord(r.a, stream_);
+  cudaEventRecord(r.a, st ? st : stream_);
   prof_.push_back(r);
 }
-void Estimator::prof_end() {
+void Estimator::prof_end(cudaStream_t st) {
   if (!profile_ || dry_) return;
-  cudaEventRecord(prof_.back().b, stream_);
+  cudaEventRecord(prof_.back().b, st ? st : stream_);
 }
 int Estimator::profile_read(double* ms, long* counts, double* flops, int n) {
   for (int i = 0; i < n; ++i) { ms[i] = 0; counts[i] = 0; flops[i] = 0; }
@@ -132,7 +146,7 @@ int Estimator::run_gemm(GemmArgs& a) {
   // per-call pointers at the API edge may move between calls
   p.out = a.out; p.rowmask = a.rowmask;
   prof_begin(0, 2.0 * (double)a.nbatch * a.R * (double)a.n_valid * a.Ktot);
-  int r = gemm_launch(p, stream_);
+  int r = (skip_ & 16u) ? 0 : gemm_launch(p, stream_);
   prof_end();
   if (r) { set_error("gemm launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return -1; }
   ++launches_;
@@ -204,8 +218,8 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
-    CKL(launch_gn_apply(c1, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
                        tb, tb_stride, nullptr, a1, 0, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -224,8 +238,8 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
-    CKL(launch_gn_apply(c2, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
                        nullptr, 0, r, h, 1, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -251,7 +265,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   void* g16 = fused_mlp_ ? nullptr : alloc(M * 1024 * 2);
   float* h2 = (float*)alloc(M * 256 * 4);
   if (!dry_) {
-    CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
+    if (!(skip_ & 2u)) CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
                             M, cfg.bf16, stream_));
     ++launches_;
   }
@@ -267,7 +281,8 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       if (attn_fwd_prepare(pl.attn.back().data(), qkv, ldq, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
     }
     prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
-    CKL(attn_fwd_launch(pl.attn[attn_idx_++].data(), kmax, iso_p, o, lse, stream_));
+    if (!(skip_ & 1u)) CKL(attn_fwd_launch(pl.attn[attn_idx_].data(), kmax, iso_p, o, lse, stream_));
+    ++attn_idx_;
     prof_end();
     ++launches_;
   }
@@ -278,7 +293,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
+    if (!(skip_ & 2u)) CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
                             M, cfg.bf16, stream_));
     ++launches_;
   }
@@ -531,8 +546,8 @@ int Estimator::forward_impl(const EstimatorIO& io) {
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
-    CKL(launch_gn_apply(cf, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
+    if (!(skip_ & 4u)) CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
                        mask1, nullptr, 0, nullptr, af, 0, B, T, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -568,6 +583,9 @@ int Estimator::backward(const void* dpred16, float grad_scale, const float* grad
 int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp) {
   const long M = (long)t.B * t.L;
   const std::string& Q = t.prefix;
+  const int par = t.lora_idx & 1;
+  void* dqkv = tmp.dqkv[par];
+  void* dxe = tmp.dxe[par];
   if (fused_mlp_) {  // dx = ((dh2 W2) o gelu'(pre)) W1 in one launch
     CK(run_mlp(1, dh16, get(Q + ".w2_t", cfg.bf16, 1024L * 256), nullptr, get(Q + ".w1_t", cfg.bf16, 256L * 1024), nullptr,
                nullptr, tmp.dx, t.pre, M));
@@ -584,7 +602,7 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     }
   }
   if (!dry_) {
-    CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+    if (!(skip_ & 2u)) CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
                              stream_));
     ++launches_;
   }
@@ -600,7 +618,12 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
         return -1;
     }
     prof_begin(2, 10.0 * t.B * 8.0 * (double)t.L * t.L * 64);
-    CKL(attn_bwd_launch(pl.attn[attn_idx_++].data(), tmp.dO, t.kmax, t.iso_p, t.o, t.lse, tmp.delta, tmp.dqkv, stream_));
+    if (wgrad_side_ && ev_done_valid_[par]) {   // the side-stream wgrad that last read this dqkv / v buffer pair has finished
+      cudaStreamWaitEvent(stream_, ev_done_[par], 0);
+      ev_done_valid_[par] = false;
+    }
+    if (!(skip_ & 1u)) CKL(attn_bwd_launch(pl.attn[attn_idx_].data(), tmp.dO, t.kmax, t.iso_p, t.o, t.lse, tmp.delta, dqkv, stream_));
+    ++attn_idx_;
     prof_end();
     launches_ += 2;
   }
@@ -608,8 +631,8 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
   const bool lora = cfg.lora_r > 0;
   const long ldx = lora ? 320 : 256;
   if (lora || need_input_grad) {
-    GemmArgs g = lora ? linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t_ext", cfg.bf16, 320L * 1536), 320, tmp.dxe, 0)
-                      : linear_args(tmp.dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, tmp.dxe, 0);
+    GemmArgs g = lora ? linear_args(dqkv, M, 1536, get(Q + ".weff_t_ext", cfg.bf16, 320L * 1536), 320, dxe, 0)
+                      : linear_args(dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, dxe, 0);
     CK(run_gemm(g));
   }
   if (lora && !dry_) {
@@ -617,19 +640,29 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     if ((size_t)wg_idx_ >= pl.wgrads.size()) {
       pl.wgrads.emplace_back(lora_wgrad_plan_bytes());
       const uint16_t* u = reinterpret_cast<const uint16_t*>(t.qkv) + 1536;
-      const uint16_t* v = reinterpret_cast<const uint16_t*>(tmp.dxe) + 256;
-      if (lora_wgrad_prepare(pl.wgrads.back().data(), tmp.dqkv, t.x1, u, t.ldq, v, ldx, M, cfg.lora_r, tmp.wg_scratch,
-                             cfg.bf16, error_buf(), error_buf_len()))
+      const uint16_t* v = reinterpret_cast<const uint16_t*>(dxe) + 256;
+      if (lora_wgrad_prepare(pl.wgrads.back().data(), dqkv, t.x1, u, t.ldq, v, ldx, M, cfg.lora_r,
+                             tmp.wg_scratch + (long)t.lora_idx * tmp.wg_stride, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
     }
-    prof_begin(4, 2.0 * M * 64.0 * (1536 + 256));
-    CKL(lora_wgrad_launch(pl.wgrads[wg_idx_++].data(), lora_table_dev_ + t.lora_idx, grad_scale, grad_scale_dev_,
-                          stream_));
-    prof_end();
-    launches_ += 2;
+    cudaStream_t ws = stream_;
+    if (wgrad_side_) {
+      cudaEventRecord(ev_fork_, stream_);
+      cudaStreamWaitEvent(side_, ev_fork_, 0);
+      ws = side_;
+    }
+    prof_begin(4, 2.0 * M * 64.0 * (1536 + 256), ws);
+    if (!(skip_ & 8u)) CKL(lora_wgrad_launch_partial(pl.wgrads[wg_idx_].data(), ws));
+    ++wg_idx_;
+    prof_end(ws);
+    if (wgrad_side_) {
+      cudaEventRecord(ev_done_[par], side_);
+      ev_done_valid_[par] = true;
+    }
+    ++launches_;
   }
   if (need_input_grad && !dry_) {
-    CKL(launch_layernorm_bwd(tmp.dxe, ldx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+    if (!(skip_ & 2u)) CKL(launch_layernorm_bwd(dxe, ldx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
                              stream_));
     ++launches_;
   }
@@ -641,7 +674,7 @@ int Estimator::resnet_bwd(const ResnetRec& r, const float* dout32, const void* d
   const std::string& P = r.prefix;
   const int B = r.B, L = r.L;
   if (!dry_) {
-    CKL(launch_gn_bwd(dout32, 1, r.c2, r.st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256),
+    if (!(skip_ & 4u)) CKL(launch_gn_bwd(dout32, 1, r.c2, r.st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256),
                      r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -650,7 +683,7 @@ int Estimator::resnet_bwd(const ResnetRec& r, const float* dout32, const void* d
     CK(run_gemm(g));
   }
   if (!dry_) {
-    CKL(launch_gn_bwd(tmp.da, 0, r.c1, r.st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256),
+    if (!(skip_ & 4u)) CKL(launch_gn_bwd(tmp.da, 0, r.c1, r.st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256),
                      r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -684,12 +717,15 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   tmp.dpre = fused_mlp_ ? nullptr : alloc(MT * 1024 * 2);
   tmp.dx = alloc(MT * 256 * 2);
   tmp.dO = alloc(MT * 512 * 2);
-  tmp.dqkv = alloc(MT * 1536 * 2);
+  tmp.dqkv[0] = alloc(MT * 1536 * 2);
+  tmp.dqkv[1] = wgrad_side_ ? alloc(MT * 1536 * 2) : tmp.dqkv[0];
   tmp.delta = (float*)alloc((long)B * 8 * T * 4);
   tmp.dc = alloc(MT * 256 * 2);
   tmp.da = alloc(MT * 256 * 2);
-  tmp.wg_scratch = (float*)alloc(lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1) * 4);
-  tmp.dxe = alloc(MT * 320 * 2);
+  tmp.wg_stride = lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1);
+  tmp.wg_scratch = (float*)alloc(tmp.wg_stride * (cfg.lora_r > 0 ? n_tbs() : 1) * 4);
+  tmp.dxe[0] = alloc(MT * 320 * 2);
+  tmp.dxe[1] = wgrad_side_ ? alloc(MT * 320 * 2) : tmp.dxe[0];
   float* dh32 = (float*)alloc(MT * 256 * 4);
   void* dh16 = alloc(MT * 256 * 2);
   void* g16a = alloc(MT * 256 * 2);
@@ -712,7 +748,7 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
     g.R = T; g.out_rows = T; g.out = tmp.da; g.ldc = 256; g.n_valid = 256;
     CK(run_gemm(g));
   }
-  CKL(launch_gn_bwd(tmp.da, 0, final_.cf, final_.st, (const float*)get("final_block.gn.w", 2, 256),
+  if (!(skip_ & 4u)) CKL(launch_gn_bwd(tmp.da, 0, final_.cf, final_.st, (const float*)get("final_block.gn.w", 2, 256),
                    (const float*)get("final_block.gn.b", 2, 256), mask1, gn_partials_, tmp.dc, B, T, cfg.bf16, stream_));
   launches_ += 3;
   {
@@ -788,6 +824,13 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   launches_ += 2;
   // ---- down 0: transformer blocks only (nothing trainable upstream of them) ----
   CK(stage_bwd(stages_[0], dh32, dh16, nullptr, true, grad_scale, tmp));
+  if (cfg.lora_r > 0) {   // join the side stream, then one final reduction of every block's split partials into the grads
+    for (int par = 0; par < 2; ++par)
+      if (wgrad_side_ && ev_done_valid_[par]) { cudaStreamWaitEvent(stream_, ev_done_[par], 0); ev_done_valid_[par] = false; }
+    CKL(launch_lora_wgrad_final(lora_table_dev_, n_tbs(), cfg.n_blocks, tmp.wg_scratch, tmp.wg_stride, lora_wgrad_splits(MT),
+                                lora_wgrad_splits(MH), cfg.lora_r, grad_scale, grad_scale_dev_, stream_));
+    ++launches_;
+  }
   if (missing_) return -1;
   return 0;
 }

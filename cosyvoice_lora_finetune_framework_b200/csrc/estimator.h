@@ -43,7 +43,9 @@ struct TBRec {
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
-struct BwdTemps { void *dpre, *dx, *dO, *dqkv; float* delta; void *dc, *da; float* wg_scratch; void* dxe; };
+struct BwdTemps {
+  void *dpre, *dx, *dO; void* dqkv[2]; float* delta; void *dc, *da; float* wg_scratch; long wg_stride; void* dxe[2];
+};
 
 struct PlanKey {
   int B, T, training; uintptr_t ws;
@@ -122,8 +124,15 @@ class Estimator {
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;
   cudaEvent_t ev_get();
-  void prof_begin(int cls, double flops);
-  void prof_end();
+  void prof_begin(int cls, double flops, cudaStream_t st = nullptr);
+  void prof_end(cudaStream_t st = nullptr);
+  // LoRA weight-gradient reductions are leaves of the backward graph: they run on a side stream (fork after the q/k/v
+  // dgrad GEMM, join before the batched final reduction) over double-buffered dqkv / v operands
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_done_[2] = {nullptr, nullptr};
+  bool ev_done_valid_[2] = {false, false};
+  bool wgrad_side_ = false;  // CVFLOW_WGRAD_SIDE=1 (measured: no gain over PDL-chained launches on one stream)
+  unsigned skip_ = 0;        // CVFLOW_SKIP bit mask (profiling aid, results become garbage): 1 attention, 2 layernorm, 4 groupnorm, 8 wgrad, 16 gemm
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
   int *kmax1_ = nullptr, *kmax2_ = nullptr;
   void *cat0_ = nullptr, *cat1_ = nullptr;

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cvflow {
 
@@ -46,7 +47,10 @@ struct EpiPrefetch {
 // run together share the A tile in L2). Accumulators are double-buffered in TMEM (2 x BN columns),
 // so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the TMA + MMA main
 // loop of tile i+1.
-template <int BN>
+// CL > 1: thread-block clusters of CL CTAs along N work on the same m-tile; every CTA fetches 1/CL of the A rows of
+// a k-block and TMA-multicasts it to the whole cluster, so the L2 -> SM traffic of the (bandwidth-bound, short-K)
+// GEMMs of this model drops from A + B to A/CL + B per k-block.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, (BN == 256) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -63,8 +67,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int ntn = p.grid_y;                    // n-tiles
-  const int total_tiles = p.grid_x * ntn;
+  const int ntn_g = (p.grid_y + CL - 1) / CL;  // groups of CL n-tiles (the last one may hold phantom tiles beyond N)
+  const int total_super = p.grid_x * ntn_g;    // (m-tile, n-group) work items of a cluster
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  constexpr int kSliceRows = BM / CL;
   long long* dbg = p.dbg ? p.dbg + (long)blockIdx.x * 8 : nullptr;
   auto stamp = [&](int k) {
     if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
@@ -74,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -91,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before a peer multicasts / arrives into them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -101,8 +110,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / ntn, nt = tile - mt * ntn;
+      for (int st = cluster_id; st < total_super; st += n_clusters) {
+        const int mt = st / ntn_g, nt = (st - mt * ntn_g) * CL + rank;
         const int b = mt / p.tiles_per_batch;
         const int i0 = (mt - b * p.tiles_per_batch) * BM;
         const int n0 = nt * BN;
@@ -114,7 +123,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
+            if (CL > 1)
+              tma_load_3d_mc(sa + rank * kSliceRows * 128, tm, full_bar(stage), sg.a_col0 + kb * BK,
+                             i0 + sg.row_shift + rank * kSliceRows, b, kMask);
+            else
+              tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
             tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
@@ -127,7 +140,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int st = cluster_id; st < total_super; st += n_clusters, ++it) {
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
@@ -144,7 +157,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if (CL > 1) umma_commit_mc(empty_bar(stage), kMask);   // the stage is refilled by every CTA of the cluster
+          else umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
@@ -185,9 +199,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       if (lane == 0) { tma_store_3d(tm, stg, col, row0, b); tma_store_commit(); }
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int st = cluster_id; st < total_super; st += n_clusters, ++it) {
       const int acc = it & 1;
-      const int mt = tile / ntn, nt = tile - mt * ntn;
+      const int mt = st / ntn_g, nt = (st - mt * ntn_g) * CL + rank;
       const int b = mt / p.tiles_per_batch;
       const int i0 = (mt - b * p.tiles_per_batch) * BM;
       const int n0 = nt * BN;
@@ -332,6 +346,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   if (warp >= 2 && lane == 0) tma_store_wait_all();   // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into / arrive on its shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * Cfg::kTmemCols);
@@ -468,6 +483,16 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->block_n = bn;
   p->grid_x = (int)mtiles;
   p->grid_y = (a.n_valid + bn - 1) / bn;
+  // cluster width (A-tile multicast along N): opt-in with CVFLOW_GEMM_CLUSTER=2|4. Measured on the estimator's shapes it
+  // does not pay (these launches are latency- not L2-bandwidth-bound: 9.7 -> 10.3 us for the q/k/v GEMM), so the default is 1.
+  static int cl_env = -1;
+  if (cl_env < 0) { const char* e = getenv("CVFLOW_GEMM_CLUSTER"); cl_env = e ? atoi(e) : 1; }
+  int cl = 1;
+  if (bn != 256 && !a.transposed_out) cl = p->grid_y >= 4 ? 4 : (p->grid_y >= 2 ? 2 : 1);
+  if (bn == 128 && cl > 2) cl = 2;
+  if (cl_env != 2 && cl_env != 4) cl = 1;
+  else if (cl_env < cl) cl = cl_env;
+  p->cluster = cl;
   for (int s = 0; s < 2; ++s) {
     if (!a.A[s] || (s == 1 && !use1)) continue;
     if ((reinterpret_cast<uintptr_t>(a.A[s]) & 15) || (a.a_ld[s] % 8) || (a.a_bstride[s] % 8))
@@ -475,7 +500,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
     int r = tma_encode_3d(&p->tmA[s], a.A[s], a.bf16, (uint64_t)a.a_cols[s], (uint64_t)a.a_rows[s],
                           (uint64_t)a.nbatch, (uint64_t)a.a_ld[s] * 2,
                           (uint64_t)(a.nbatch > 1 ? a.a_bstride[s] : a.a_ld[s] * (long)a.a_rows[s]) * 2,
-                          BK, BM, 1);
+                          BK, BM / p->cluster, 1);
     if (r) GEMM_FAIL("gemm: cuTensorMapEncodeTiled(A[%d]) failed (%d)", s, r);
   }
   if (!use1) p->tmA[1] = p->tmA[0];
@@ -516,12 +541,12 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
 int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<64>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<128>::kSmemBytes);
-    cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GemmCfg<256>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
     attr_done = true;
   }
   static int num_sms = 0;
@@ -530,15 +555,28 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const long total = (long)p.grid_x * p.grid_y;
-  const long slots = (long)num_sms * (p.block_n == 256 ? 1 : 2);
+  const int cl = p.cluster;
+  const long total = (long)p.grid_x * ((p.grid_y + cl - 1) / cl) * cl;   // CTAs if every (m-tile, n-group) had its own cluster
+  long slots = (long)num_sms * (p.block_n == 256 ? 1 : 2);
+  slots -= slots % cl;
   dim3 grid((unsigned)(total < slots ? total : slots));
-  if (p.block_n == 256)
-    launch_pdl(gemm_tc_kernel<256>, grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream, p);
-  else if (p.block_n == 128)
-    launch_pdl(gemm_tc_kernel<128>, grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream, p);
-  else
-    launch_pdl(gemm_tc_kernel<64>, grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = (unsigned)cl; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = cl > 1 ? 2 : 1;
+#define CVFLOW_GEMM_LAUNCH(BN_, CL_)                               \
+  do {                                                             \
+    cfg.dynamicSmemBytes = GemmCfg<BN_>::kSmemBytes;               \
+    cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN_, CL_>, p);         \
+  } while (0)
+  if (p.block_n == 256) CVFLOW_GEMM_LAUNCH(256, 1);
+  else if (p.block_n == 128) { if (cl == 2) CVFLOW_GEMM_LAUNCH(128, 2); else CVFLOW_GEMM_LAUNCH(128, 1); }
+  else { if (cl == 4) CVFLOW_GEMM_LAUNCH(64, 4); else if (cl == 2) CVFLOW_GEMM_LAUNCH(64, 2); else CVFLOW_GEMM_LAUNCH(64, 1); }
+#undef CVFLOW_GEMM_LAUNCH
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -78,7 +78,8 @@ struct alignas(64) GemmParams {
   const float* rowmask; const float* resid; long ldr;
   long long* dbg;
   const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
-  int block_n;   // 128 or 256
+  int block_n;   // 64, 128 or 256
+  int cluster;   // CTAs per cluster along N sharing (multicasting) the A tile: 1, 2 or 4
   int grid_x, grid_y;
 };
 

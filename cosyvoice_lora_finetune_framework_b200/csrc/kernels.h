@@ -112,8 +112,12 @@ int lora_wgrad_plan_bytes();
 long lora_wgrad_scratch_floats(long M, int r);
 int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void* u16, long ld_u, const void* v16,
                        long ld_v, long M, int r, float* scratch, int bf16, char* err, int errlen);
-int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float grad_scale, const float* grad_scale_dev,
-                      cudaStream_t st);
+// per block: split partial reductions into its scratch region (any stream) ...
+int lora_wgrad_splits(long M);
+int lora_wgrad_launch_partial(const void* plan, cudaStream_t st);
+// ... and one final reduction for all nb blocks (block i: scratch + i*stride; the first / last nfull blocks are full-rate)
+int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
+                            int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st);
 
 // ---- optim.cu ------------------------------------------------------------------------------
 // Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).

@@ -194,24 +194,32 @@ __global__ void __launch_bounds__(192, 2) lora_wgrad_tc_kernel(const __grid_cons
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 64); }
 }
 
-__global__ void __launch_bounds__(256) lora_wgrad_final_kernel(const LoraBlockPtrs* __restrict__ blkp,
-                                                               const float* __restrict__ part_b, const float* __restrict__ part_a,
-                                                               int S, int r, float grad_scale, const float* __restrict__ gs_dev) {
+// One launch for every attention block of the step: block i keeps its split partials in its own scratch region
+// (scratch + i * stride), so the tensor-core reductions of the blocks can run on a side stream while the main
+// backward chain continues, and the 64 small final reductions collapse into this one.
+__global__ void __launch_bounds__(256) lora_wgrad_final_kernel(const LoraBlockPtrs* __restrict__ blocks, int nb, int nfull,
+                                                               const float* __restrict__ scratch, long stride, int S_full,
+                                                               int S_half, int r, float grad_scale,
+                                                               const float* __restrict__ gs_dev) {
   pdl_wait();
   pdl_launch();
-  const int nb = 1536 * r, na = 3 * r * 256;
+  const int nbw = 1536 * r, na = 3 * r * 256;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= nb + na) return;
+  if (i >= nbw + na) return;
+  const int bi = blockIdx.y;
+  const int S = (bi < nfull || bi >= nb - nfull) ? S_full : S_half;   // full-rate stages come first and last
+  const float* part_b = scratch + (long)bi * stride;
+  const float* part_a = part_b + (long)S * 1536 * r;
   if (gs_dev) grad_scale *= gs_dev[0];
-  const LoraBlockPtrs& blk = *blkp;
+  const LoraBlockPtrs& blk = blocks[bi];
   float s = 0.f;
-  if (i < nb) {
-    for (int sp = 0; sp < S; ++sp) s += part_b[(long)sp * nb + i];
+  if (i < nbw) {
+    for (int sp = 0; sp < S; ++sp) s += part_b[(long)sp * nbw + i];
     const int n_all = i / r, j = i - n_all * r;
     const int pj = n_all >> 9, n = n_all & 511;
     if (blk.p[pj].dB) blk.p[pj].dB[n * r + j] += s * grad_scale * blk.p[pj].scaling;
   } else {
-    const int k2 = i - nb;                 // (p, j, k)
+    const int k2 = i - nbw;                 // (p, j, k)
     const int pj = k2 / (r * 256), rem = k2 - pj * r * 256;
     const int j = rem >> 8, k = rem & 255;
     for (int sp = 0; sp < S; ++sp) s += part_a[((long)sp * 256 + k) * 64 + pj * r + j];
@@ -225,6 +233,7 @@ static int wgrad_splits(long M) {
   if (s > 32) s = 32;
   return (int)s;
 }
+int lora_wgrad_splits(long M) { return wgrad_splits(M); }
 long lora_wgrad_scratch_floats(long M, int r) {
   const long S = wgrad_splits(M);
   return S * (1536L * r + 256L * 64) + 64;
@@ -250,8 +259,7 @@ int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void*
   return 0;
 }
 
-int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float grad_scale, const float* gs_dev,
-                      cudaStream_t st) {
+int lora_wgrad_launch_partial(const void* plan, cudaStream_t st) {
   const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
   static bool attr_done = false;
   if (!attr_done) {
@@ -259,9 +267,14 @@ int lora_wgrad_launch(const void* plan, const LoraBlockPtrs* block_dev, float gr
     attr_done = true;
   }
   launch_pdl(lora_wgrad_tc_kernel, dim3(p->S, 14), 192, kWgSmem, st, *p);
-  const int total = 1536 * p->r + 3 * p->r * 256;
-  launch_pdl(lora_wgrad_final_kernel, (total + 255) / 256, 256, 0, st, block_dev, (const float*)p->part_b,
-             (const float*)p->part_a, p->S, p->r, grad_scale, gs_dev);
+  LAUNCH_RET();
+}
+
+int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
+                            int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st) {
+  const int total = 1536 * r + 3 * r * 256;
+  launch_pdl(lora_wgrad_final_kernel, dim3((total + 255) / 256, nb), 256, 0, st, blocks_dev, nb, nfull, scratch, stride, S_full,
+             S_half, r, grad_scale, gs_dev);
   LAUNCH_RET();
 }
 

@@ -141,3 +141,15 @@ def test_two_sources_and_interleaved_rows():
     ref = torch.cat([a0, a1s], -1).float() @ W.float().t()
     assert torch.allclose(out[:, 1::2, 256:].float(), ref, atol=1e-2, rtol=3e-3)
     assert out[:, 0::2].abs().max().item() == 0 and out[:, :, :256].abs().max().item() == 0
+
+
+def test_cluster_multicast_path_matches():
+    """The opt-in A-tile multicast (thread-block clusters along N, CVFLOW_GEMM_CLUSTER=4) is read once per process,
+    so the same parity tests run in a child process with it enabled."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CVFLOW_GEMM_CLUSTER="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "not cluster_multicast"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
