@@ -197,8 +197,20 @@ def run_reference(a):
     print(json.dumps(out))
 
 
+def _trace(msg):
+    if os.environ.get("CVFLOW_BENCH_TRACE"):
+        print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def run_cvflow(a):
     import torch.distributed as dist
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if os.environ.get("CVFLOW_BENCH_TRACE"):   # where is a hung rank? dump every thread's stack after a while
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("CVFLOW_BENCH_TRACE_AFTER", "75")), repeat=False, file=sys.stderr)
     from cosyvoice_lora_finetune_framework_b200 import _estimator as E
     from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer
     rank = int(os.environ.get("RANK", "0"))
@@ -208,6 +220,7 @@ def run_cvflow(a):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    _trace("process group ready")
     dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float16
     B, T, K, W = a.batch, a.frames, a.steps, max(3, a.warmup)
     cfm, est, stats = build_model(a, device, dtype)
@@ -246,12 +259,17 @@ def run_cvflow(a):
         return float(ms.item())
 
     count = lambda: ne.launch_count() + sum(r.launch_count() for r in ne.replicas)
+    _trace("model built")
     eager_step(batch)
+    torch.cuda.synchronize()
+    _trace("first eager step done")
     l0 = count()
     eager_step(batch)
     per_step_launches = (count() - l0) + max(1, a.streams) * (1 + 3) + (2 + 1 + 1)   # + cfm_prep, loss(3), sumsq(2), adamw, merge
     for _ in range(W):
         step(batch)
+    torch.cuda.synchronize()
+    _trace("warm-up (graph capture) done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -259,6 +277,7 @@ def run_cvflow(a):
     launches = K * per_step_launches
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * T * K / (ms / 1e3)
+    _trace("timed region done: %.2f ms/step" % (ms / K))
 
     # ---- end to end through the public API with host buffers --------------------------------------
     host = {k: v.cpu().pin_memory() for k, v in batch.items()}
@@ -275,15 +294,19 @@ def run_cvflow(a):
 
     e2e_step()
     ms_e2e = timed(e2e_step, K)
+    _trace("e2e done")
     e2e_val = world * B * T * K / (ms_e2e / 1e3)
 
     # ---- per-kernel-class device time (CUDA events on the launching stream) -----------------------
     roofline, kernels = None, None
+    L = E._lib()
     if rank == 0:
-        L = E._lib()
         L.cvflow_set_profile(ne.handle, 1)
-        for _ in range(2):
-            eager_step(batch)
+    for _ in range(2):          # every rank steps (the optimiser step holds the gradient allreduce); rank 0 records
+        eager_step(batch)
+    sync()
+    _trace("profiled eager steps done")
+    if rank == 0:
         n = 5
         msa, cnt, fl = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)()
         L.cvflow_profile_read(ne.handle, msa, cnt, fl, n)
@@ -304,7 +327,7 @@ def run_cvflow(a):
 
     # ---- Euler-ODE inference (BASELINE configs[1]) -------------------------------------------------
     inference = None
-    if rank == 0 and not a.no_inference:
+    if rank == 0 and world == 1 and not a.no_inference:   # batch-1 by construction (replicas only): reported at N=1
         est.eval()
         Ti, P_, n_steps = 700, 200, 10
         g = torch.Generator().manual_seed(5)
@@ -316,7 +339,7 @@ def run_cvflow(a):
         run = lambda: cfm(mu=mu.clone(), mask=mask1, n_timesteps=n_steps, spks=spk, cond=cond, prompt_len=P_)
         for _ in range(3):
             run()
-        ms_inf = timed(run, 10) / 10 if world == 1 else None
+        ms_inf = timed(run, 10) / 10
         if ms_inf:
             audio_s = (Ti - P_) * 256 / 22050.0
             inference = {"config": "configs[1]: 10 Euler steps + CFG, 500 target + 200 prompt frames, CUDA-graph replay",
@@ -341,9 +364,19 @@ def run_cvflow(a):
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
                "inference": inference, "valid_frames_per_step_rank0": int(lens.sum()),
                "lora": {"replaced_layers": stats["replaced_layers"], "lora_params": stats["lora_params"]}}
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
+        # NCCL: a communicator whose collectives were captured into a CUDA graph must outlive that graph -- drop the
+        # captured step first, and never let a teardown problem turn a finished benchmark into a hang
+        sys.stdout.flush()
+        dist.barrier()
+        trainer._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
