@@ -219,9 +219,9 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, gn_partials_, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
                        tb, tb_stride, nullptr, a1, 0, B, L, cfg.bf16, stream_));
-    launches_ += 3;
+    launches_ += 2;
   }
   {
     GemmArgs g = conv3_args(a1, B, L, 256, 0, 256, get(P + ".block2.w", cfg.bf16, 256L * 768), 256, c2, 256, 0);
@@ -239,7 +239,7 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, gn_partials_, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
                        nullptr, 0, r, h, 1, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -547,7 +547,7 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, gn_partials_, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
                        mask1, nullptr, 0, nullptr, af, 0, B, T, cfg.bf16, stream_));
     launches_ += 3;
   }

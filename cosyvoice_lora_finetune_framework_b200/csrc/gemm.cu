@@ -270,9 +270,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
             }
-            if (p.act == ACT_GELU_TANH) {
+            if (p.act == ACT_GELU_TANH) {   // packed fp32x2 arithmetic: half the issue slots
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+              for (int j = 0; j < 32; j += 2) f2_unpack(gelu_tanh_f2(f2_pack(x[j], x[j + 1])), x[j], x[j + 1]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
@@ -288,7 +288,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               unpack2_h16(v.w, bf, pre[6], pre[7]);
               if (p.act == ACT_MUL_GELU_TANH_GRAD) {   // kernel-uniform branch hoisted out of the element loop
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[8 * j + e] *= gelu_tanh_grad_f(pre[e]);
+                for (int e = 0; e < 8; e += 2)
+                  f2_unpack(gelu_tanh_grad_mul_f2(f2_pack(x[8 * j + e], x[8 * j + e + 1]), f2_pack(pre[e], pre[e + 1])),
+                            x[8 * j + e], x[8 * j + e + 1]);
               } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[8 * j + e] *= gelu_erf_grad_f(pre[e]);

@@ -160,35 +160,33 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restric
     o[2] = n > 0.f ? q - a * a / n : 0.f;
   }
 }
-__global__ void gn_stats_final_kernel(const float* __restrict__ partials, float* __restrict__ stats, int nsplit,
-                                      int total) {
-  pdl_wait();
-  pdl_launch();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, g)
-  if (i >= total) return;
-  const int b = i >> 3, g = i & 7;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
+// Chan merge of the split partials of one (sample, group): every consumer thread does it for its own group
+// (a few dozen cached loads) instead of a separate single-CTA launch between the reduction and the apply pass.
+__device__ __forceinline__ void gn_merge_partials(const float* __restrict__ partials, int b, int g, int nsplit, float& mean,
+                                                  float& rstd) {
+  float n = 0.f, mu = 0.f, m2 = 0.f;
   for (int s = 0; s < nsplit; ++s) {
     const float* p = partials + (((long)b * nsplit + s) * 8 + g) * 3;
     const float nb = p[0];
     if (nb <= 0.f) continue;
-    const float delta = p[1] - mean;
+    const float delta = p[1] - mu;
     const float nn = n + nb;
-    mean += delta * nb / nn;
+    mu += delta * nb / nn;
     m2 += p[2] + delta * delta * n * nb / nn;
     n = nn;
   }
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(m2 / n + 1e-5f);
+  mean = mu;
+  rstd = rsqrtf(m2 / n + 1e-5f);
 }
 int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st) {
   const int ns = gn_num_splits(B, L);
+  (void)stats;   // written by the apply pass (first row of every sample)
   launch_pdl(gn_stats_kernel, dim3(ns, B), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials, L, ns, bf16);
-  launch_pdl(gn_stats_final_kernel, (B * 8 + 127) / 128, 128, 0, st, partials, stats, ns, B * 8);
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ partials,
+                                                       int nsplit, float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mask, const float* __restrict__ tb, long tb_stride,
                                                        const uint16_t* __restrict__ add16, void* __restrict__ out, int mode,
@@ -201,7 +199,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
   const int lane = (int)(i & 31);
   const int b = (int)(row / L);
   const int c8 = lane * 8, grp = lane >> 2;
-  const float mean = stats[(b * 8 + grp) * 2], rstd = stats[(b * 8 + grp) * 2 + 1];
+  float mean, rstd;
+  gn_merge_partials(partials, b, grp, nsplit, mean, rstd);
+  if (row == (long)b * L && (lane & 3) == 0) {   // keep (mean, rstd) for the backward pass
+    stats[(b * 8 + grp) * 2] = mean;
+    stats[(b * 8 + grp) * 2 + 1] = rstd;
+  }
   const float m = mask[row];
   float x[8], g[8], be[8];
   load8_h16(c + row * 256 + c8, bf, x);
@@ -227,11 +230,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
     store8_f32(reinterpret_cast<float*>(out) + row * 256 + c8, x);
   }
 }
-int launch_gn_apply(const void* c16, const float* stats, const float* gamma, const float* beta, const float* mask,
-                    const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L, int bf16,
-                    cudaStream_t st) {
+int launch_gn_apply(const void* c16, const float* partials, float* stats, const float* gamma, const float* beta,
+                    const float* mask, const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L,
+                    int bf16, cudaStream_t st) {
   const long M = (long)B * L, n = M * 32;
-  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), stats, gamma,
+  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials,
+                                                               gn_num_splits(B, L), stats, gamma,
                                                                beta, mask, tb, tb_stride,
                                                                reinterpret_cast<const uint16_t*>(add16), out, mode, L,
                                                                M, bf16);
@@ -293,26 +297,12 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
     o[0] = a; o[1] = q;
   }
 }
-__global__ void gn_bwd_final_kernel(float* __restrict__ partials, float* __restrict__ sums, int nsplit, int total,
-                                    float inv_n) {
-  pdl_wait();
-  pdl_launch();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int b = i >> 3, g = i & 7;
-  float a = 0.f, q = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float* p = partials + (((long)b * nsplit + s) * 8 + g) * 2;
-    a += p[0]; q += p[1];
-  }
-  sums[2 * i] = a * inv_n;
-  sums[2 * i + 1] = q * inv_n;
-}
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32,
                                                            const uint16_t* __restrict__ c, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ mask, const float* __restrict__ sums,
-                                                           uint16_t* __restrict__ dc, int L, long M, int bf) {
+                                                           const float* __restrict__ mask, const float* __restrict__ partials,
+                                                           int nsplit, float inv_n, uint16_t* __restrict__ dc, int L, long M,
+                                                           int bf) {
   pdl_wait();
   pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,7 +312,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
   const int b = (int)(row / L);
   const int c8 = lane * 8, grp = lane >> 2;
   const float mean = stats[(b * 8 + grp) * 2], rstd = stats[(b * 8 + grp) * 2 + 1];
-  const float m1 = sums[(b * 8 + grp) * 2], m2 = sums[(b * 8 + grp) * 2 + 1];
+  float m1 = 0.f, m2 = 0.f;   // group means of dxhat and dxhat * xhat from the split partials
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const float* pp = partials + (((long)b * nsplit + sp) * 8 + grp) * 2;
+    m1 += pp[0]; m2 += pp[1];
+  }
+  m1 *= inv_n; m2 *= inv_n;
   float xh[8], dxh[8];
   gn_bwd_load(dy, dy_f32, c, gamma, beta, mean, rstd, mask[row], row * 256 + c8, c8, bf, xh, dxh);
 #pragma unroll
@@ -335,10 +330,9 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
   const int ns = gn_num_splits(B, L);
   const uint16_t* c = reinterpret_cast<const uint16_t*>(c16);
   launch_pdl(gn_bwd_reduce_kernel, dim3(ns, B), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, partials, L, ns, bf16);
-  float* sums = partials + (long)B * ns * 8 * 2;
-  launch_pdl(gn_bwd_final_kernel, (B * 8 + 127) / 128, 128, 0, st, partials, sums, ns, B * 8, 1.f / (32.f * (float)L));
   const long M = (long)B * L, n = M * 32;
-  launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, sums,
+  launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask,
+                                                                   (const float*)partials, ns, 1.f / (32.f * (float)L),
                                                                    reinterpret_cast<uint16_t*>(dc16), L, M, bf16);
   LAUNCH_RET();
 }
