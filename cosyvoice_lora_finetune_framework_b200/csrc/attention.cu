@@ -179,7 +179,8 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = plan.L, bf = plan.bf16;
-  const int npairs = (L + 255) / 256;
+  const int tpi = plan.tpi;
+  const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
   long long* dbg = plan.dbg ? plan.dbg + (long)blockIdx.x * 32 : nullptr;
   auto stamp = [&](int k) {
@@ -215,10 +216,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     if (lane == 0) {
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);   // extent of the next item: load issued early
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);   // extent of the next item: load issued early
         if (!a.act[0]) continue;
         mbar_wait(q_empty(qs), qph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
@@ -226,7 +227,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
         for (int t = 0; t < ntile; ++t)
           for (int hf = 0; hf < 2; ++hf)
             tma_load_3d(base + FwdSmem::kQ + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, q_full(qs), a.h * 64,
-                        (2 * a.pair + t) * 128 + hf * 64, a.b);
+                        (a.tile0 + t) * 128 + hf * 64, a.b);
         const int nkb = (a.ext + kFwdKB - 1) / kFwdKB;
         for (int blk = 0; blk < nkb; ++blk) {
           const int k0 = blk * kFwdKB;
@@ -252,10 +253,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
       const uint32_t idesc_o = umma_idesc_f16(bf, 128, 64, 0, 1);
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);
         if (!a.act[0]) continue;
         mbar_wait(q_full(qs), qph);
         if (w == 0 && n == 0) stamp(17);
@@ -302,21 +303,21 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     const int wtid = threadIdx.x & 127;
     const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
     uint32_t n = 0;
-    const int nwords = 8 * npairs;
+    const int nwords = 8 * ((L + 255) / 256);
     const int* bits_base = kmax_arr + ((plan.B + 3) & ~3);
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kmax_arr);
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
     uint4 nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
     uint4 nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const AttnItem a = nxt;
       const uint4 fb0 = nb0, fb1 = nb1;   // validity words of the item's first key block
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kmax_arr);
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);
       nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
       nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
-      const int qi = (2 * a.pair + w) * 128 + r;
+      const int qi = (a.tile0 + w) * 128 + r;
       uint16_t* dst = o_out + ((long)a.b * L + qi) * 512 + a.h * 64;
       if (!a.act[w]) {   // tile of padding rows only: defined zeros instead of the reference's masked garbage
-        if (qi < L) {
+        if (w < tpi && qi < L) {   // (with one tile per item the second warpgroup owns no tile at all)
 #pragma unroll
           for (int u = 0; u < 8; ++u) reinterpret_cast<uint4*>(dst)[u] = make_uint4(0u, 0u, 0u, 0u);
           if (lse_out) lse_out[((long)a.b * 8 + a.h) * L + qi] = INFINITY;
@@ -410,7 +411,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
         fence_proxy_async_smem();
         wg_bar_sync(w);
         if (wtid == 0) {
-          const int q0 = (2 * a.pair + w) * 128;
+          const int q0 = (a.tile0 + w) * 128;
           tma_store_3d(&plan.tm_o, stg, a.h * 64, q0, a.b);
           if (q0 + 64 < L) tma_store_3d(&plan.tm_o, stg + 8192, a.h * 64, q0 + 64, a.b);
           tma_store_commit();
@@ -450,7 +451,8 @@ int attn_fwd_launch(void* plan_, const int* kinfo, int iso_p, void* o, float* ls
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kBytes);
     attr_done = true;
   }
-  const int n_items = p->B * 8 * ((p->L + 255) / 256);
+  p->tpi = attn_tiles_per_item(p->B, p->L);
+  const int n_items = attn_num_items(p->B, p->L, p->tpi);
   const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
   launch_pdl(attn_fwd_kernel, dim3((unsigned)grid), kAttnThreads, FwdSmem::kBytes, st, *p, kinfo, iso_p,
              reinterpret_cast<uint16_t*>(o), lse);

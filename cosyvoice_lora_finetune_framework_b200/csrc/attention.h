@@ -27,6 +27,7 @@ struct AttnPlan {
   CUtensorMap tm_dqkv;  // backward output [B][L][1536], box {64, 64, 1} (TMA store)
   const void* o_ptr;    // destination tm_o / tm_dqkv was encoded for
   int B, L, bf16;
+  int tpi;              // 128-row tiles per item: 2 (one per warpgroup) or, when that leaves SMs idle, 1 (warpgroup 0 only)
   long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
 };
 
@@ -37,21 +38,21 @@ static constexpr float kAttnScaleLog2 = 0.125f * 1.4426950408889634f;     // d^-
 static constexpr int kAttnThreads = 352;
 
 struct AttnItem {
-  int b, h, pair;       // pair of 128-row tiles: tiles 2*pair, 2*pair+1
+  int b, h, tile0;      // the item's 128-row tiles: tile0 (warpgroup 0) and, with two tiles per item, tile0 + 1 (warpgroup 1)
   int kmax;             // valid extent of sample b (0 = nothing valid)
   int ext;              // kmax rounded up to 16 (MMA granularity), <= round16(L)
   bool act[2];          // does tile (2*pair + w) contain a valid row?
 };
-__device__ __forceinline__ AttnItem attn_item(int it, int npairs, const int* __restrict__ kmax_arr) {
+__device__ __forceinline__ AttnItem attn_item(int it, int npairs, int tpi, const int* __restrict__ kmax_arr) {
   AttnItem a;
-  a.pair = it % npairs;
+  a.tile0 = (it % npairs) * tpi;
   const int bh = it / npairs;
   a.h = bh & 7;
   a.b = bh >> 3;
   a.kmax = kmax_arr[a.b];
   a.ext = (a.kmax + 15) & ~15;
-  a.act[0] = (2 * a.pair) * 128 < a.kmax;
-  a.act[1] = (2 * a.pair + 1) * 128 < a.kmax;
+  a.act[0] = a.tile0 * 128 < a.kmax;
+  a.act[1] = tpi == 2 && (a.tile0 + 1) * 128 < a.kmax;
   return a;
 }
 
@@ -120,5 +121,8 @@ __device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) 
 }
 
 int attn_num_sms();
+// items of a launch and tiles per item: two tiles per item unless that leaves SMs without work (small batches, inference)
+inline int attn_tiles_per_item(int B, int L) { return B * 8 * (((L + 127) / 128 + 1) / 2) >= attn_num_sms() ? 2 : 1; }
+inline int attn_num_items(int B, int L, int tpi) { return B * 8 * (((L + 127) / 128 + tpi - 1) / tpi); }
 
 }  // namespace cvflow

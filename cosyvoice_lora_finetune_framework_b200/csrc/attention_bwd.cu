@@ -56,7 +56,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = plan.L, bf = plan.bf16;
-  const int npairs = (L + 255) / 256;
+  const int tpi = plan.tpi;
+  const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
 
   if (threadIdx.x == 0) {
@@ -86,17 +87,17 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
     if (lane == 0) {
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
         if (!a.act[0]) continue;
         mbar_wait(q_empty(qs), qph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
         mbar_expect_tx(q_full(qs), (uint32_t)ntile * 32768u);
         for (int t = 0; t < ntile; ++t)
           for (int hf = 0; hf < 2; ++hf) {
-            const int row = (2 * a.pair + t) * 128 + hf * 64;
+            const int row = (a.tile0 + t) * 128 + hf * 64;
             tma_load_3d(base + DqSmem::kQ + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, q_full(qs), a.h * 64, row, a.b);
             tma_load_3d(base + DqSmem::kdO + qs * 32768 + t * 16384 + hf * 8192, &plan.tm_do, q_full(qs), a.h * 64, row, a.b);
           }
@@ -125,10 +126,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
       const uint32_t idesc_q = umma_idesc_f16(bf, 128, 64, 0, 1);
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0, m = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
         if (!a.act[0]) continue;
         mbar_wait(q_full(qs), qph);
         const int nkb = (a.ext + kDqKB - 1) / kDqKB;
@@ -176,18 +177,18 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
     const int r = qd * 32 + lane;
     const int wtid = threadIdx.x & 127;
     const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
-    const int nwords = 8 * npairs;
+    const int nwords = 8 * ((L + 255) / 256);
     const int* bits_base = kinfo + ((plan.B + 3) & ~3);
     uint32_t n = 0, m = 0;
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const AttnItem a = nxt;
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
-      const int q0 = (2 * a.pair + w) * 128;
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+      const int q0 = (a.tile0 + w) * 128;
       const int qi = q0 + r;
       const long stat_idx = ((long)a.b * 8 + a.h) * L + qi;
       if (!a.act[w]) {   // tile of padding rows only
-        if (qi < L) {
+        if (w < tpi && qi < L) {
           uint16_t* dst = dqkv + ((long)a.b * L + qi) * 1536 + a.h * 64;
 #pragma unroll
           for (int u = 0; u < 8; ++u) reinterpret_cast<uint4*>(dst)[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -336,7 +337,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = plan.L, bf = plan.bf16;
-  const int npairs = (L + 255) / 256;
+  const int tpi = plan.tpi;
+  const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
 
   if (threadIdx.x == 0) {
@@ -365,17 +367,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
     if (lane == 0) {
       int ks = 0, ring = 0;
       uint32_t kph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
         if (!a.act[0]) continue;
         mbar_wait(kv_empty(ks), kph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
         mbar_expect_tx(kv_full(ks), (uint32_t)ntile * 32768u);
         for (int t = 0; t < ntile; ++t)
           for (int hf = 0; hf < 2; ++hf) {
-            const int row = (2 * a.pair + t) * 128 + hf * 64;
+            const int row = (a.tile0 + t) * 128 + hf * 64;
             tma_load_3d(base + DkvSmem::kK + ks * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, kv_full(ks), 512 + a.h * 64, row, a.b);
             tma_load_3d(base + DkvSmem::kV + ks * 32768 + t * 16384 + hf * 8192, &plan.tm_qkv, kv_full(ks), 1024 + a.h * 64, row, a.b);
           }
@@ -399,10 +401,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
       const uint32_t idesc_a = umma_idesc_f16(bf, 128, 64, 0, 1);
       int ks = 0, ring = 0;
       uint32_t kph = 0, rph = 0, n = 0, m = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
+        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
         if (!a.act[0]) continue;
         mbar_wait(kv_full(ks), kph);
         const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
@@ -454,18 +456,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
     const int r = qd * 32 + lane;
     const int wtid = threadIdx.x & 127;
     const uint32_t treg = tmem + (uint32_t)(w * 256) + ((uint32_t)(qd * 32) << 16);
-    const int nwords = 8 * npairs;
+    const int nwords = 8 * ((L + 255) / 256);
     const int* bits_base = kinfo + ((plan.B + 3) & ~3);
     float* stat = reinterpret_cast<float*>(gbase + DkvSmem::kStat) + w * 256;   // [2 buffers][lse 64 | delta 64]
     uint32_t n = 0, m = 0;
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, kinfo);
+    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const AttnItem a = nxt;
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, kinfo);
-      const int k0 = (2 * a.pair + w) * 128;
+      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+      const int k0 = (a.tile0 + w) * 128;
       const int kj = k0 + r;
       if (!a.act[w]) {   // tile of padding keys only
-        if (kj < L) {
+        if (w < tpi && kj < L) {
           uint16_t* dst = dqkv + ((long)a.b * L + kj) * 1536 + 512 + a.h * 64;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -616,7 +618,8 @@ int attn_bwd_launch(void* plan_, const void* dout, const int* kinfo, int iso_p, 
     if (r) return -(int)cudaErrorInvalidValue;
     p->o_ptr = dqkv;
   }
-  const int n_items = p->B * 8 * ((p->L + 255) / 256);
+  p->tpi = attn_tiles_per_item(p->B, p->L);
+  const int n_items = attn_num_items(p->B, p->L, p->tpi);
   const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
   launch_pdl(attn_bwd_dq_kernel, dim3((unsigned)grid), kAttnThreads, DqSmem::kBytes, st, *p, kinfo, iso_p,
              reinterpret_cast<const uint16_t*>(o), reinterpret_cast<const uint16_t*>(dout), lse, delta,
