@@ -478,8 +478,10 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   const long mtiles = (long)p->tiles_per_batch * a.nbatch;
   // tile width: these GEMMs are short (K = 256..1536) and latency-bound, so prefer enough CTAs to
   // keep >= 2 resident per SM over wide tiles
+  static int bn256_min = -1;   // tiles needed before 256-wide tiles are used (tuning knob)
+  if (bn256_min < 0) { const char* e = getenv("CVFLOW_GEMM_BN256_MIN"); bn256_min = e ? atoi(e) : 4 * 148; }
   int bn = 64;
-  if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= 4 * 148) bn = 256;
+  if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= bn256_min) bn = 256;
   else if (mtiles * ((a.n_valid + 127) / 128) >= 2 * 148 || a.n_valid > 512) bn = 128;
   if (a.transposed_out) bn = 128;
   p->block_n = bn;
