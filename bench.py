@@ -325,6 +325,28 @@ def run_cvflow(a):
                     "note": "algorithmic FLOPs = 2*M*N*K per launch with M = real (unpadded) rows, summed over the "
                             "%d GEMM launches of a step; event-bracketed, so launch gaps are included" % (cnt[0] // 2)}
 
+    # ---- the GEMM class inside the step graph: step time with and without its launches (PDL-chained, no event gaps) ----
+    if rank == 0 and world == 1 and roofline is not None and use_graph and not os.environ.get("CVFLOW_SKIP"):
+        os.environ["CVFLOW_SKIP"] = "16"            # read when a native estimator is created: its GEMM launches are dropped
+        try:
+            cfm2, _, _ = build_model(a, device, dtype)
+            tr2 = FlowLoRATrainer(cfm2, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0)
+            step2 = lambda: tr2.train_step_graphed(batch["x1"], batch["mask"], batch["mu"], batch["spks"], batch["cond"])
+            for _ in range(W):
+                step2()
+            ms_skip = timed(step2, K)
+            in_graph_ms = (ms - ms_skip) / K
+            if in_graph_ms > 0:
+                ach2 = (fl[0] / 2) / (in_graph_ms * 1e9)
+                roofline["in_graph"] = {"ms_per_step": in_graph_ms, "achieved": ach2, "frac": ach2 / peak,
+                                        "how": "step graph replayed with and without the GEMM launches (CVFLOW_SKIP=16); "
+                                               "the difference is what the %d launches cost inside the PDL-chained graph" % (cnt[0] // 2)}
+            del tr2, cfm2
+        finally:
+            del os.environ["CVFLOW_SKIP"]
+        torch.cuda.empty_cache()
+        _trace("in-graph GEMM marginal done")
+
     # ---- Euler-ODE inference (BASELINE configs[1]) -------------------------------------------------
     inference = None
     if rank == 0 and world == 1 and not a.no_inference:   # batch-1 by construction (replicas only): reported at N=1

@@ -108,3 +108,40 @@ def test_attention_backward(B, L, lens, iso_p, dt):
         # padded rows: dk = dv = 0 exactly (their probability is 0), dq = 0 because dout = 0 there
         if n < L:
             assert dqkv[b, n:].float().abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_attention_mask_with_holes(dt):
+    """The key mask is an arbitrary {0,1} row, not only a prefix (utils.py:103-109 builds the bias from any mask): keys masked
+    in the middle of a sample get probability 0, forward and backward; the valid extent is 1 + the last non-zero index."""
+    L_ = E._lib()
+    torch.manual_seed(11)
+    B, L = 3, 300
+    qkv = (torch.randn(B, L, 1536, device="cuda") * 1.3).to(dt)
+    mask = torch.ones(B, L, device="cuda")
+    mask[0, 40:75] = 0
+    mask[1, 0:10] = 0
+    mask[1, 130:190] = 0
+    mask[1, 260:] = 0
+    mask[2, ::3] = 0
+    ext = [300, 260, 300]
+    dout = (torch.randn(B, L, 512, device="cuda")).to(dt)
+    for b in range(B):
+        dout[b, ext[b]:] = 0
+    o, lse, kmax = _run_fwd(qkv, mask, 0, dt)
+    assert kmax[:B].tolist() == ext
+    delta = torch.zeros(B, 8, L, device="cuda")
+    dqkv = torch.full((B, L, 1536), float("nan"), device="cuda", dtype=dt)
+    N.check(L_.cvflow_attention_backward(qkv.data_ptr(), 1536, B, L, N.dtype_code(dt), mask.data_ptr(), kmax.data_ptr(), 0,
+                                         o.data_ptr(), lse.data_ptr(), dout.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
+                                         E._stream()))
+    torch.cuda.synchronize()
+    ref, gref = _reference(qkv, mask, 0, dout)
+    tol = 6e-3 if dt == torch.float16 else 3e-2
+    for b in range(B):
+        n = ext[b]
+        assert (o[b, :n].float() - ref[b, :n]).abs().max().item() <= tol * max(1.0, ref[b, :n].abs().max().item())
+        got, want = dqkv[b, :n].float(), gref[b, :n]
+        assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+        dead = mask[b, :n] == 0   # masked keys receive no gradient through k and v
+        assert dqkv[b, :n][dead][:, 512:].float().abs().max().item() == 0.0
