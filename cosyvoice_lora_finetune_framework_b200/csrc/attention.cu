@@ -106,8 +106,12 @@ __device__ __forceinline__ void fwd_softmax_chunk(uint32_t t_s, uint32_t t_p, ui
     for (int j = 0; j < NC; j += 2) {
       float a0, a1;
       ffma2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), kAttnScaleLog2, -m_use);
-      p[j] = exp2_fast(a0);
-      p[j + 1] = exp2_fast(a1);
+      if ((CVFLOW_POLY_PAIR_MASK >> (j >> 1)) & 1u) {   // compile-time choice per pair: FMA-pipe polynomial ...
+        exp2_poly2(p[j], p[j + 1], a0, a1);
+      } else {                                          // ... or MUFU.EX2
+        p[j] = exp2_fast(a0);
+        p[j + 1] = exp2_fast(a1);
+      }
       fadd2(rs0, rs1, p[j], p[j + 1]);
     }
   } else {

@@ -122,6 +122,32 @@ __device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) 
       : "f"(b0), "f"(b1));
 }
 
+// 2^x for x <= 0 on the FMA pipe (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, degree-4 polynomial for 2^f
+// (relative error 5e-5, below the 16-bit rounding of the probabilities it feeds), exponent patched in with integer
+// adds. The exp phases of the attention kernels are MUFU-bound (16 ex2 per clock per SM); sending a share of the
+// elements down this path balances the two pipes. Both lanes of a pair are processed with packed fp32x2 arithmetic.
+__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const f32x2 x = f2_pack(x0, x1);
+  const f32x2 magic = f2_pack(12582912.f, 12582912.f), nmagic = f2_pack(-12582912.f, -12582912.f);
+  const f32x2 t = f2_add(x, magic);                       // round-to-nearest integer n lands in the low mantissa bits
+  const f32x2 f = f2_add(x, f2_mul(f2_add(t, nmagic), f2_pack(-1.f, -1.f)));
+  f32x2 p = f2_fma(f2_pack(0.009618129f, 0.009618129f), f, f2_pack(0.05550411f, 0.05550411f));
+  p = f2_fma(p, f, f2_pack(0.2402265f, 0.2402265f));
+  p = f2_fma(p, f, f2_pack(0.6931472f, 0.6931472f));
+  p = f2_fma(p, f, f2_pack(1.f, 1.f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// pairs (of the 16 pairs of a 32-column chunk) whose exponentials take the polynomial path
+#ifndef CVFLOW_POLY_PAIR_MASK
+#define CVFLOW_POLY_PAIR_MASK 0x0000u   // measured: 19 % and 44 % polynomial shares are both slower (issue-bound), so off
+#endif
+
 int attn_num_sms();
 inline int attn_nodead_env() {
   static int v = -1;
