@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvflow.so")
+# CVFLOW_LIB_PATH: load another build of the same ABI (A/B timing of kernel changes on one box)
+LIB_PATH = os.environ.get("CVFLOW_LIB_PATH") or os.path.join(_HERE, "libcvflow.so")
 
 DTYPE_F16 = 0
 DTYPE_BF16 = 1

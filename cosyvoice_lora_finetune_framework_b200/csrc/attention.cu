@@ -330,7 +330,6 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
       }
       const uint4* bits = reinterpret_cast<const uint4*>(bits_base + (long)a.b * nwords);
       const bool q_below = qi < iso_p;
-      const bool warp_dead = !plan.nodead && __all_sync(0xffffffffu, qi >= a.kmax);
       float m_run = -INFINITY, l_run = 0.f;
       float o[64];
 #pragma unroll
@@ -356,36 +355,23 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
         const bool st_on = threadIdx.x == 0 && n < 2;
         if (st_on) stamp(3 + 6 * n);
         tc_fence_after();
-        float m_new = m_run, m_use = (m_run == -INFINITY) ? 0.f : m_run, alpha = 1.f;
+        // pass 1: row maximum over the valid keys of the block
+        float m_loc = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nfull) m_loc = fwd_max_chunk<32>(treg + (uint32_t)(c * 32), vw[c], m_loc);
+        if (tail) m_loc = fwd_max_chunk<16>(treg + (uint32_t)(nfull * 32), vt, m_loc);
+        if (st_on) stamp(4 + 6 * n);
+        const float m_new = fmaxf(m_run, m_loc * kAttnScaleLog2);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = exp2_fast(m_run - m_use);
+        // pass 2: P = 2^(s c - m), row sum, 16-bit P written over S
         float rs0 = 0.f, rs1 = 0.f;
-        if (warp_dead) {
-          // all 32 rows of this warp are padding (beyond the sample's extent): no max / exp work, P = 0
-          uint32_t z[16];
+        if (w == 1 && n == 0) mbar_wait(skew_bar, 0);   // one-shot stagger: the two warpgroups' exp phases alternate
 #pragma unroll
-          for (int j = 0; j < 16; ++j) z[j] = 0u;
-          const int nst = nfull + (tail ? 1 : 0);
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < nst) tmem_st_32x32b_x16(treg + (uint32_t)(c * 16), z);
-          if (w == 1 && n == 0) mbar_wait(skew_bar, 0);
-        } else {
-          // pass 1: row maximum over the valid keys of the block
-          float m_loc = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < nfull) m_loc = fwd_max_chunk<32>(treg + (uint32_t)(c * 32), vw[c], m_loc);
-          if (tail) m_loc = fwd_max_chunk<16>(treg + (uint32_t)(nfull * 32), vt, m_loc);
-          if (st_on) stamp(4 + 6 * n);
-          m_new = fmaxf(m_run, m_loc * kAttnScaleLog2);
-          m_use = (m_new == -INFINITY) ? 0.f : m_new;
-          alpha = exp2_fast(m_run - m_use);
-          // pass 2: P = 2^(s c - m), row sum, 16-bit P written over S
-          if (w == 1 && n == 0) mbar_wait(skew_bar, 0);   // one-shot stagger: the two warpgroups' exp phases alternate
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < nfull) fwd_softmax_chunk<32>(treg + (uint32_t)(c * 32), treg + (uint32_t)(c * 16), vw[c], m_use, rs0, rs1, bf);
-          if (tail) fwd_softmax_chunk<16>(treg + (uint32_t)(nfull * 32), treg + (uint32_t)(nfull * 16), vt, m_use, rs0, rs1, bf);
-        }
+        for (int c = 0; c < 8; ++c)
+          if (c < nfull) fwd_softmax_chunk<32>(treg + (uint32_t)(c * 32), treg + (uint32_t)(c * 16), vw[c], m_use, rs0, rs1, bf);
+        if (tail) fwd_softmax_chunk<16>(treg + (uint32_t)(nfull * 32), treg + (uint32_t)(nfull * 16), vt, m_use, rs0, rs1, bf);
         if (w == 0 && n == 0) mbar_arrive(skew_bar);
         const float rowsum = rs0 + rs1;
         tmem_st_wait();
@@ -470,7 +456,6 @@ int attn_fwd_launch(void* plan_, const int* kinfo, int iso_p, void* o, float* ls
     attr_done = true;
   }
   p->tpi = attn_tiles_per_item(p->B, p->L);
-  p->nodead = attn_nodead_env();
   const int n_items = attn_num_items(p->B, p->L, p->tpi);
   const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
   launch_pdl(attn_fwd_kernel, dim3((unsigned)grid), kAttnThreads, FwdSmem::kBytes, st, *p, kinfo, iso_p,

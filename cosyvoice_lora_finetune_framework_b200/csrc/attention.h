@@ -28,7 +28,6 @@ struct AttnPlan {
   CUtensorMap tm_dqkv;  // backward output [B][L][1536], box {64, 64, 1} (TMA store)
   const void* o_ptr;    // destination tm_o / tm_dqkv was encoded for
   int B, L, bf16;
-  int nodead;           // profiling aid (CVFLOW_ATTN_NODEAD=1): do the exp work of all-padding warps too
   int tpi;              // 128-row tiles per item: 2 (one per warpgroup) or, when that leaves SMs idle, 1 (warpgroup 0 only)
   long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
 };
@@ -149,11 +148,6 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
 #endif
 
 int attn_num_sms();
-inline int attn_nodead_env() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("CVFLOW_ATTN_NODEAD"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
-}
 // items of a launch and tiles per item: two tiles per item unless that leaves SMs without work (small batches, inference)
 inline int attn_tiles_per_item(int B, int L) { return B * 8 * (((L + 127) / 128 + 1) / 2) >= attn_num_sms() ? 2 : 1; }
 inline int attn_num_items(int B, int L, int tpi) { return B * 8 * (((L + 127) / 128 + tpi - 1) / tpi); }

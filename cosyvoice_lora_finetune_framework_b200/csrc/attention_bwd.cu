@@ -216,7 +216,6 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
         delta_out[stat_idx] = my_delta;
       }
       const bool q_below = qi < iso_p;
-      const bool warp_dead = !plan.nodead && __all_sync(0xffffffffu, qi >= a.kmax);   // 32 padding rows: dS = 0 without any exp work
       const float lse_s = my_lse + 3.0f;   // d^-1/2 folded into the exponent: -log2(0.125) = 3
       const int nkb = (a.ext + kDqKB - 1) / kDqKB;
       const int* bits = bits_base + (long)a.b * nwords;
@@ -231,12 +230,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          if (c * 32 < keb && warp_dead) {
-            uint32_t z[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = 0u;
-            tmem_st_32x32b_x16(treg + (uint32_t)(c * 16), z);
-          } else if (c * 32 < keb) {   // the last chunk of a block may hold only 16 live columns; the rest is masked by vw
+          if (c * 32 < keb) {   // the last chunk of a block may hold only 16 live columns; the rest is masked by vw
             uint32_t sv[32], pv[32];
             tmem_ld_32x32b_x32(treg + (uint32_t)(c * 32), sv);
             tmem_ld_32x32b_x32(treg + 96u + (uint32_t)(c * 32), pv);
@@ -485,7 +479,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
       }
       const bool key_ok = kj < a.kmax && ((__ldg(bits_base + (long)a.b * nwords + (kj >> 5)) >> (kj & 31)) & 1);
       const bool k_below = kj < iso_p;
-      const bool warp_dead = !plan.nodead && __all_sync(0xffffffffu, !key_ok);   // 32 padded keys: P^T = dS^T = 0 without any exp work
       const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
       const float* lse_row = lse + ((long)a.b * 8 + a.h) * L;
       const float* del_row = delta + ((long)a.b * 8 + a.h) * L;
@@ -503,13 +496,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (c * 32 < qeb && warp_dead) {
-            uint32_t z[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = 0u;
-            tmem_st_32x32b_x16(treg + (uint32_t)(c * 16), z);
-            tmem_st_32x32b_x16(treg + 64u + (uint32_t)(c * 16), z);
-          } else if (c * 32 < qeb) {
+          if (c * 32 < qeb) {
             const int nlive = a.kmax - (q0 + 32 * c);   // live query columns of this chunk
             uint32_t col_ok = !key_ok || nlive <= 0 ? 0u : (nlive >= 32 ? 0xffffffffu : ((1u << nlive) - 1u));
             col_ok = attn_iso_word(col_ok, q0 + 32 * c, iso_p, k_below);
@@ -632,7 +619,6 @@ int attn_bwd_launch(void* plan_, const void* dout, const int* kinfo, int iso_p, 
     p->o_ptr = dqkv;
   }
   p->tpi = attn_tiles_per_item(p->B, p->L);
-  p->nodead = attn_nodead_env();
   const int n_items = attn_num_items(p->B, p->L, p->tpi);
   const int grid = n_items < attn_num_sms() ? n_items : attn_num_sms();
   launch_pdl(attn_bwd_dq_kernel, dim3((unsigned)grid), kAttnThreads, DqSmem::kBytes, st, *p, kinfo, iso_p,

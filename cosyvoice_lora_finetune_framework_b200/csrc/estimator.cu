@@ -219,7 +219,7 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, gn_partials_, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
                        tb, tb_stride, nullptr, a1, 0, B, L, cfg.bf16, stream_));
     launches_ += 2;
   }
@@ -239,7 +239,7 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, gn_partials_, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
                        nullptr, 0, r, h, 1, B, L, cfg.bf16, stream_));
     launches_ += 3;
   }
@@ -450,7 +450,7 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   float* te1 = (float*)alloc((long)B * 1024 * 4);
   float* te2 = (float*)alloc((long)B * 1024 * 4);
   tb_all_ = (float*)alloc((long)B * nres * 256 * 4);
-  gn_partials_ = (float*)alloc(gn_scratch_floats(B) * 4);
+  gn_partials_ = (float*)alloc(((long)B * 64 * 8 * 3 + (long)B * 16) * 4);
   void* xin0 = alloc((long)B * T * 320 * 2);
   void* cat1 = alloc((long)B * T * 512 * 2);
   void* cat0 = alloc((long)B * T2 * 512 * 2);
@@ -459,10 +459,6 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   kmax2_ = (int*)alloc(attn_kinfo_ints(B, T2) * 4);
   mask1_ = mask1; mask2_ = mask2; cat1_ = cat1; cat0_ = cat0;
   if (!dry_) {
-    if (cudaMemsetAsync(gn_partials_ + gn_counter_offset(B), 0, (size_t)B * 4, stream_) != cudaSuccess) {
-      set_error("cudaMemsetAsync(gn counters) failed");
-      return -1;
-    }
     CKL(launch_mask_down(io.mask, io.mask_nb, mask1, mask2, B, T, T2, stream_));
     CKL(launch_attn_kinfo(mask1, B, T, kmax1_, stream_));
     CKL(launch_attn_kinfo(mask2, B, T2, kmax2_, stream_));
@@ -551,7 +547,7 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   }
   if (!dry_) {
     if (!(skip_ & 4u)) CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
+    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, gn_partials_, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
                        mask1, nullptr, 0, nullptr, af, 0, B, T, cfg.bf16, stream_));
     launches_ += 3;
   }

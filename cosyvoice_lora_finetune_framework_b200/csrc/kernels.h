@@ -49,15 +49,12 @@ int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, cons
                          void* dh16, long M, int bf16, cudaStream_t st);
 // GroupNorm(8 groups of 32 channels, C=256) over the padded extent L of [B][L][256]
 int gn_num_splits(int B, int L);
-// floats of scratch for B samples; the last B words are arrival counters that must be zero before the first reduction
-long gn_scratch_floats(int B);
-long gn_counter_offset(int B);
 int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st);
 // mode 0: out16 = (mish(gn(c)) + tb[b][c]) * mask        (tb nullable)
 // mode 1: out32 = mish(gn(c)) * mask + add16             (resnet output, fp32 residual stream)
-int launch_gn_apply(const void* c16, const float* stats, const float* gamma, const float* beta, const float* mask,
-                    const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L, int bf16,
-                    cudaStream_t st);
+int launch_gn_apply(const void* c16, const float* partials, float* stats, const float* gamma, const float* beta,
+                    const float* mask, const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L,
+                    int bf16, cudaStream_t st);
 // dy: fp32 (dy_f32=1) or 16-bit; masked by rowmask. Produces dc16.
 int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stats, const float* gamma,
                   const float* beta, const float* mask, float* partials, void* dc16, int B, int L, int bf16,

@@ -117,10 +117,6 @@ int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, cons
 // ------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (b, split) shifted sums -> (n, mean, M2); Chan merge over splits.
 // ------------------------------------------------------------------------------------------
-// scratch layout (floats): [B * 64 splits * 8 groups * 3] partials | [B * 16] backward sums | [B] arrival counters (zeroed once
-// per forward by the caller; every reduction leaves them at zero again)
-long gn_counter_offset(int B) { return (long)B * 64 * 8 * 3 + (long)B * 16; }
-long gn_scratch_floats(int B) { return gn_counter_offset(B) + B; }
 int gn_num_splits(int B, int L) {
   int s = (2 * 148 + B - 1) / B;
   const int max_s = (L + 15) / 16;
@@ -130,31 +126,11 @@ int gn_num_splits(int B, int L) {
   return s;
 }
 
-// Chan merge of the split partials of one (sample, group); run by the last-arriving reduction block of the sample,
-// so no separate finalise launch sits between the reduction and the apply pass.
-__device__ __forceinline__ void gn_merge_partials(const float* __restrict__ partials, int b, int g, int nsplit, float& mean,
-                                                  float& rstd) {
-  float n = 0.f, mu = 0.f, m2 = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float* p = partials + (((long)b * nsplit + s) * 8 + g) * 3;   // written by other blocks of this launch: L2 reads
-    const float nb = __ldcg(p);
-    if (nb <= 0.f) continue;
-    const float delta = __ldcg(p + 1) - mu;
-    const float nn = n + nb;
-    mu += delta * nb / nn;
-    m2 += __ldcg(p + 2) + delta * delta * n * nb / nn;
-    n = nn;
-  }
-  mean = mu;
-  rstd = rsqrtf(m2 / n + 1e-5f);
-}
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restrict__ c, float* __restrict__ partials,
-                                                       float* __restrict__ stats, unsigned* __restrict__ counters, int L,
-                                                       int nsplit, int bf) {
+                                                       int L, int nsplit, int bf) {
   pdl_wait();
   pdl_launch();
   __shared__ float red[8][8][2];
-  __shared__ bool s_last;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int rows_per = (L + nsplit - 1) / nsplit;
   const int l0 = sp * rows_per, l1 = min(L, l0 + rows_per);
@@ -183,32 +159,34 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restric
     o[1] = n > 0.f ? Kg + a / n : 0.f;
     o[2] = n > 0.f ? q - a * a / n : 0.f;
   }
-  // single-pass finish: the block of this sample that arrives last merges the split partials (Chan) into (mean, rstd)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(counters + b, 1u);
-    s_last = prev == (unsigned)nsplit - 1u;
-    if (s_last) counters[b] = 0u;   // ready for the next GroupNorm call on this stream
+}
+// Chan merge of the split partials of one (sample, group): every consumer thread does it for its own group
+// (a few dozen cached loads) instead of a separate single-CTA launch between the reduction and the apply pass.
+__device__ __forceinline__ void gn_merge_partials(const float* __restrict__ partials, int b, int g, int nsplit, float& mean,
+                                                  float& rstd) {
+  float n = 0.f, mu = 0.f, m2 = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float* p = partials + (((long)b * nsplit + s) * 8 + g) * 3;
+    const float nb = p[0];
+    if (nb <= 0.f) continue;
+    const float delta = p[1] - mu;
+    const float nn = n + nb;
+    mu += delta * nb / nn;
+    m2 += p[2] + delta * delta * n * nb / nn;
+    n = nn;
   }
-  __syncthreads();
-  if (s_last && threadIdx.x < 8) {
-    __threadfence();
-    float mean, rstd;
-    gn_merge_partials(partials, b, threadIdx.x, nsplit, mean, rstd);
-    stats[(b * 8 + threadIdx.x) * 2] = mean;
-    stats[(b * 8 + threadIdx.x) * 2 + 1] = rstd;
-  }
+  mean = mu;
+  rstd = rsqrtf(m2 / n + 1e-5f);
 }
 int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st) {
   const int ns = gn_num_splits(B, L);
-  unsigned* counters = reinterpret_cast<unsigned*>(partials + gn_counter_offset(B));
-  launch_pdl(gn_stats_kernel, dim3(ns, B), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials, stats, counters, L, ns,
-             bf16);
+  (void)stats;   // written by the apply pass (first row of every sample)
+  launch_pdl(gn_stats_kernel, dim3(ns, B), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials, L, ns, bf16);
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ partials,
+                                                       int nsplit, float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mask, const float* __restrict__ tb, long tb_stride,
                                                        const uint16_t* __restrict__ add16, void* __restrict__ out, int mode,
@@ -221,7 +199,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
   const int lane = (int)(i & 31);
   const int b = (int)(row / L);
   const int c8 = lane * 8, grp = lane >> 2;
-  const float mean = stats[(b * 8 + grp) * 2], rstd = stats[(b * 8 + grp) * 2 + 1];
+  float mean, rstd;
+  gn_merge_partials(partials, b, grp, nsplit, mean, rstd);
+  if (row == (long)b * L && (lane & 3) == 0) {   // keep (mean, rstd) for the backward pass
+    stats[(b * 8 + grp) * 2] = mean;
+    stats[(b * 8 + grp) * 2 + 1] = rstd;
+  }
   const float m = mask[row];
   float x[8], g[8], be[8];
   load8_h16(c + row * 256 + c8, bf, x);
@@ -247,11 +230,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
     store8_f32(reinterpret_cast<float*>(out) + row * 256 + c8, x);
   }
 }
-int launch_gn_apply(const void* c16, const float* stats, const float* gamma, const float* beta, const float* mask,
-                    const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L, int bf16,
-                    cudaStream_t st) {
+int launch_gn_apply(const void* c16, const float* partials, float* stats, const float* gamma, const float* beta,
+                    const float* mask, const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L,
+                    int bf16, cudaStream_t st) {
   const long M = (long)B * L, n = M * 32;
-  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), stats, gamma,
+  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials,
+                                                               gn_num_splits(B, L), stats, gamma,
                                                                beta, mask, tb, tb_stride,
                                                                reinterpret_cast<const uint16_t*>(add16), out, mode, L,
                                                                M, bf16);
@@ -283,12 +267,10 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
                                                             const uint16_t* __restrict__ c, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ partials,
-                                                            float* __restrict__ sums, unsigned* __restrict__ counters,
-                                                            float inv_n, int L, int nsplit, int bf) {
+                                                            int L, int nsplit, int bf) {
   pdl_wait();
   pdl_launch();
   __shared__ float red[8][8][2];
-  __shared__ bool s_last;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int rows_per = (L + nsplit - 1) / nsplit;
   const int l0 = sp * rows_per, l1 = min(L, l0 + rows_per);
@@ -314,30 +296,13 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
     float* o = partials + (((long)b * nsplit + sp) * 8 + g) * 2;
     o[0] = a; o[1] = q;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(counters + b, 1u);
-    s_last = prev == (unsigned)nsplit - 1u;
-    if (s_last) counters[b] = 0u;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < 8) {   // last block of the sample: group means of dxhat and dxhat * xhat
-    __threadfence();
-    float a = 0.f, q = 0.f;
-    for (int s2 = 0; s2 < nsplit; ++s2) {
-      const float* pp = partials + (((long)b * nsplit + s2) * 8 + threadIdx.x) * 2;
-      a += __ldcg(pp); q += __ldcg(pp + 1);
-    }
-    sums[(b * 8 + threadIdx.x) * 2] = a * inv_n;
-    sums[(b * 8 + threadIdx.x) * 2 + 1] = q * inv_n;
-  }
 }
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32,
                                                            const uint16_t* __restrict__ c, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ mask, const float* __restrict__ sums,
-                                                           uint16_t* __restrict__ dc, int L, long M, int bf) {
+                                                           const float* __restrict__ mask, const float* __restrict__ partials,
+                                                           int nsplit, float inv_n, uint16_t* __restrict__ dc, int L, long M,
+                                                           int bf) {
   pdl_wait();
   pdl_launch();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,7 +312,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
   const int b = (int)(row / L);
   const int c8 = lane * 8, grp = lane >> 2;
   const float mean = stats[(b * 8 + grp) * 2], rstd = stats[(b * 8 + grp) * 2 + 1];
-  const float m1 = sums[(b * 8 + grp) * 2], m2 = sums[(b * 8 + grp) * 2 + 1];
+  float m1 = 0.f, m2 = 0.f;   // group means of dxhat and dxhat * xhat from the split partials
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const float* pp = partials + (((long)b * nsplit + sp) * 8 + grp) * 2;
+    m1 += pp[0]; m2 += pp[1];
+  }
+  m1 *= inv_n; m2 *= inv_n;
   float xh[8], dxh[8];
   gn_bwd_load(dy, dy_f32, c, gamma, beta, mean, rstd, mask[row], row * 256 + c8, c8, bf, xh, dxh);
 #pragma unroll
@@ -359,14 +329,11 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
                   cudaStream_t st) {
   const int ns = gn_num_splits(B, L);
   const uint16_t* c = reinterpret_cast<const uint16_t*>(c16);
-  float* sums = partials + (long)B * 64 * 8 * 3;
-  unsigned* counters = reinterpret_cast<unsigned*>(partials + gn_counter_offset(B));
-  launch_pdl(gn_bwd_reduce_kernel, dim3(ns, B), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, partials, sums, counters,
-             1.f / (32.f * (float)L), L, ns, bf16);
+  launch_pdl(gn_bwd_reduce_kernel, dim3(ns, B), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, partials, L, ns, bf16);
   const long M = (long)B * L, n = M * 32;
   launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask,
-                                                                   (const float*)sums, reinterpret_cast<uint16_t*>(dc16), L, M,
-                                                                   bf16);
+                                                                   (const float*)partials, ns, 1.f / (32.f * (float)L),
+                                                                   reinterpret_cast<uint16_t*>(dc16), L, M, bf16);
   LAUNCH_RET();
 }
 
