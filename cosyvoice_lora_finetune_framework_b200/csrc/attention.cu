@@ -357,9 +357,8 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
         tc_fence_after();
         // pass 1: row maximum over the valid keys of the block
         float m_loc = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nfull) m_loc = fwd_max_chunk<32>(treg + (uint32_t)(c * 32), vw[c], m_loc);
+#pragma unroll 1   // rolled on purpose: eight inlined copies of the chunk body blow the instruction footprint of the hot loop
+        for (int c = 0; c < nfull; ++c) m_loc = fwd_max_chunk<32>(treg + (uint32_t)(c * 32), vw[c], m_loc);
         if (tail) m_loc = fwd_max_chunk<16>(treg + (uint32_t)(nfull * 32), vt, m_loc);
         if (st_on) stamp(4 + 6 * n);
         const float m_new = fmaxf(m_run, m_loc * kAttnScaleLog2);
@@ -368,9 +367,9 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
         // pass 2: P = 2^(s c - m), row sum, 16-bit P written over S
         float rs0 = 0.f, rs1 = 0.f;
         if (w == 1 && n == 0) mbar_wait(skew_bar, 0);   // one-shot stagger: the two warpgroups' exp phases alternate
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nfull) fwd_softmax_chunk<32>(treg + (uint32_t)(c * 32), treg + (uint32_t)(c * 16), vw[c], m_use, rs0, rs1, bf);
+#pragma unroll 1
+        for (int c = 0; c < nfull; ++c)
+          fwd_softmax_chunk<32>(treg + (uint32_t)(c * 32), treg + (uint32_t)(c * 16), vw[c], m_use, rs0, rs1, bf);
         if (tail) fwd_softmax_chunk<16>(treg + (uint32_t)(nfull * 32), treg + (uint32_t)(nfull * 16), vt, m_use, rs0, rs1, bf);
         if (w == 0 && n == 0) mbar_arrive(skew_bar);
         const float rowsum = rs0 + rs1;
