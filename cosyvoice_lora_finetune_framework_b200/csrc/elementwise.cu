@@ -96,39 +96,57 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// warp per output feature n, 8 batch rows per pass staged in shared memory
+// y[b][n] = out_act(sum_k in_act(x[b][k]) W[n][k] + bias[n]) for small batches (time MLP: B <= 128, K <= 1024, N up to 4096).
+// One warp per output feature; the weight row is read exactly once: 256-column k-tiles of up to 32 activated input rows sit
+// in shared memory, every lane keeps 8 weights of the tile in registers and accumulates all 32 batch rows (32 accumulators),
+// and the cross-lane sums are taken once at the end. HBM-bound on the fp32 weights (22 MB for the three layers).
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            int B, int K, int N, int in_act, int out_act) {
-  extern __shared__ float xs[];  // [8][K]
+  __shared__ float4 xs[32][64];   // [row][256 columns of the k-tile]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
-  for (int b0 = 0; b0 < B; b0 += 8) {
-    const int nb = min(8, B - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb * K; i += 256) xs[i] = apply_act(x[(long)b0 * K + i], in_act);
-    __syncthreads();
-    if (n < N) {
-      float acc[8];
+  const int nc = n < N ? n : N - 1;   // clamp: every warp takes part in the barriers
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int nb = min(32, B - b0);
+    float acc[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int k = lane; k < K; k += 32) {
-        const float w = W[(long)n * K + k];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nb) acc[j] += w * xs[j * K + k];
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 256) {
+      const int kw = min(256, K - k0);   // multiple of 4 (K % 4 == 0 checked by the launcher)
+      __syncthreads();
+      for (int i = threadIdx.x; i < nb * 64; i += 256) {
+        const int r = i >> 6, c4 = (i & 63) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < kw) {
+          v = *reinterpret_cast<const float4*>(x + (long)(b0 + r) * K + k0 + c4);
+          v.x = apply_act(v.x, in_act); v.y = apply_act(v.y, in_act); v.z = apply_act(v.z, in_act); v.w = apply_act(v.w, in_act);
+        }
+        xs[r][i & 63] = v;
       }
+      __syncthreads();
+      float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+      if (lane * 4 < kw) w0 = __ldg(reinterpret_cast<const float4*>(W + (long)nc * K + k0 + lane * 4));
+      if (128 + lane * 4 < kw) w1 = __ldg(reinterpret_cast<const float4*>(W + (long)nc * K + k0 + 128 + lane * 4));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s = warp_sum(acc[j]);
-        if (lane == 0 && j < nb) y[(long)(b0 + j) * N + n] = apply_act(s + (bias ? bias[n] : 0.f), out_act);
+      for (int j = 0; j < 32; ++j) {
+        if (j < nb) {
+          const float4 a = xs[j][lane], b = xs[j][32 + lane];
+          acc[j] += w0.x * a.x + w0.y * a.y + w0.z * a.z + w0.w * a.w + w1.x * b.x + w1.y * b.y + w1.z * b.z + w1.w * b.w;
+        }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float sum = warp_sum(acc[j]);
+      if (lane == 0 && j < nb && n < N) y[(long)(b0 + j) * N + n] = apply_act(sum + (bias ? bias[n] : 0.f), out_act);
     }
   }
 }
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
                         int in_act, int out_act, cudaStream_t st) {
-  small_linear_kernel<<<(N + 7) / 8, 256, 8 * K * sizeof(float), st>>>(x, W, bias, y, B, K, N, in_act, out_act);
+  if (K % 4) return -(int)cudaErrorInvalidValue;
+  small_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(x, W, bias, y, B, K, N, in_act, out_act);
   LAUNCH_RET();
 }
 
