@@ -238,11 +238,12 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
             float ds[32];
             if (vw[c] == 0xffffffffu) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
+              for (int j = 0; j < 32; j += 2) {   // packed fp32x2: one FFMA2, one FADD2, one FMUL2 and two MUFU.EX2 per pair
                 float a0, a1;
                 ffma2(a0, a1, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]), kAttnScaleLog2, -lse_s);
-                ds[j] = exp2_fast(a0) * (__uint_as_float(pv[j]) - my_delta);
-                ds[j + 1] = exp2_fast(a1) * (__uint_as_float(pv[j + 1]) - my_delta);
+                const f32x2 e = f2_pack(exp2_fast(a0), exp2_fast(a1));
+                const f32x2 d = f2_add(f2_pack(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1])), f2_pack(-my_delta, -my_delta));
+                f2_unpack(f2_mul(e, d), ds[j], ds[j + 1]);
               }
             } else {
 #pragma unroll
@@ -489,7 +490,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
         {   // per-column statistics of the block: lse and delta of its queries (dead queries: P = 0)
           const int q = q0 + (wtid & 63);
           const bool live = q < a.kmax;
-          sb[wtid] = wtid < 64 ? (live ? lse_row[q] : INFINITY) : (live ? del_row[q] : 0.f);
+          sb[wtid] = wtid < 64 ? (live ? -lse_row[q] : -INFINITY) : (live ? -del_row[q] * kAttnScale : 0.f);   // -lse | -delta d^-1/2
         }
         wg_bar_sync(w);
         mbar_wait(s_full(w), n & 1u);
@@ -512,20 +513,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
               const float4 lv = l4[g], dv = d4[g];
               const float ls[4] = {lv.x, lv.y, lv.z, lv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w};
               float pp[4], dd[4];
-              if (col_ok == 0xffffffffu) {
+              if (col_ok == 0xffffffffu) {   // packed fp32x2: per pair two FFMA2, one FMUL2 and two MUFU.EX2
+                const f32x2 c2 = f2_pack(kAttnScaleLog2, kAttnScaleLog2), k2 = f2_pack(kAttnScale, kAttnScale);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < 4; e += 2) {
                   const int j = 4 * g + e;
-                  pp[e] = exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, -ls[e]));
-                  dd[e] = pp[e] * ((__uint_as_float(pv[j]) - de[e]) * kAttnScale);
+                  float a0, a1;
+                  f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), c2, f2_pack(ls[e], ls[e + 1])), a0, a1);
+                  const f32x2 pr = f2_pack(exp2_fast(a0), exp2_fast(a1));
+                  const f32x2 t = f2_fma(f2_pack(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1])), k2, f2_pack(de[e], de[e + 1]));
+                  f2_unpack(pr, pp[e], pp[e + 1]);
+                  f2_unpack(f2_mul(pr, t), dd[e], dd[e + 1]);
                 }
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int j = 4 * g + e;
                   const bool on = (col_ok >> j) & 1u;
-                  pp[e] = on ? exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, -ls[e])) : 0.f;
-                  dd[e] = on ? pp[e] * ((__uint_as_float(pv[j]) - de[e]) * kAttnScale) : 0.f;
+                  pp[e] = on ? exp2_fast(fmaf(__uint_as_float(sv[j]), kAttnScaleLog2, ls[e])) : 0.f;
+                  dd[e] = on ? pp[e] * fmaf(__uint_as_float(pv[j]), kAttnScale, de[e]) : 0.f;
                 }
               }
               pk[2 * g] = pack2_h16(pp[0], pp[1], bf); pk[2 * g + 1] = pack2_h16(pp[2], pp[3], bf);
