@@ -7,8 +7,8 @@
 //        dS = P o (dP - delta) d^-1/2, P = 2^(s c - lse) -> 16-bit, stored over S with tcgen05.st
 //        dQ += dS K   (A = dS from TMEM, B = K block as MN-major smem operand) -> TMEM [192,256),
 //        accumulated in TMEM over the key blocks
-//   dK/dV kernel: item = (b, h, pair of 128-key tiles); thread = key row; query blocks of <= 64
-//        S^T = K Q^T, dP^T = V dO^T                    -> TMEM [0,64) / [64,128)
+//   dK/dV kernel: item = (b, h, pair of 128-key tiles); thread = key row; query blocks of <= 32, score tiles
+//        double-buffered in TMEM (buffer b: S^T = K Q^T at [64b,+32), dP^T = V dO^T at [64b+32,+32))
 //        P^T, dS^T -> 16-bit over S^T / dP^T
 //        dV += P^T dO, dK += dS^T Q (A from TMEM, B = dO / Q blocks as MN-major operands) -> [128,192) / [192,256)
 // P is recomputed from the stored base-2 log-sum-exp of the forward pass. Both kernels are
