@@ -212,7 +212,6 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   if (threadIdx.x == 0) stamp(1);
   pdl_wait();
-  pdl_launch();
   if (threadIdx.x == 0) stamp(2);
 
   if (warp == 8) {
@@ -426,6 +425,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     if (wtid == 0) tma_store_wait_all();   // the staging tile must outlive the bulk stores
   }
   if (threadIdx.x == 0) { stamp(15); if (dbg) dbg[31] = clock64(); }
+  pdl_launch();   // dependents are released late: CTAs of the next kernel that spin at their grid-dependency wait next to the working ones cost more than their prologue overlap gains (same-box A/B)
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }

@@ -80,7 +80,6 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   pdl_wait();
-  pdl_launch();
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -298,6 +297,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
     }
     if (wtid == 0) tma_store_wait_all();
   }
+  pdl_launch();   // dependents are released late: CTAs of the next kernel that spin at their grid-dependency wait next to the working ones cost more than their prologue overlap gains (same-box A/B)
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -367,7 +367,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   pdl_wait();
-  pdl_launch();
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -625,6 +624,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
     }
     if (wtid == 0) tma_store_wait_all();
   }
+  pdl_launch();   // dependents are released late: CTAs of the next kernel that spin at their grid-dependency wait next to the working ones cost more than their prologue overlap gains (same-box A/B)
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }

@@ -104,7 +104,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   pdl_wait();     // everything above overlapped the previous kernel's tail; global memory from here on
-  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -345,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_arrive(tempty_bar(acc));
     }
   }
+  pdl_launch();   // dependents are released late: CTAs of the next kernel that spin at their grid-dependency wait next to the working ones cost more than their prologue overlap gains (same-box A/B)
   if (warp >= 2 && lane == 0) tma_store_wait_all();   // staging smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
