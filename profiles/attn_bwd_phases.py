@@ -1,4 +1,5 @@
-"""clock64 timeline of the dK/dV kernel's row thread 0 (needs the stamps compiled into attention_bwd.cu)."""
+"""clock64 timeline of the dK/dV kernel row thread 0. The stamps are not compiled into the shipped kernel: re-apply them
+(see the git history of attention_bwd.cu around the double-buffering change) before running this."""
 import ctypes as C
 import os
 import sys
