@@ -16,13 +16,16 @@ namespace cvflow {
 
 #define LAUNCH_RET() do { cudaError_t e_ = cudaGetLastError(); return e_ == cudaSuccess ? 0 : -(int)e_; } while (0)
 
-// grid (32 row-tiles of 16, 3 projections, nblocks); 256 threads = one k each
+// grid (8 row-tiles of 64 output features, 3 projections, nblocks); 256 threads = one input feature k each.
+// The K-major image is written row by row (512 B per warp store); the transposed image goes through a 16-bit shared-memory
+// tile so that every row of it receives 64 contiguous values (128 B) instead of 2-element fragments.
+static constexpr int kMergeRows = 64;
 __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __restrict__ blocks, int r, int bf) {
-  __shared__ float tile[16][257];
+  __shared__ __align__(16) uint16_t tile[kMergeRows][256 + 8];
   const LoraBlockPtrs& blk = blocks[blockIdx.z];
   const int p = blockIdx.y;
   const LoraLayerPtrs lp = blk.p[p];
-  const int n0 = blockIdx.x * 16;
+  const int n0 = blockIdx.x * kMergeRows;
   const int k = threadIdx.x;
   float a[16];
 #pragma unroll
@@ -36,12 +39,12 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __
     uint16_t* bblk = reinterpret_cast<uint16_t*>(blk.bblk16);
     if (blockIdx.x == 0)
       for (int j = 0; j < r; ++j) acat[(p * r + j) * 256 + k] = f32_to_h16(a[j], bf);
-    if (k < 16 * r) {
-      const int i = k / r, j = k - i * r;
+    for (int t = k; t < kMergeRows * r; t += 256) {
+      const int i = t / r, j = t - i * r;
       bblk[(long)(p * r + j) * 1536 + p * 512 + n0 + i] = f32_to_h16(lp.Bm[(n0 + i) * r + j], bf);
     }
   }
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kMergeRows; ++i) {
     const int n = n0 + i;
     float w = lp.W[n * 256 + k];
     if (lp.A) {
@@ -51,20 +54,23 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __
         if (j < r) acc += lp.Bm[n * r + j] * a[j];
       w += lp.scaling * acc;
     }
-    tile[i][k] = w;
-    weff[(long)(p * 512 + n) * 256 + k] = f32_to_h16(w, bf);
+    const uint16_t h = f32_to_h16(w, bf);
+    tile[i][k] = h;
+    weff[(long)(p * 512 + n) * 256 + k] = h;
   }
   __syncthreads();
-  // transposed image: row k, columns p*512 + n0 .. +16
+  // transposed image: row kk, columns p*512 + n0 .. +64 as 8 x 16-byte stores
   for (int idx = threadIdx.x; idx < 256 * 8; idx += 256) {
-    const int kk = idx >> 3, pr = idx & 7;
-    reinterpret_cast<uint32_t*>(weff_t + (long)kk * 1536 + p * 512 + n0)[pr] =
-        pack2_h16(tile[2 * pr][kk], tile[2 * pr + 1][kk], bf);
+    const int kk = idx >> 3, u = idx & 7;
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (uint32_t)tile[8 * u + 2 * e][kk] | ((uint32_t)tile[8 * u + 2 * e + 1][kk] << 16);
+    *reinterpret_cast<uint4*>(weff_t + (long)kk * 1536 + p * 512 + n0 + 8 * u) = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
 int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, cudaStream_t st) {
   if (r > 16) return -1;
-  lora_merge_kernel<<<dim3(32, 3, nblocks), 256, 0, st>>>(blocks_dev, r, bf16);
+  lora_merge_kernel<<<dim3(512 / kMergeRows, 3, nblocks), 256, 0, st>>>(blocks_dev, r, bf16);
   LAUNCH_RET();
 }
 
