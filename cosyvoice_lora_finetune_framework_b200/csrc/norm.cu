@@ -38,12 +38,12 @@ __device__ __forceinline__ void store8_h16(uint16_t* p, int bf, const float (&v)
 // ------------------------------------------------------------------------------------------
 // LayerNorm
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, uint16_t* __restrict__ out,
                                                             long M, int bf) {
   pdl_wait();
   pdl_launch();
-  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   float x[8], g[8], b[8];
@@ -64,18 +64,18 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, void* out, long M, int bf16,
                          cudaStream_t st) {
-  launch_pdl(layernorm_fwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, h, gamma, beta, reinterpret_cast<uint16_t*>(out), M,
+  launch_pdl(layernorm_fwd_kernel, (unsigned)((M + 3) / 4), 128, 0, st, h, gamma, beta, reinterpret_cast<uint16_t*>(out), M,
                                                                bf16);
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __restrict__ dxn, long ld_dxn, const float* __restrict__ h_in,
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const uint16_t* __restrict__ dxn, long ld_dxn, const float* __restrict__ h_in,
                                                             const float* __restrict__ gamma, const float* __restrict__ dres,
                                                             float* __restrict__ dh, uint16_t* __restrict__ dh16, long M,
                                                             int bf) {
   pdl_wait();
   pdl_launch();
-  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   float x[8], g[8], d[8];
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
 }
 int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, const float* gamma, const float* dres, float* dh,
                          void* dh16, long M, int bf16, cudaStream_t st) {
-  launch_pdl(layernorm_bwd_kernel, (unsigned)((M + 7) / 8), 256, 0, st, reinterpret_cast<const uint16_t*>(dxn16), ld_dxn, h_in, gamma,
+  launch_pdl(layernorm_bwd_kernel, (unsigned)((M + 3) / 4), 128, 0, st, reinterpret_cast<const uint16_t*>(dxn16), ld_dxn, h_in, gamma,
                                                                dres, dh, reinterpret_cast<uint16_t*>(dh16), M, bf16);
   LAUNCH_RET();
 }
