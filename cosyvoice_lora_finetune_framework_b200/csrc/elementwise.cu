@@ -153,7 +153,7 @@ int launch_small_linear(const float* x, const float* W, const float* bias, float
 // ------------------------------------------------------------------------------------------
 // residual stream (fp32 [M][256]) -> masked 16-bit into a strided destination
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stage_out_kernel(const float* __restrict__ h, const float* __restrict__ rowmask,
+__global__ void __launch_bounds__(128) stage_out_kernel(const float* __restrict__ h, const float* __restrict__ rowmask,
                                                         uint16_t* __restrict__ dst, long ldc, int col_off, long M,
                                                         int bf) {
   pdl_wait();
@@ -175,12 +175,12 @@ __global__ void __launch_bounds__(256) stage_out_kernel(const float* __restrict_
 int launch_stage_out(const float* h, const float* rowmask, void* dst, long ldc, int col_off, long M, int bf16,
                      cudaStream_t st) {
   const long n = M * 32;
-  launch_pdl(stage_out_kernel, (unsigned)((n + 255) / 256), 256, 0, st, h, rowmask, reinterpret_cast<uint16_t*>(dst), ldc,
+  launch_pdl(stage_out_kernel, (unsigned)((n + 127) / 128), 128, 0, st, h, rowmask, reinterpret_cast<uint16_t*>(dst), ldc,
                                                                 col_off, M, bf16);
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) grad_route_kernel(const uint16_t* __restrict__ src, long ld_src, int col_off,
+__global__ void __launch_bounds__(128) grad_route_kernel(const uint16_t* __restrict__ src, long ld_src, int col_off,
                                                          const float* __restrict__ rowmask, float* __restrict__ dst,
                                                          int accumulate, uint16_t* __restrict__ dst16, long M, int bf) {
   pdl_wait();
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) grad_route_kernel(const uint16_t* __restr
 int launch_grad_route(const void* src, long ld_src, int col_off, const float* rowmask, float* dst, int accumulate,
                       void* dst16, long M, int bf16, cudaStream_t st) {
   const long n = M * 32;
-  launch_pdl(grad_route_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(src), ld_src,
+  launch_pdl(grad_route_kernel, (unsigned)((n + 127) / 128), 128, 0, st, reinterpret_cast<const uint16_t*>(src), ld_src,
                                                                  col_off, rowmask, dst, accumulate,
                                                                  reinterpret_cast<uint16_t*>(dst16), M, bf16);
   LAUNCH_RET();

@@ -185,7 +185,7 @@ int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L
   LAUNCH_RET();
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ partials,
+__global__ void __launch_bounds__(128) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ partials,
                                                        int nsplit, float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mask, const float* __restrict__ tb, long tb_stride,
@@ -234,7 +234,7 @@ int launch_gn_apply(const void* c16, const float* partials, float* stats, const 
                     const float* mask, const float* tb, long tb_stride, const void* add16, void* out, int mode, int B, int L,
                     int bf16, cudaStream_t st) {
   const long M = (long)B * L, n = M * 32;
-  launch_pdl(gn_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, reinterpret_cast<const uint16_t*>(c16), partials,
+  launch_pdl(gn_apply_kernel, (unsigned)((n + 127) / 128), 128, 0, st, reinterpret_cast<const uint16_t*>(c16), partials,
                                                                gn_num_splits(B, L), stats, gamma,
                                                                beta, mask, tb, tb_stride,
                                                                reinterpret_cast<const uint16_t*>(add16), out, mode, L,
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
     o[0] = a; o[1] = q;
   }
 }
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32,
+__global__ void __launch_bounds__(128) gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32,
                                                            const uint16_t* __restrict__ c, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mask, const float* __restrict__ partials,
@@ -331,7 +331,7 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
   const uint16_t* c = reinterpret_cast<const uint16_t*>(c16);
   launch_pdl(gn_bwd_reduce_kernel, dim3(ns, B), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask, partials, L, ns, bf16);
   const long M = (long)B * L, n = M * 32;
-  launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dy, dy_f32, c, stats, gamma, beta, mask,
+  launch_pdl(gn_bwd_apply_kernel, (unsigned)((n + 127) / 128), 128, 0, st, dy, dy_f32, c, stats, gamma, beta, mask,
                                                                    (const float*)partials, ns, 1.f / (32.f * (float)L),
                                                                    reinterpret_cast<uint16_t*>(dc16), L, M, bf16);
   LAUNCH_RET();
