@@ -233,7 +233,7 @@ def run_cvflow(a):
     use_graph = not a.no_graph
 
     def step(b):
-        if use_graph:   # the whole optimiser step (~1,600 launches) replayed as one CUDA graph
+        if use_graph:   # the whole optimiser step (~1,340 launches) replayed as one CUDA graph
             return trainer.train_step_graphed(b["x1"], b["mask"], b["mu"], b["spks"], b["cond"])
         return trainer.train_step(b["x1"], b["mask"], b["mu"], b["spks"], b["cond"])
 

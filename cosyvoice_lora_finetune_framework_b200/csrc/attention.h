@@ -8,7 +8,7 @@
 // warpgroup is in its exp-heavy phase the tensor core runs the other one's MMAs.
 //
 // Padding is skipped, not computed: kmax[b] = 1 + (last index with mask != 0) bounds both the rows
-// and the columns that are touched. Rows >= kmax[b] are written as zeros (the reference computes
+// and the columns that are touched (the `kinfo` array: per-sample extents followed by key-validity bit words). Rows >= kmax[b] are written as zeros (the reference computes
 // garbage there and masks it downstream, modules.py:1046-1049,1104-1106), columns >= kmax[b] carry
 // the -1e10 bias in the reference (utils.py:103-109), i.e. probability exactly 0 in fp32.
 #pragma once
@@ -85,12 +85,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 __device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, 128;" ::"r"(w + 1) : "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// validity bits of the 32 columns [c0, c0+32) for this warp: mask != 0 and below the valid extent
-__device__ __forceinline__ uint32_t attn_valid_word(const float* __restrict__ maskrow, int c0, int lane, int kmax) {
-  const int c = c0 + lane;
-  const bool ok = c < kmax && maskrow[c] != 0.f;
-  return __ballot_sync(0xffffffffu, ok);
-}
 // prompt-isolation (modules.py:844-879): a row on one side of the boundary p only sees columns on the same side
 __device__ __forceinline__ uint32_t attn_iso_word(uint32_t vw, int c0, int iso_p, bool row_below) {
   if (iso_p <= 0) return vw;

@@ -106,7 +106,7 @@ class FlowLoRATrainer:
     # -- whole-step CUDA graph ------------------------------------------------------------------------
     def train_step_graphed(self, x1, mask, mu, spks, cond):
         """One full optimiser step (CFM prep, estimator fwd, loss, bwd, allreduce, clip+AdamW, W_eff
-        refresh: ~1,600 kernel launches) replayed as ONE CUDA graph. Shapes must stay fixed; the
+        refresh: ~1,340 kernel launches) replayed as ONE CUDA graph. Shapes must stay fixed; the
         inputs are copied into static buffers, the RNG advances per replay (graph-safe Philox), and
         the per-step optimiser scalars come from device memory. Returns the (static) loss tensor."""
         if self.accumulate != 1:
