@@ -23,6 +23,10 @@ class EstimatorIO(C.Structure):
                 ("iso_len", C.c_int32), ("training", C.c_int32)]
 
 
+class InputGrads(C.Structure):
+    _fields_ = [("dx", C.c_void_p), ("dmu", C.c_void_p), ("dspks", C.c_void_p), ("dcond", C.c_void_p)]
+
+
 class Config(C.Structure):
     _fields_ = [("n_blocks", C.c_int32), ("n_mid", C.c_int32), ("dtype", C.c_int32), ("gelu_erf", C.c_int32),
                 ("lora_r", C.c_int32), ("lora_scaling", C.c_float)]
@@ -46,6 +50,7 @@ def _lib():
         L.cvflow_lora_refresh.argtypes = [vp, vp]
         L.cvflow_estimator_forward.argtypes = [vp, C.POINTER(EstimatorIO), vp]
         L.cvflow_estimator_backward.argtypes = [vp, vp, f, vp, vp]
+        L.cvflow_estimator_backward_inputs.argtypes = [vp, vp, f, vp, C.POINTER(InputGrads), vp]
         L.cvflow_launch_count.argtypes = [vp]
         L.cvflow_launch_count.restype = i64
         L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
@@ -400,11 +405,22 @@ class NativeEstimator:
         N.check(self.L.cvflow_estimator_forward(self.handle, C.byref(io), _stream()), "cvflow_estimator_forward")
         return out
 
-    def backward(self, dpred16, grad_scale=1.0, grad_scale_dev=None):
+    def backward(self, dpred16, grad_scale=1.0, grad_scale_dev=None, input_grads=None):
+        """LoRA gradients into the flat bucket; `input_grads` = {'dx'|'dmu'|'dspks'|'dcond': fp32 tensor} additionally
+        receives dL/d(estimator inputs) (for training the modules that produce mu / spks upstream)."""
         self.attach_grads()
+        gs = C.c_void_p(grad_scale_dev.data_ptr()) if grad_scale_dev is not None else None
+        if input_grads:
+            ig = InputGrads()
+            for k, t in input_grads.items():
+                assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, k
+                setattr(ig, k, t.data_ptr())
+            N.check(self.L.cvflow_estimator_backward_inputs(
+                self.handle, C.c_void_p(dpred16.data_ptr()), float(grad_scale), gs, C.byref(ig), _stream()),
+                "cvflow_estimator_backward_inputs")
+            return
         N.check(self.L.cvflow_estimator_backward(
-            self.handle, C.c_void_p(dpred16.data_ptr()), float(grad_scale),
-            C.c_void_p(grad_scale_dev.data_ptr()) if grad_scale_dev is not None else None, _stream()),
+            self.handle, C.c_void_p(dpred16.data_ptr()), float(grad_scale), gs, _stream()),
             "cvflow_estimator_backward")
 
     def dpred_buffer(self, B, T):
@@ -421,6 +437,13 @@ class NativeEstimator:
 
 def _prep(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _prep_g(t, device):
+    """_prep that stays on the autograd graph when the tensor requires grad (inputs trained upstream)."""
+    if t.requires_grad and torch.is_grad_enabled():
+        return t.to(device=device, dtype=torch.float32).contiguous()
+    return _prep(t, device)
 
 
 def native_of(module, dtype=None):
@@ -440,6 +463,8 @@ class _EstimatorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ne, x, mask, mu, t, spks, cond, iso_len, *lora_params):
         ctx.ne = ne
+        ctx.shapes = (x.shape, mu.shape, spks.shape if spks is not None else None,
+                      cond.shape if cond is not None else None)
         out = ne.forward(x, mask, mu, t, spks, cond, iso_len=iso_len, training=True)
         return out
 
@@ -449,20 +474,29 @@ class _EstimatorFn(torch.autograd.Function):
         B, _, T = gout.shape
         g = torch.zeros(B, T, 128, device=gout.device, dtype=ne.dtype)
         g[:, :, :80] = (gout.float() * ne.loss_scale).transpose(1, 2).to(ne.dtype)
-        ne.backward(g, grad_scale=1.0 / ne.loss_scale)
-        return (None,) * (8 + len(ne.lora_views))
+        want = {}
+        for key, pos, shape in (("dx", 1, ctx.shapes[0]), ("dmu", 3, ctx.shapes[1]), ("dspks", 5, ctx.shapes[2]),
+                                ("dcond", 6, ctx.shapes[3])):
+            if ctx.needs_input_grad[pos] and shape is not None:
+                want[key] = (pos, torch.empty(shape, device=gout.device, dtype=torch.float32))
+        ne.backward(g, grad_scale=1.0 / ne.loss_scale, input_grads={k: v for k, (_, v) in want.items()})
+        grads = [None] * (8 + len(ne.lora_views))
+        for _, (pos, v) in want.items():
+            grads[pos] = v
+        return tuple(grads)
 
 
 def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
     ne = native_of(module)
     ne.sync_lora()
     dev = ne.device
-    x_, mu_, t_ = _prep(x, dev), _prep(mu, dev), _prep(t, dev)
+    x_, mu_, t_ = _prep_g(x, dev), _prep_g(mu, dev), _prep(t, dev)
     mask_ = _prep(mask, dev).reshape(mask.shape[0], -1)
-    spks_ = _prep(spks, dev) if spks is not None else None
-    cond_ = _prep(cond, dev) if cond is not None else None
+    spks_ = _prep_g(spks, dev) if spks is not None else None
+    cond_ = _prep_g(cond, dev) if cond is not None else None
     iso = int(module.prompt_isolation_len) if getattr(module, "prompt_isolation_enabled", False) else 0
-    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in ne.lora_views)
+    needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p, _, _ in ne.lora_views) or
+                                              any(v is not None and v.requires_grad for v in (x_, mu_, spks_, cond_)))
     if needs_grad:
         out = _EstimatorFn.apply(ne, x_, mask_, mu_, t_, spks_, cond_, iso, *[p for p, _, _ in ne.lora_views])
     else:

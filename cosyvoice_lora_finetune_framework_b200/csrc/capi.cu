@@ -122,6 +122,13 @@ extern "C" CVFLOW_API int cvflow_estimator_backward(cvflow_estimator* h, const v
   if (!h || !dpred16) { set_error("cvflow_estimator_backward: null argument"); return CVFLOW_ERR_ARG; }
   return h->e->backward(dpred16, grad_scale, grad_scale_dev, (cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void* dpred16, float grad_scale,
+                                                           const float* grad_scale_dev, const cvflow_input_grads* ig,
+                                                           void* stream) {
+  if (!h || !dpred16 || !ig) { set_error("cvflow_estimator_backward_inputs: null argument"); return CVFLOW_ERR_ARG; }
+  InputGrads g{ig->dx, ig->dmu, ig->dspks, ig->dcond};
+  return h->e->backward(dpred16, grad_scale, grad_scale_dev, (cudaStream_t)stream, &g) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h) { return h ? h->e->launches() : 0; }
 
 #define RET_LAUNCH(call, what)                                                                       \

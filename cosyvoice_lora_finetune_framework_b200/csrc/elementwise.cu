@@ -52,6 +52,60 @@ int launch_pack_inputs(const float* x, int x_nb, const float* mu, int mu_nb, con
   LAUNCH_RET();
 }
 
+// ------------------------------------------------------------------------------------------
+// unpack (backward of pack): 16-bit token-major dL/d(packed input) [B][T][320] -> fp32 channel-major
+// dL/dx, dL/dmu, dL/dcond [B][80][T] and per-tile partial sums of dL/dspks (summed in fixed order by
+// spk_grad_reduce_kernel: deterministic, no atomics). The row mask is already applied by the
+// producing dgrad GEMM; mu / spks / cond carry the CFG keep factor of the forward pack.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_input_grads_kernel(
+    const uint32_t* __restrict__ g, const float* __restrict__ keep, float scale, const float* __restrict__ gs_dev,
+    float* __restrict__ dx, float* __restrict__ dmu, float* __restrict__ dcond, float* __restrict__ spk_part,
+    int T, int bf) {
+  __shared__ float tile[320][33];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const float s = scale * (gs_dev ? gs_dev[0] : 1.f);
+  const float sk = s * (keep ? keep[b] : 1.f);
+  for (int idx = threadIdx.x; idx < 32 * 160; idx += 256) {
+    const int r = idx / 160, cp = idx - r * 160;
+    float a = 0.f, c = 0.f;
+    if (t0 + r < T) unpack2_h16(g[((long)b * T + t0 + r) * 160 + cp], bf, a, c);
+    tile[2 * cp][r] = a;
+    tile[2 * cp + 1][r] = c;
+  }
+  __syncthreads();
+  const int t = t0 + tx;
+  const bool ok = t < T;
+  for (int c = wy; c < 80; c += 8) {
+    const long o = ((long)b * 80 + c) * T + t;
+    if (dx && ok) dx[o] = tile[c][tx] * s;
+    if (dmu && ok) dmu[o] = tile[80 + c][tx] * sk;
+    if (dcond && ok) dcond[o] = tile[240 + c][tx] * sk;
+    if (spk_part) {
+      const float v = warp_sum(tile[160 + c][tx]);   // rows beyond T hold zeros
+      if (tx == 0) spk_part[((long)b * gridDim.x + blockIdx.x) * 80 + c] = v * sk;
+    }
+  }
+}
+__global__ void spk_grad_reduce_kernel(const float* __restrict__ spk_part, int ntiles, float* __restrict__ dspks) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= 80) return;
+  float acc = 0.f;
+  for (int i = 0; i < ntiles; ++i) acc += spk_part[((long)b * ntiles + i) * 80 + c];
+  dspks[(long)b * 80 + c] = acc;
+}
+int launch_unpack_input_grads(const void* g16, const float* keep, float scale, const float* gs_dev, float* dx,
+                              float* dmu, float* dspks, float* dcond, float* spk_part, int B, int T, int bf16,
+                              cudaStream_t st) {
+  dim3 grid((T + 31) / 32, B);
+  unpack_input_grads_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(g16), keep, scale, gs_dev, dx, dmu,
+                                                  dcond, dspks ? spk_part : nullptr, T, bf16);
+  if (dspks) spk_grad_reduce_kernel<<<B, 96, 0, st>>>(spk_part, (int)grid.x, dspks);
+  LAUNCH_RET();
+}
+
 __global__ void mask_down_kernel(const float* __restrict__ mask, int mask_nb, float* __restrict__ mask1,
                                  float* __restrict__ mask2, int B, int T, int T2) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -416,7 +416,7 @@ long Estimator::workspace_bytes(int B, int T, int training) {
   if (training) {
     const EstimatorIO saved = last_io_;
     last_io_ = io;
-    backward_impl(nullptr, 1.f);
+    backward_impl(nullptr, 1.f, nullptr);
     last_io_ = saved;
   }
   stages_.clear();
@@ -568,13 +568,23 @@ int Estimator::forward_impl(const EstimatorIO& io) {
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-int Estimator::backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st) {
+int Estimator::backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st,
+                        const InputGrads* in_grads) {
   grad_scale_dev_ = grad_scale_dev;
   if (!have_fwd_) { set_error("estimator: backward needs a preceding forward with training=1"); return -1; }
+  if (in_grads && !(in_grads->dx || in_grads->dmu || in_grads->dspks || in_grads->dcond)) in_grads = nullptr;
+  if (in_grads) {
+    const EstimatorIO& io = last_io_;
+    if ((in_grads->dx && io.x_nb != io.B) || (in_grads->dmu && io.mu_nb != io.B) ||
+        (in_grads->dspks && (!io.spks || io.spks_nb != io.B)) || (in_grads->dcond && (!io.cond || io.cond_nb != io.B))) {
+      set_error("estimator: input gradients need every requested input to be present with its own row per batch item");
+      return -1;
+    }
+  }
   stream_ = st;
   dry_ = false; missing_ = false; oom_ = false;
   ws_off_ = fwd_ws_end_;
-  int r = backward_impl(dpred16, grad_scale);
+  int r = backward_impl(dpred16, grad_scale, in_grads);
   if (oom_) { set_error("estimator: workspace too small for backward"); return -1; }
   have_fwd_ = false;
   return r;
@@ -710,7 +720,7 @@ int Estimator::stage_bwd(const StageRec& s, float* dh32, void* dh16, void* dxin1
   return 0;
 }
 
-int Estimator::backward_impl(const void* dpred16, float grad_scale) {
+int Estimator::backward_impl(const void* dpred16, float grad_scale, const InputGrads* in_grads) {
   const int B = last_io_.B, T = last_io_.T, T2 = (T + 1) / 2;
   const long MT = (long)B * T, MH = (long)B * T2;
   BwdTemps tmp;
@@ -732,6 +742,8 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   void* dcat1 = alloc(MT * 512 * 2);
   void* dcat0 = alloc(MH * 512 * 2);
   void* dx16 = alloc(MH * 256 * 2);
+  void* dxin0 = alloc(MT * 320 * 2);                                        // dL/d(packed input), only with in_grads
+  float* spk_part = (float*)alloc((long)B * ((T + 31) / 32) * 80 * 4);
   if (dry_) {
     // mirror the memoised-launch counters only; nothing to launch
     return 0;
@@ -822,8 +834,14 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale) {
   CKL(launch_grad_route(g16a, 256, 0, nullptr, dh32, 0, nullptr, MT, cfg.bf16, stream_));
   CKL(launch_grad_route(dcat1, 512, 256, mask1, dh32, 1, dh16, MT, cfg.bf16, stream_));
   launches_ += 2;
-  // ---- down 0: transformer blocks only (nothing trainable upstream of them) ----
-  CK(stage_bwd(stages_[0], dh32, dh16, nullptr, true, grad_scale, tmp));
+  // ---- down 0: transformer blocks only (nothing trainable upstream of them inside the estimator) unless the
+  // caller asked for dL/d(inputs): then also the first block's input gradient, the first resnet and the unpack ----
+  CK(stage_bwd(stages_[0], dh32, dh16, in_grads ? dxin0 : nullptr, in_grads == nullptr, grad_scale, tmp));
+  if (in_grads) {
+    CKL(launch_unpack_input_grads(dxin0, last_io_.keep, grad_scale, grad_scale_dev_, in_grads->dx, in_grads->dmu,
+                                  in_grads->dspks, in_grads->dcond, spk_part, B, T, cfg.bf16, stream_));
+    launches_ += in_grads->dspks ? 2 : 1;
+  }
   if (cfg.lora_r > 0) {   // join the side stream, then one final reduction of every block's split partials into the grads
     for (int par = 0; par < 2; ++par)
       if (wgrad_side_ && ev_done_valid_[par]) { cudaStreamWaitEvent(stream_, ev_done_[par], 0); ev_done_valid_[par] = false; }

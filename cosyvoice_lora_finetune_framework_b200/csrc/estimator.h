@@ -34,6 +34,9 @@ struct EstimatorIO {
   int B, T, iso_len, training;
 };
 
+// optional outputs of the backward: dL/d(estimator inputs), fp32, same layouts as the inputs (each nullable)
+struct InputGrads { float* dx; float* dmu; float* dspks; float* dcond; };
+
 struct BoundTensor { void* ptr; long numel; int dtype; };  // dtype: 0 f16, 1 bf16, 2 f32
 
 struct ResnetRec { std::string prefix; int cin, B, L; void *c1, *c2; float *st1, *st2; const float* mask; };
@@ -70,7 +73,8 @@ class Estimator {
   long workspace_bytes(int B, int T, int training);
   int lora_refresh(cudaStream_t st, bool merge = true);
   int forward(const EstimatorIO& io, cudaStream_t st);
-  int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
+  int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st,
+               const InputGrads* in_grads = nullptr);
   long launches() const { return launches_; }
   void set_profile(int on);
   // class ids: 0 gemm, 1 attn_fwd, 2 attn_bwd, 3 norm/elementwise, 4 lora_wgrad
@@ -89,7 +93,7 @@ class Estimator {
   int iso_at(int L, int T, int iso_len) const;
   void for_each_tb(const std::function<void(const std::string&)>& f);
   int forward_impl(const EstimatorIO& io);
-  int backward_impl(const void* dpred16, float grad_scale);
+  int backward_impl(const void* dpred16, float grad_scale, const InputGrads* in_grads);
   int resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L, const float* mask,
                  const float* tb, long tb_stride, float** h_out, ResnetRec* rec);
   int tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, const int* kmax, int iso_p,

@@ -15,6 +15,12 @@ namespace cvflow {
 int launch_pack_inputs(const float* x, int x_nb, const float* mu, int mu_nb, const float* spks, int spks_nb,
                        const float* cond, int cond_nb, const float* mask, int mask_nb, const float* keep,
                        void* out, int B, int T, int bf16, cudaStream_t st);
+// Backward of the pack: 16-bit dL/d(packed) [B][T][320] (already row-masked) -> fp32 channel-major dL/dx, dL/dmu,
+// dL/dcond [B][80][T] and dL/dspks [B][80] (sum over frames), each nullable; mu / spks / cond are multiplied by keep[b];
+// everything by scale * (*gs_dev). spk_part: scratch of B * ceil(T/32) * 80 floats (autograd of modules.py:1008-1014).
+int launch_unpack_input_grads(const void* g16, const float* keep, float scale, const float* gs_dev, float* dx,
+                              float* dmu, float* dspks, float* dcond, float* spk_part, int B, int T, int bf16,
+                              cudaStream_t st);
 // mask2[b][j] = mask[b % mask_nb][2j]   (modules.py:1049, masks.append(mask[:, :, ::2]))
 int launch_mask_down(const float* mask, int mask_nb, float* mask1, float* mask2, int B, int T, int T2,
                      cudaStream_t st);

@@ -46,7 +46,9 @@ class _CFMLossFn(torch.autograd.Function):
                                   ne.loss_scale, N.dtype_code(ne.dtype), None, st), "cvflow_cfm_loss")
         ctx.ne = ne
         ctx.dpred = dpred
+        ctx.keep = keep          # the backward's unpack kernel reads the CFG keep factors again
         ctx.n_extra = len(lora_params)
+        ctx.in_shapes = (mu.shape, spks.shape if spks is not None else None, cond.shape if cond is not None else None)
         ctx.mark_non_differentiable(y)
         ne.last_pred = pred
         return scal[2].clone(), y
@@ -55,8 +57,17 @@ class _CFMLossFn(torch.autograd.Function):
     def backward(ctx, gloss, gy):
         ne = ctx.ne
         g = gloss.detach().reshape(1).to(torch.float32).contiguous()
-        ne.backward(ctx.dpred, grad_scale=1.0 / ne.loss_scale, grad_scale_dev=g)
-        return (None,) * (12 + ctx.n_extra)
+        # dL/dmu, dL/dspks, dL/dcond only when the caller trains something upstream of the estimator
+        want = {}
+        for key, pos, shape in (("dmu", 3, ctx.in_shapes[0]), ("dspks", 4, ctx.in_shapes[1]), ("dcond", 5, ctx.in_shapes[2])):
+            if ctx.needs_input_grad[pos] and shape is not None:
+                want[key] = (pos, torch.empty(shape, device=g.device, dtype=torch.float32))
+        ne.backward(ctx.dpred, grad_scale=1.0 / ne.loss_scale, grad_scale_dev=g,
+                    input_grads={k: v for k, (_, v) in want.items()})
+        grads = [None] * (12 + ctx.n_extra)
+        for _, (pos, v) in want.items():
+            grads[pos] = v
+        return tuple(grads)
 
 
 class _CFMLossShardedFn(torch.autograd.Function):
@@ -262,12 +273,10 @@ class ConditionalCFM(nn.Module):
     def _loss_with_noise(self, x1, mask, mu, spks, cond, prompt_lens, t_step, z, keep):
         """compute_loss with the random draws supplied (t already warped): used by the parity tests."""
         est = self.estimator
-        for name, v in (("mu", mu), ("spks", spks), ("cond", cond), ("x1", x1)):
-            if torch.is_tensor(v) and v.requires_grad:
-                raise NotImplementedError(
-                    "compute_loss: %s requires grad, but the CUDA flow path does not produce dL/d%s yet (only the "
-                    "estimator's attn1 q/k/v LoRA gradients; SURVEY section 8f-3). Detach the prepared tensors or "
-                    "restrict LoRA to target_modules=['to_q','to_k','to_v']." % (name, name))
+        if torch.is_tensor(x1) and x1.requires_grad:
+            raise NotImplementedError("compute_loss: x1 (the target mel) requires grad; the CUDA flow path produces "
+                                      "dL/dmu, dL/dspks and dL/dcond, not dL/dx1")
+        upstream = torch.is_grad_enabled() and any(torch.is_tensor(v) and v.requires_grad for v in (mu, spks, cond))
         ne = E.native_of(est)
         ne.check_trainable(est)
         dev = ne.device
@@ -288,19 +297,22 @@ class ConditionalCFM(nn.Module):
                         w[i, :, p:min(p + frames, w.shape[2])] = weight
         b, _, T = x1.shape
         f = lambda v: E._prep(v, dev)
-        spks_ = f(spks) if spks is not None else None
-        cond_ = f(cond) if cond is not None else None
+        fg = lambda v: E._prep_g(v, dev)
+        spks_ = fg(spks) if spks is not None else None
+        cond_ = fg(cond) if cond is not None else None
         keep_ = keep.to(dev).float().contiguous() if keep is not None else None
         ne.sync_lora()
         S = min(int(self.num_streams), b)
         if S > 1:
+            if upstream:
+                raise NotImplementedError("num_streams > 1 does not produce dL/d(mu, spks, cond); use num_streams = 1")
             while len(self._streams) < S - 1:
                 self._streams.append(torch.cuda.Stream(device=dev))
             loss, y = _CFMLossShardedFn.apply(ne.shard_handles(S), self._streams[: S - 1], f(x1), f(mask).reshape(b, T),
                                               f(mu), spks_, cond_, f(w).reshape(b, T), f(t_step).reshape(b), f(z),
                                               keep_, iso, float(self.sigma_min), *[p for p, _, _ in ne.lora_views])
         else:
-            loss, y = _CFMLossFn.apply(ne, f(x1), f(mask).reshape(b, T), f(mu), spks_, cond_, f(w).reshape(b, T),
+            loss, y = _CFMLossFn.apply(ne, f(x1), f(mask).reshape(b, T), fg(mu), spks_, cond_, f(w).reshape(b, T),
                                        f(t_step).reshape(b), f(z), keep_, iso, float(self.sigma_min),
                                        *[p for p, _, _ in ne.lora_views])
         return loss, y.to(x1.dtype)

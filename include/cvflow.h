@@ -138,6 +138,21 @@ CVFLOW_API int cvflow_estimator_forward(cvflow_estimator* h, const cvflow_estima
  * autograd factor never forces a host synchronisation. */
 CVFLOW_API int cvflow_estimator_backward(cvflow_estimator* h, const void* dpred16, float grad_scale,
                                          const float* grad_scale_dev, void* stream);
+/* The same backward, continued through the first transformer block's input, the first ResnetBlock1D and the
+ * input pack (autograd of modules.py:1008-1019 and 89-94), so that the modules that PRODUCE the estimator inputs --
+ * the Conformer encoder / length regulator behind mu, the speaker affine layer behind spks (flow_model.py:248-400;
+ * LoRA targets of config.py:207-216) -- can be trained upstream. Outputs are fp32 in the input layouts
+ * (dx, dmu, dcond [B][80][T]; dspks [B][80]), each nullable, overwritten (not accumulated), zero on masked frames,
+ * including the CFG keep factor of the forward call and grad_scale * (*grad_scale_dev). */
+typedef struct cvflow_input_grads {
+  float* dx;
+  float* dmu;
+  float* dspks;
+  float* dcond;
+} cvflow_input_grads;
+CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void* dpred16, float grad_scale,
+                                                const float* grad_scale_dev, const cvflow_input_grads* grads,
+                                                void* stream);
 CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
 /* Measurement aid (bench.py roofline): when on, CUDA events bracket every tensor-core launch on
  * the launching stream. cvflow_profile_read synchronises the stream and sums per class

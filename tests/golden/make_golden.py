@@ -91,6 +91,27 @@ def train_case(name, n_blocks, n_mid, B, T, lengths, prompt_lens, data_seed, ste
     print(name, "loss", float(loss), "gradnorm", fx["grad_total_norm"], "ngrads", len(grads), "kept", len(fx["grads"]))
 
 
+def input_grad_case(name, src):
+    """dL/dmu, dL/dspks, dL/dcond of the reference's compute_loss (same inputs and draws as the fixture `src`):
+    what the encoder / speaker-affine LoRA layers upstream of the estimator receive (config.py:207-216)."""
+    fx = torch.load(os.path.join(HERE, src + ".pt"), map_location="cpu", weights_only=False)
+    cfm, sd, _ = build_ref(fx["n_blocks"], fx["n_mid"])
+    assert abs(wsum(sd) - fx["wsum"]) < 1e-6 * fx["wsum"]
+    cfm.train()
+    mu = fx["mu"].clone().requires_grad_(True)
+    spks = fx["spks"].clone().requires_grad_(True)
+    cond = fx["cond"].clone().requires_grad_(True)
+    step_seed = {"train_tiny": 7, "train_tiny_prompt": 8, "train_c1": 7, "train_c1_prompt": 7}[src]
+    torch.manual_seed(step_seed)
+    loss, _ = cfm.compute_loss(fx["x1"], fx["mask"], mu, spks, cond=cond, prompt_lens=fx["prompt_lens"])
+    assert float(loss) == float(fx["loss"]), (float(loss), float(fx["loss"]))
+    loss.backward()
+    torch.save(dict(kind="input_grads", src=src, loss=loss.detach(), dmu=mu.grad.clone(), dspks=spks.grad.clone(),
+                    dcond=cond.grad.clone()), os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "|dmu|", float(mu.grad.norm()), "|dspks|", float(spks.grad.norm()), "|dcond|",
+          float(cond.grad.norm()))
+
+
 def estimator_case(name, n_blocks, n_mid, Ts, seed):
     """export_onnx.py:34-41,95-116 protocol: batch 2, torch.rand inputs, random T."""
     cfm, sd, _ = build_ref(n_blocks, n_mid, r=0)
@@ -151,6 +172,10 @@ def structure_checks():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["inputgrads"]:      # added later: leaves the other fixtures untouched
+        input_grad_case("inputgrads_tiny_prompt", "train_tiny_prompt")
+        input_grad_case("inputgrads_c1", "train_c1")
+        sys.exit(0)
     structure_checks()
     first_mid_last = lambda k: any(s in k for s in ("down_blocks.0.1.0.", "mid_blocks.5.1.2.", "up_blocks.1.1.3."))
     train_case("train_tiny", 1, 1, 2, 37, [37, 21], None, 99, 7, lambda k: True)

@@ -59,3 +59,21 @@ def test_euler_matches_reference(name):
                                    prompt_len=fx["prompt"])
     assert cache.shape == fx["cache"].shape and torch.equal(cache, fx["cache"])
     assert torch.allclose(mel, fx["mel"], atol=2e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["inputgrads_tiny_prompt", "inputgrads_c1"])
+def test_input_gradients_match_reference(name):
+    """dL/dmu, dL/dspks, dL/dcond of compute_loss: what the modules upstream of the estimator train on."""
+    ig = load_golden(name)
+    fx = load_golden(ig["src"])
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    mu, spks, cond = (fx[k].clone().requires_grad_(True) for k in ("mu", "spks", "cond"))
+    loss, _, _ = O.cfm_compute_loss(sd, fx["x1"], fx["mask"], mu, spks, cond, fx["prompt_lens"], fx["t_rand"], fx["z"],
+                                    fx["cfg_rand"], lora_scaling=lora_scaling_of(sd))
+    loss.backward()
+    for got, key in ((mu.grad, "dmu"), (spks.grad, "dspks"), (cond.grad, "dcond")):
+        want = ig[key]
+        assert torch.allclose(got, want, atol=1e-7 + 1e-3 * float(want.abs().max()), rtol=1e-3), key
+    # masked frames and CFG-dropped samples get exactly zero
+    pad = fx["mask"].expand_as(mu) == 0
+    assert float(ig["dmu"][pad].abs().sum()) == 0.0 and float(mu.grad[pad].abs().sum()) == 0.0

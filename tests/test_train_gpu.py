@@ -134,3 +134,58 @@ def test_long_ragged_utterances_T1500():
             num += float((p.grad.cpu() - P[k].grad).double().pow(2).sum())
             den += float(P[k].grad.double().pow(2).sum())
     assert (num / den) ** 0.5 <= 1e-2, (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("name,dtype,tol", [("inputgrads_tiny_prompt", torch.float16, 1e-2),
+                                           ("inputgrads_c1", torch.float16, 1e-2),
+                                           ("inputgrads_c1", torch.bfloat16, 6e-2)])
+def test_input_gradients_vs_reference(name, dtype, tol):
+    """dL/dmu, dL/dspks, dL/dcond through cvflow_estimator_backward_inputs vs the reference's autograd
+    (golden vectors): rel-L2 <= 1e-2 with fp16 operands (bf16: its own noise floor, as for the LoRA grads);
+    exact zeros on padded frames; LoRA gradients unchanged by asking for the input gradients."""
+    from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
+    ig = load_golden(name)
+    fx = load_golden(ig["src"])
+    _, _, ref_lora_grads, _ = _step(fx, dtype)
+    est, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    est = est.cuda().train()
+    est.cvflow_dtype = dtype
+    cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
+    c = lambda k: fx[k].cuda()
+    mu, spks, cond = (c(k).requires_grad_(True) for k in ("mu", "spks", "cond"))
+    t = 1 - torch.cos(c("t_rand") * 0.5 * 3.14159265359)
+    loss, _ = cfm._loss_with_noise(c("x1"), c("mask"), mu, spks, cond, fx["prompt_lens"], t, c("z"), c("cfg_rand") > 0.2)
+    (2.0 * loss).backward()                  # the upstream factor must reach the input gradients too
+    assert abs(loss.item() - float(ig["loss"])) <= 1e-2 * float(ig["loss"])
+    for got, key in ((mu.grad, "dmu"), (spks.grad, "dspks"), (cond.grad, "dcond")):
+        want = 2.0 * ig[key]
+        rel = float((got.cpu() - want).double().norm() / want.double().norm())
+        assert rel <= tol, (key, rel)
+    pad = (fx["mask"].expand_as(fx["mu"]) == 0)
+    assert float(mu.grad.cpu()[pad].abs().sum()) == 0.0 and float(cond.grad.cpu()[pad].abs().sum()) == 0.0
+    for k, p in est.named_parameters():
+        if p.requires_grad:
+            assert torch.allclose(p.grad.cpu(), 2.0 * ref_lora_grads[k],
+                                  atol=1e-7 + 2e-3 * float(ref_lora_grads[k].abs().max())), k
+
+
+def test_input_gradients_generic_autograd():
+    """ConditionalDecoder.forward under autograd with an arbitrary loss: dL/dx, dL/dmu, dL/dspks, dL/dcond vs the oracle."""
+    from oracle import flow_oracle as O
+    from tests.helpers import lora_scaling_of
+    fx = load_golden("train_tiny")
+    est, sd, _ = build_estimator(1, 1, lora_r=8)
+    t = 1 - torch.cos(fx["t_rand"] * 0.5 * 3.14159265359)
+    leaves = [fx[k].clone().requires_grad_(True) for k in ("y", "mu", "spks", "cond")]
+    out = O.estimator_forward(sd, leaves[0], fx["mask"], leaves[1], t.view(-1), leaves[2], leaves[3],
+                              lora_scaling=lora_scaling_of(sd))
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out * gout).sum().backward()
+    est = est.cuda().train()
+    dl = [fx[k].cuda().requires_grad_(True) for k in ("y", "mu", "spks", "cond")]
+    o = est(dl[0], fx["mask"].cuda(), dl[1], t.view(-1).cuda(), dl[2], dl[3])
+    (o * gout.cuda()).sum().backward()
+    assert torch.allclose(o.detach().cpu(), out.detach(), atol=2e-2, rtol=2e-2)
+    for a, b, key in zip(dl, leaves, ("dx", "dmu", "dspks", "dcond")):
+        rel = float((a.grad.cpu() - b.grad).double().norm() / b.grad.double().norm())
+        assert rel <= 1e-2, (key, rel)
