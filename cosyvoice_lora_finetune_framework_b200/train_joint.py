@@ -89,12 +89,14 @@ def main(argv=None):
     lr = args.lr or cfg.get('learning_rate', 5e-5)
     accumulate = cfg.get('accumulate_grad_batches', 8)
 
-    # flow LoRA restricted to the estimator's attn1 q/k/v: the part of the flow the CUDA path trains
+    # flow LoRA on the reference's target list (config.py:207-216): the estimator's attn1 q/k/v run on the CUDA path,
+    # the Conformer encoder's linear_q/k/v, w_1, w_2 are host-side modules trained through dL/dmu of the estimator
+    # backward. lora_dropout is forced to 0: the CUDA path folds B A into the GEMM operand.
     flow_lora = dict(cfg.get('flow_lora', {}))
-    flow_lora['target_modules'] = ['to_q', 'to_k', 'to_v']
     flow_lora['lora_dropout'] = 0.0
     model = build_joint_model(PRETRAINED_MODEL_DIR, str(device), 'flow_only', None, flow_lora)
     model.flow.decoder.estimator.cvflow_dtype = torch.float16 if args.dtype == 'fp16' else torch.bfloat16
+    upstream = [p for n, p in model.flow.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]
     if args.resume:
         state = torch.load(args.resume, map_location='cpu').get('state_dict', {})
         model.load_state_dict({k[len('model.'):]: v for k, v in state.items() if k.startswith('model.')}, strict=False)
@@ -103,7 +105,8 @@ def main(argv=None):
     trainer = FlowLoRATrainer(model.flow.decoder, lr=lr, weight_decay=TRAIN_CONFIG.get('weight_decay', 0.01),
                               max_grad_norm=TRAIN_CONFIG.get('gradient_clip_val', 1.0),
                               warmup_steps=TRAIN_CONFIG.get('warmup_steps', 50), total_steps=epochs * steps_per_epoch,
-                              min_lr=TRAIN_CONFIG.get('min_learning_rate', 1e-6), accumulate=accumulate)
+                              min_lr=TRAIN_CONFIG.get('min_learning_rate', 1e-6), accumulate=accumulate,
+                              extra_params=upstream)
     model.train()
     os.makedirs(args.output_dir, exist_ok=True)
     for epoch in range(epochs):

@@ -8,6 +8,11 @@ accumulation), re-expressed for one process per GPU:
              NVLink/NVSwitch; nothing else crosses ranks (frozen weights are replicated)
   tail       fused global-norm clip + AdamW over the flat bucket, then the W_eff refresh kernel
 
+LoRA parameters UPSTREAM of the estimator (Conformer encoder linear_q/k/v, w_1/w_2 -- the rest of the
+reference's flow_lora target list, config.py:207-216) can be handed in as `extra_params`: they receive
+their gradients through dL/dmu / dL/dspks of the estimator backward, live in a second flat bucket and
+go through the same allreduce, the same global gradient norm and the same fused AdamW kernel.
+
 N-rank result == the average of N single-process reference runs, one per shard.
 """
 import ctypes as C
@@ -30,7 +35,7 @@ def lr_lambda(step, warmup_steps, total_steps, base_lr, min_lr):
 
 class FlowLoRATrainer:
     def __init__(self, cfm, lr=1e-4, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0,
-                 warmup_steps=0, total_steps=0, min_lr=1e-6, accumulate=1, process_group=None):
+                 warmup_steps=0, total_steps=0, min_lr=1e-6, accumulate=1, process_group=None, extra_params=None):
         self.cfm = cfm
         self.ne = E.native_of(cfm.estimator)
         self.L = E._lib()
@@ -55,6 +60,28 @@ class FlowLoRATrainer:
         self.hyper = torch.zeros(4, device=dev)
         self.hyper_host = torch.zeros(4).pin_memory()
         self._graph = None
+        # second flat bucket: trainable parameters upstream of the estimator (become views into it)
+        self.extra = [p for p in (extra_params or []) if p.requires_grad]
+        self.n_extra = sum(p.numel() for p in self.extra)
+        if self.extra:
+            with torch.inference_mode(False), torch.no_grad():
+                self.xparam = torch.empty(self.n_extra, device=dev, dtype=torch.float32)
+                self.xgrad = torch.zeros(self.n_extra, device=dev, dtype=torch.float32)
+                self.xviews, off = [], 0
+                for p in self.extra:
+                    if p.device != dev or p.dtype != torch.float32:
+                        raise ValueError("extra_params must be fp32 parameters on %s" % dev)
+                    n = p.numel()
+                    view = self.xparam[off:off + n].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
+                    p.grad = self.xgrad[off:off + n].view_as(p)
+                    self.xviews.append((p, off, n))
+                    off += n
+            self.xm = torch.zeros(self.n_extra, device=dev)
+            self.xv = torch.zeros(self.n_extra, device=dev)
+            self.xsumsq = torch.zeros(1, device=dev)
+            self.xpartials = torch.zeros(296, device=dev)
 
     def current_lr(self):
         if self.total_steps <= 0:
@@ -77,16 +104,43 @@ class FlowLoRATrainer:
         self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
 
+    def _gather_extra(self):
+        """Upstream gradients back into the flat bucket when autograd (or zero_grad(set_to_none=True)) replaced the
+        .grad views."""
+        with torch.no_grad():
+            for p, off, n in self.xviews:
+                view = self.xgrad[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = view
+                elif p.grad.data_ptr() != view.data_ptr():
+                    view.add_(p.grad)
+                    p.grad = view
+
     def optimizer_step(self, from_graph=False):
         ne = self.ne
         st = E._stream()
         g = ne.grad_bucket
+        if self.extra:
+            self._gather_extra()
         if self.world > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.extra:
+                dist.all_reduce(self.xgrad, op=dist.ReduceOp.SUM, group=self.pg)
         if not from_graph:
             self._advance_hyper()
         N.check(self.L.cvflow_sumsq(g.data_ptr(), ne.n_lora, self.partials.data_ptr(), self.sumsq.data_ptr(), st),
                 "cvflow_sumsq")
+        if self.extra:      # one global gradient norm over both buckets (clip_grad_norm_ over all trainable parameters)
+            N.check(self.L.cvflow_sumsq(self.xgrad.data_ptr(), self.n_extra, self.xpartials.data_ptr(),
+                                        self.xsumsq.data_ptr(), st), "cvflow_sumsq")
+            self.sumsq.add_(self.xsumsq)
+            N.check(self.L.cvflow_adamw_step(self.xparam.data_ptr(), self.xgrad.data_ptr(), self.xm.data_ptr(),
+                                             self.xv.data_ptr(), self.n_extra, self.sumsq.data_ptr(), 1.0 / self.world,
+                                             float(self.max_grad_norm), float(self.current_lr()), self.betas[0],
+                                             self.betas[1], self.eps, self.wd, max(1, self.step_count),
+                                             self.found_inf.data_ptr(), C.c_void_p(self.hyper.data_ptr()), st),
+                    "cvflow_adamw_step")
+            self.xgrad.zero_()
         N.check(self.L.cvflow_adamw_step(ne.param_bucket.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                          ne.n_lora, self.sumsq.data_ptr(), 1.0 / self.world, float(self.max_grad_norm),
                                          float(self.current_lr()), self.betas[0], self.betas[1], self.eps, self.wd,
@@ -111,6 +165,9 @@ class FlowLoRATrainer:
         the per-step optimiser scalars come from device memory. Returns the (static) loss tensor."""
         if self.accumulate != 1:
             raise ValueError("train_step_graphed captures a whole optimiser step: accumulate must be 1")
+        if self.extra:
+            raise ValueError("train_step_graphed captures the estimator-only step (prepared mu / spks); with "
+                             "extra_params use micro_step / optimizer_step around the model's own forward")
         key = (tuple(x1.shape), tuple(spks.shape))
         if self._graph is None or self._graph["key"] != key:
             dev = self.ne.device

@@ -112,6 +112,62 @@ def input_grad_case(name, src):
           float(cond.grad.norm()))
 
 
+FLOW_TINY = dict(encoder_num_blocks=2, decoder_n_blocks=1, decoder_num_mid_blocks=1)
+FLOW_TARGETS = ['to_q', 'to_k', 'to_v', 'linear_q', 'linear_k', 'linear_v', 'w_1', 'w_2']     # config.py:207-216
+
+
+def flow_model_case(name, init_seed, py_seed, step_seed):
+    """MaskedDiffWithXvec.forward(batch) + backward of the REAL reference with LoRA on the estimator's attn1 q/k/v
+    AND on the Conformer encoder (the reference's flow_lora target list): loss and every LoRA gradient. Weights are
+    the seeded random init (bit-identical between the reference and our module tree, asserted here). The encoder runs
+    in eval() so that its dropout does not consume the torch RNG; the three draws of compute_loss are recorded."""
+    import random
+    from cosyvoice_lora_finetune_framework_b200 import flow_model as our_flow, lora as our_lora
+    ref_utils.set_all_random_seed(init_seed)
+    m = ref_flow.build_flow_model(None, 'cpu', **FLOW_TINY)
+    stats = ref_lora.apply_lora_to_model(m, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=FLOW_TARGETS)
+    ref_utils.set_all_random_seed(init_seed)
+    o = our_flow.build_flow_model(None, 'cpu', **FLOW_TINY)
+    our_lora.apply_lora_to_model(o, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=FLOW_TARGETS)
+    sa, sb = m.state_dict(), o.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa), "seeded init differs"
+    m.train()
+    m.encoder.eval()
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    batch = dict(speech_token=torch.randint(0, 4096, (B, 40), generator=g), speech_token_len=torch.tensor([40, 33, 21]),
+                 speech_feat=torch.randn(B, 70, 80, generator=g) * 2 - 6, speech_feat_len=torch.tensor([70, 57, 36]),
+                 embedding=torch.randn(B, 192, generator=g),
+                 cross_sample_mel=torch.randn(B, 30, 80, generator=g) * 2 - 6,
+                 cross_sample_mel_len=torch.tensor([30, 0, 12]))
+    rec = {}
+    orig = m.decoder.compute_loss
+
+    def recording(x1, mask, mu, spks, cond=None, prompt_lens=None):
+        st = torch.get_rng_state()
+        b = mu.shape[0]
+        rec.update(t_rand=torch.rand([b, 1, 1]), z=torch.randn_like(x1), cfg_rand=torch.rand(b),
+                   prompt_lens=list(prompt_lens) if prompt_lens is not None else None, mu=mu.detach().clone(),
+                   spks=spks.detach().clone(), cond=cond.detach().clone(), x1=x1.detach().clone())
+        torch.set_rng_state(st)
+        return orig(x1, mask, mu, spks, cond=cond, prompt_lens=prompt_lens)
+
+    m.decoder.compute_loss = recording
+    random.seed(py_seed)
+    torch.manual_seed(step_seed)
+    out = m(batch, torch.device('cpu'))
+    out['loss'].backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.requires_grad}
+    assert all(v is not None for v in grads.values())
+    fx = dict(kind="flow_model", arch=FLOW_TINY, targets=FLOW_TARGETS, init_seed=init_seed, py_seed=py_seed, batch=batch,
+              wsum=wsum(sa), lora_stats=stats, loss=out['loss'].detach(), grads=grads, **rec)
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    enc = torch.sqrt(sum(v.double().pow(2).sum() for k, v in grads.items() if k.startswith("encoder.")))
+    est = torch.sqrt(sum(v.double().pow(2).sum() for k, v in grads.items() if k.startswith("decoder.")))
+    print(name, "loss", float(out['loss']), "prompt_lens", rec["prompt_lens"], "ngrads", len(grads), "|enc|", float(enc),
+          "|est|", float(est), stats["replaced_layers"])
+
+
 def estimator_case(name, n_blocks, n_mid, Ts, seed):
     """export_onnx.py:34-41,95-116 protocol: batch 2, torch.rand inputs, random T."""
     cfm, sd, _ = build_ref(n_blocks, n_mid, r=0)
@@ -175,6 +231,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["inputgrads"]:      # added later: leaves the other fixtures untouched
         input_grad_case("inputgrads_tiny_prompt", "train_tiny_prompt")
         input_grad_case("inputgrads_c1", "train_c1")
+        sys.exit(0)
+    if sys.argv[1:] == ["flowmodel"]:
+        flow_model_case("flowmodel_tiny", 21, 3, 5)
         sys.exit(0)
     structure_checks()
     first_mid_last = lambda k: any(s in k for s in ("down_blocks.0.1.0.", "mid_blocks.5.1.2.", "up_blocks.1.1.3."))

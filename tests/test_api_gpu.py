@@ -63,13 +63,21 @@ def test_flow_only_training_reduces_loss_and_merges(tmp_path):
     assert (mel_lora - mel_merged).abs().max().item() <= 2e-2 * mel_lora.abs().max().item()
 
 
-def test_requires_grad_on_prepared_tensors_is_refused():
+def test_requires_grad_on_prepared_tensors():
+    """mu / spks / cond that require grad get their gradients (modules upstream of the estimator can be trained);
+    a target mel that requires grad is refused loudly."""
     model = _model()
     est = model.flow.decoder
     x = torch.randn(1, 80, 16, device='cuda')
     mu = torch.randn(1, 80, 16, device='cuda', requires_grad=True)
+    spk = torch.randn(1, 80, device='cuda', requires_grad=True)
+    est.training_cfg_rate = 0.0
+    loss, _ = est.compute_loss(x, torch.ones(1, 1, 16, device='cuda'), mu, spk, cond=torch.zeros(1, 80, 16, device='cuda'))
+    loss.backward()
+    for g in (mu.grad, spk.grad):
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
     with pytest.raises(NotImplementedError):
-        est.compute_loss(x, torch.ones(1, 1, 16, device='cuda'), mu, torch.randn(1, 80, device='cuda'),
+        est.compute_loss(x.clone().requires_grad_(True), torch.ones(1, 1, 16, device='cuda'), mu.detach(), spk.detach(),
                          cond=torch.zeros(1, 80, 16, device='cuda'))
 
 
@@ -85,6 +93,7 @@ def test_train_joint_cli_synthetic(tmp_path):
         config.JOINT_TRAINING_CONFIG.update(old)
     ck = torch.load(os.path.join(str(tmp_path), 'joint_flow_only_last.ckpt'), map_location='cpu', weights_only=False)
     assert any(k.startswith('model.flow.decoder.estimator.') and k.endswith('lora_A') for k in ck['state_dict'])
+    assert any(k.startswith('model.flow.encoder.') and k.endswith('lora_A') for k in ck['state_dict'])
     merged = torch.load(os.path.join(str(tmp_path), 'flow_merged_flow_only.pt'), map_location='cpu')
     assert not any('lora_' in k or 'original_layer' in k for k in merged)
 
