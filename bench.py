@@ -141,6 +141,13 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel<64,1> launch (grid 256, 12.6 us) from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_full_v3_summary.txt: the operands of a step's GEMMs are
+# L2-resident (126 MB L2), so DRAM traffic per launch is far below the algorithmic operand bytes.
+NCU_GEMM_TRAFFIC = 3744256   # bytes per launch
+NCU_GEMM_TRAFFIC_SOURCE = "profiles/r01_ncu_full_v3_summary.txt (ncu --set full, one gemm_tc_kernel<64,1> launch)"
+
+
 def oracle_train_step_timer(B, T, steps, warmup):
     """The reference algorithm (oracle port, plain PyTorch fp32 + autograd + AdamW) on the host cores."""
     from oracle import flow_oracle as O
@@ -302,9 +309,13 @@ def run_cvflow(a):
     L = E._lib()
     if rank == 0:
         L.cvflow_set_profile(ne.handle, 1)
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
     for _ in range(2):          # every rank steps (the optimiser step holds the gradient allreduce); rank 0 records
         eager_step(batch)
+    ev_b.record()
     sync()
+    ms_eager2 = ev_a.elapsed_time(ev_b)
     _trace("profiled eager steps done")
     if rank == 0:
         n = 5
@@ -319,9 +330,12 @@ def run_cvflow(a):
         peak, _, how = peaks()
         ach = (fl[0] / 2) / (msa[0] / 2 * 1e9)
         roofline = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": how,
+                    "frac": ach / peak, "traffic": NCU_GEMM_TRAFFIC, "traffic_source": NCU_GEMM_TRAFFIC_SOURCE,
+                    "peak_source": how,
                     "avg_launch_us": 1e3 * msa[0] / max(1, cnt[0]),
-                    "share_of_eager_step": None,
+                    # GEMM device time / device time of the same two eager (event-bracketed) steps; the ncu launch list
+                    # of the same step (profiles/r01_launches_train_v7_summary.txt) gives 46 % (cold-cache, serialised)
+                    "share_of_eager_step": msa[0] / ms_eager2 if ms_eager2 > 0 else None,
                     "note": "algorithmic FLOPs = 2*M*N*K per launch with M = real (unpadded) rows, summed over the "
                             "%d GEMM launches of a step; event-bracketed, so launch gaps are included" % (cnt[0] // 2)}
 
