@@ -51,6 +51,7 @@ def _lib():
         L.cvflow_estimator_forward.argtypes = [vp, C.POINTER(EstimatorIO), vp]
         L.cvflow_estimator_backward.argtypes = [vp, vp, f, vp, vp]
         L.cvflow_estimator_backward_inputs.argtypes = [vp, vp, f, vp, C.POINTER(InputGrads), vp]
+        L.cvflow_set_lora_dropout.argtypes = [vp, f, C.c_uint64, vp, i64]
         L.cvflow_launch_count.argtypes = [vp]
         L.cvflow_launch_count.restype = i64
         L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
@@ -152,11 +153,15 @@ class NativeEstimator:
                         raise NotImplementedError("the fused estimator supports LoRA on attn1.to_q/to_k/to_v only")
         r = loras[0].r if loras else 0
         scaling = loras[0].scaling if loras else 1.0
+        drop_ps = {float(lm.lora_dropout.p) if isinstance(lm.lora_dropout, nn.Dropout) else 0.0 for lm in loras}
         for lm in loras:
             if lm.r != r or lm.scaling != scaling:
                 raise NotImplementedError("all LoRA layers must share rank and alpha")
-            if isinstance(lm.lora_dropout, nn.Dropout) and lm.lora_dropout.p > 0 and False:
-                pass
+        if len(drop_ps) > 1:
+            raise NotImplementedError("all LoRA layers of the estimator must share lora_dropout")
+        self.lora_dropout_p = drop_ps.pop() if drop_ps else 0.0
+        self._drop_active = 0.0          # dropout rate currently set on the handle (0 when the module is in eval())
+        self._drop_mask = None           # explicit keep masks for parity tests (set_debug_dropout_mask)
         self.lora_modules = loras
         self.lora_r = r
         gelu = m.down_blocks[0][1][0].ff.net[0].approximate
@@ -256,6 +261,20 @@ class NativeEstimator:
                     self._bind(Q + ".w2", self._h(w2_))
                     self._bind(Q + ".w2_t", self._h(w2_.t()))
                     self._bind(Q + ".b2", self._f(b2_))
+            if r > 0 and self.lora_dropout_p > 0:
+                # lora_dropout > 0: the branch cannot be folded; per block [W0 | s B_cat] ([1536][320]) for the forward
+                # and [W0^T ; B_blk] ([320][1536]) for the dgrad, stacked so that the LoRA halves are refreshed by a few
+                # batched torch ops after every optimiser step (_refresh_dropout_images)
+                tbs = [(("%s.1.%d" % (S, j)), tb) for S, st in stages for j, tb in enumerate(st[1])]
+                nb = len(tbs)
+                self.w0d = torch.zeros(nb, 1536, 320, device=self.device, dtype=self.dtype)
+                self.w0t_ext = torch.zeros(nb, 320, 1536, device=self.device, dtype=self.dtype)
+                for i, (Q, tb) in enumerate(tbs):
+                    w0 = torch.cat([_lin(getattr(tb.attn1, pn))[0].detach().float() for pn in ("to_q", "to_k", "to_v")], 0)
+                    self.w0d[i, :, :256] = w0.to(self.dtype)
+                    self.w0t_ext[i, :256] = w0.t().to(self.dtype)
+                    self._bind(Q + ".w0d", self.w0d[i])
+                    self._bind(Q + ".w0t_ext", self.w0t_ext[i])
             # resolution changes
             wds = m.down_blocks[0][2].conv.weight
             self._bind("down_blocks.0.2.w", self._h(conv3_w(wds)))
@@ -345,8 +364,45 @@ class NativeEstimator:
     def refresh_lora(self):
         """Rebuild W_eff = W + (alpha/r) B A (call after every optimiser step)."""
         N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
+        if self.lora_dropout_p > 0 and self.lora_r > 0:
+            self._refresh_dropout_images()
         self._merged_version = self._version()
         self._dirty = False
+
+    def _refresh_dropout_images(self):
+        """LoRA halves of the un-folded operands from the fp32 masters: w0d[:, n, 256 + p r + j] = s B_p[n][j] (block
+        structure), w0t_ext[:, 256 + p r + j, p 512 + n] = B_p[n][j]. The flat bucket holds, per attention block,
+        A_q, B_q, A_k, B_k, A_v, B_v in this order."""
+        r = self.lora_r
+        nb = self.w0d.shape[0]
+        with torch.no_grad():
+            per = self.param_bucket[: nb * 3 * (r * 256 + 512 * r)].view(nb, 3, r * 256 + 512 * r)
+            Bm = per[:, :, r * 256:].reshape(nb, 3, 512, r)
+            s = float(self.cfg.lora_scaling)
+            for p in range(3):
+                self.w0d[:, p * 512:(p + 1) * 512, 256 + p * r:256 + (p + 1) * r] = (Bm[:, p] * s).to(self.dtype)
+                self.w0t_ext[:, 256 + p * r:256 + (p + 1) * r, p * 512:(p + 1) * 512] = Bm[:, p].transpose(1, 2).to(self.dtype)
+
+    def set_debug_dropout_mask(self, mask):
+        """Explicit keep masks (uint8 [n_blocks][3][B*T][256], 1 = keep) instead of the hash RNG: parity tests only."""
+        self._drop_mask = mask.contiguous() if mask is not None else None
+        self._drop_active = -1.0      # force a re-send
+
+    def dropout_seed(self):
+        """Base seed of the mask hash: a function of torch.manual_seed (no RNG stream is consumed)."""
+        return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x51ED270B) & (2 ** 63 - 1)
+
+    def sync_dropout(self, training):
+        """Tell the handle whether the LoRA dropout is active (the nn.Module's train()/eval() state decides)."""
+        p = self.lora_dropout_p if (training and self.lora_r > 0) else 0.0
+        if p != self._drop_active:
+            seed = self.dropout_seed() if p > 0 else 0
+            mk = self._drop_mask if p > 0 else None
+            N.check(self.L.cvflow_set_lora_dropout(self.handle, float(p), C.c_uint64(seed),
+                                                   C.c_void_p(mk.data_ptr()) if mk is not None else None,
+                                                   int(mk.shape[2]) if mk is not None else 0), "cvflow_set_lora_dropout")
+            self._drop_active = p
+            self.ws_key = None       # the training workspace holds the u_d stashes only when dropout is on
 
     def _version(self):
         try:
@@ -364,13 +420,8 @@ class NativeEstimator:
             self.refresh_lora()
 
     def check_trainable(self, est):
-        if est.training and not getattr(est, "cvflow_ignore_lora_dropout", False):
-            for lm in self.lora_modules:
-                if isinstance(lm.lora_dropout, nn.Dropout) and lm.lora_dropout.p > 0:
-                    raise NotImplementedError(
-                        "lora_dropout=%g: the fused q/k/v path folds B A into the GEMM operand and therefore "
-                        "supports lora_dropout == 0 only (set estimator.cvflow_ignore_lora_dropout = True to "
-                        "train without LoRA dropout, or call estimator.eval())" % lm.lora_dropout.p)
+        """LoRA dropout follows the module's train()/eval() state, like nn.Dropout in the reference."""
+        self.sync_dropout(bool(est.training) and not getattr(est, "cvflow_ignore_lora_dropout", False))
 
     # -- calls -----------------------------------------------------------------------------------
     def _workspace(self, B, T, training):
@@ -498,6 +549,7 @@ def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
     needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p, _, _ in ne.lora_views) or
                                               any(v is not None and v.requires_grad for v in (x_, mu_, spks_, cond_)))
     if needs_grad:
+        ne.sync_dropout(bool(module.training) and not getattr(module, "cvflow_ignore_lora_dropout", False))
         out = _EstimatorFn.apply(ne, x_, mask_, mu_, t_, spks_, cond_, iso, *[p for p, _, _ in ne.lora_views])
     else:
         out = ne.forward(x_, mask_, mu_, t_, spks_, cond_, iso_len=iso, training=False)

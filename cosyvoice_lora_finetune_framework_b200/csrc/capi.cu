@@ -129,6 +129,11 @@ extern "C" CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, 
   InputGrads g{ig->dx, ig->dmu, ig->dspks, ig->dcond};
   return h->e->backward(dpred16, grad_scale, grad_scale_dev, (cudaStream_t)stream, &g) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, uint64_t seed, const uint8_t* debug_mask,
+                                                  int64_t debug_rows) {
+  if (!h) { set_error("cvflow_set_lora_dropout: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->set_lora_dropout(p, (unsigned long long)seed, debug_mask, (long)debug_rows) ? CVFLOW_ERR_ARG : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h) { return h ? h->e->launches() : 0; }
 
 #define RET_LAUNCH(call, what)                                                                       \

@@ -49,6 +49,31 @@ Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {
 Estimator::~Estimator() {
   if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_done_[0]); cudaEventDestroy(ev_done_[1]); }
   if (lora_table_dev_) cudaFree(lora_table_dev_);
+  if (drop_seed_dev_) cudaFree(drop_seed_dev_);
+}
+
+int Estimator::set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows) {
+  if (!(p >= 0.f && p < 1.f)) { set_error("estimator: lora_dropout must be in [0, 1)"); return -1; }
+  if (p > 0.f && cfg.lora_r <= 0) { set_error("estimator: lora_dropout needs LoRA on q/k/v"); return -1; }
+  if (!drop_seed_dev_ && cudaMalloc(&drop_seed_dev_, sizeof(unsigned long long)) != cudaSuccess) {
+    set_error("cudaMalloc(dropout seed) failed");
+    return -1;
+  }
+  if (cudaMemcpy(drop_seed_dev_, &seed, sizeof(seed), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("cudaMemcpy(dropout seed) failed");
+    return -1;
+  }
+  drop_p_ = p; drop_dbg_ = dbg_mask; drop_dbg_rows_ = dbg_rows;
+  plans_.clear();
+  return 0;
+}
+LoraDropSpec Estimator::drop_spec(int blk) const {
+  LoraDropSpec d;
+  d.seed = drop_seed_dev_; d.dbg = drop_dbg_; d.mcap = drop_mcap_; d.blk = blk;
+  const double t = (double)drop_p_ * 4294967296.0;
+  d.thr = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+  d.inv_keep = 1.f / (1.f - drop_p_);
+  return d;
 }
 
 int Estimator::bind(const char* name, void* ptr, long numel, int dtype) {
@@ -253,9 +278,13 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   const long M = (long)B * L;
   // with LoRA in training the q/k/v GEMM also emits u = x1 A_cat^T as 64 extra output columns
   // (operand rows 1536..1599 of weff_ext), which the wgrad kernel consumes in the backward pass
-  const bool ext = cfg.lora_r > 0 && training_;
+  // lora_dropout > 0: the low-rank branch is not foldable; u_d = drop(x1) A^T comes from a CUDA-core kernel and enters the
+  // q/k/v GEMM as a second K segment against [W0 | s B_cat]
+  const bool drop = cfg.lora_r > 0 && training_ && drop_p_ > 0.f;
+  const bool ext = cfg.lora_r > 0 && training_ && !drop;
   const long ldq = ext ? 1600 : 1536;
   void* x1 = alloc(M * 256 * 2);
+  void* ud = drop ? alloc(M * 64 * 2) : nullptr;
   void* qkv = alloc(M * ldq * 2);
   void* o = alloc(M * 512 * 2);
   float* lse = (float*)alloc((long)B * 8 * L * 4);
@@ -269,7 +298,18 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
                             M, cfg.bf16, stream_));
     ++launches_;
   }
-  {
+  if (drop) {
+    if (!dry_) {
+      CKL(launch_lora_down_dropout(x1, get(Q + ".acat16", cfg.bf16, 64L * 256), ud, M, cfg.lora_r, cfg.bf16,
+                                   drop_spec(lora_idx), stream_));
+      ++launches_;
+    }
+    GemmArgs g = linear_args(x1, M, 256, get(Q + ".w0d", cfg.bf16, 1536L * 320), 1536, qkv, 0);
+    g.A[1] = ud; g.a_rows[1] = (int)M; g.a_cols[1] = 64; g.a_ld[1] = 64; g.a_bstride[1] = M * 64L;
+    g.Ktot = 320; g.nseg = 2;
+    g.seg[1] = GemmSeg{1, 0, 0, 1};
+    CK(run_gemm(g));
+  } else {
     GemmArgs g = ext ? linear_args(x1, M, 256, get(Q + ".weff_ext", cfg.bf16, 1600L * 256), 1600, qkv, 0)
                      : linear_args(x1, M, 256, get(Q + ".weff", cfg.bf16, 1536L * 256), 1536, qkv, 0);
     CK(run_gemm(g));
@@ -316,7 +356,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     }
   }
   *h_out = h2;
-  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p};
+  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p, ud, drop ? 1 : 0};
   return 0;
 }
 
@@ -458,6 +498,15 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   kmax1_ = (int*)alloc(attn_kinfo_ints(B, T) * 4);
   kmax2_ = (int*)alloc(attn_kinfo_ints(B, T2) * 4);
   mask1_ = mask1; mask2_ = mask2; cat1_ = cat1; cat0_ = cat0;
+  drop_mcap_ = (long)B * T;
+  if (!dry_ && training_ && cfg.lora_r > 0 && drop_p_ > 0.f) {
+    if (drop_dbg_ && drop_dbg_rows_ != drop_mcap_) {
+      set_error("estimator: explicit dropout mask has %ld rows per projection, this batch needs %ld", drop_dbg_rows_, drop_mcap_);
+      return -1;
+    }
+    CKL(launch_lora_seed_bump(drop_seed_dev_, stream_));   // fresh masks per training forward; the backward reuses them
+    ++launches_;
+  }
   if (!dry_) {
     CKL(launch_mask_down(io.mask, io.mask_nb, mask1, mask2, B, T, T2, stream_));
     CKL(launch_attn_kinfo(mask1, B, T, kmax1_, stream_));
@@ -641,31 +690,42 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
   const bool lora = cfg.lora_r > 0;
   const long ldx = lora ? 320 : 256;
   if (lora || need_input_grad) {
-    GemmArgs g = lora ? linear_args(dqkv, M, 1536, get(Q + ".weff_t_ext", cfg.bf16, 320L * 1536), 320, dxe, 0)
+    GemmArgs g = lora ? linear_args(dqkv, M, 1536, get(Q + (t.drop ? ".w0t_ext" : ".weff_t_ext"), cfg.bf16, 320L * 1536),
+                                    320, dxe, 0)
                       : linear_args(dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, dxe, 0);
     CK(run_gemm(g));
+  }
+  if (t.drop && !dry_) {   // dx1 += s/(1-p) sum_p keep_p o (v_p A_p)
+    CKL(launch_lora_dropout_bwd(dxe, get(Q + ".acat16", cfg.bf16, 64L * 256), M, cfg.lora_r, cfg.lora_scaling, cfg.bf16,
+                                drop_spec(t.lora_idx), stream_));
+    ++launches_;
   }
   if (lora && !dry_) {
     Plan& pl = *plan_;
     if ((size_t)wg_idx_ >= pl.wgrads.size()) {
       pl.wgrads.emplace_back(lora_wgrad_plan_bytes());
-      const uint16_t* u = reinterpret_cast<const uint16_t*>(t.qkv) + 1536;
+      const uint16_t* u = t.drop ? reinterpret_cast<const uint16_t*>(t.ud) : reinterpret_cast<const uint16_t*>(t.qkv) + 1536;
       const uint16_t* v = reinterpret_cast<const uint16_t*>(dxe) + 256;
-      if (lora_wgrad_prepare(pl.wgrads.back().data(), dqkv, t.x1, u, t.ldq, v, ldx, M, cfg.lora_r,
+      if (lora_wgrad_prepare(pl.wgrads.back().data(), dqkv, t.x1, u, t.drop ? 64 : t.ldq, v, ldx, M, cfg.lora_r,
                              tmp.wg_scratch + (long)t.lora_idx * tmp.wg_stride, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
     }
     cudaStream_t ws = stream_;
-    if (wgrad_side_) {
+    if (wgrad_side_ && !t.drop) {
       cudaEventRecord(ev_fork_, stream_);
       cudaStreamWaitEvent(side_, ev_fork_, 0);
       ws = side_;
     }
     prof_begin(4, 2.0 * M * 64.0 * (1536 + 256), ws);
     if (!(skip_ & 8u)) CKL(lora_wgrad_launch_partial(pl.wgrads[wg_idx_].data(), ws));
+    if (t.drop) {   // the masked x^T v partials replace the un-masked ones of the tensor-core kernel
+      CKL(lora_wgrad_launch_a_dropout(pl.wgrads[wg_idx_].data(), t.x1, reinterpret_cast<const uint16_t*>(dxe) + 256, ldx,
+                                      drop_spec(t.lora_idx), ws));
+      ++launches_;
+    }
     ++wg_idx_;
     prof_end(ws);
-    if (wgrad_side_) {
+    if (wgrad_side_ && !t.drop) {
       cudaEventRecord(ev_done_[par], side_);
       ev_done_valid_[par] = true;
     }

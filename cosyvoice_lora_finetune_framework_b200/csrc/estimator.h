@@ -43,6 +43,7 @@ struct ResnetRec { std::string prefix; int cin, B, L; void *c1, *c2; float *st1,
 struct TBRec {
   std::string prefix; int lora_idx, B, L; long ldq; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
   const float* mask; const int* kmax; int iso_p;
+  void* ud; int drop;   // lora_dropout > 0: u_d = (drop(x) A^T) stash [M][64], and the flag
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
@@ -75,6 +76,9 @@ class Estimator {
   int forward(const EstimatorIO& io, cudaStream_t st);
   int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st,
                const InputGrads* in_grads = nullptr);
+  // lora_dropout p of the q/k/v LoRA branches in training forwards (0 = off: B A is folded into the GEMM operand);
+  // dbg_mask: optional explicit keep masks [n_tbs][3][dbg_rows][256] bytes for parity tests (dbg_rows must be B*T)
+  int set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows);
   long launches() const { return launches_; }
   void set_profile(int on);
   // class ids: 0 gemm, 1 attn_fwd, 2 attn_bwd, 3 norm/elementwise, 4 lora_wgrad
@@ -136,6 +140,11 @@ class Estimator {
   cudaEvent_t ev_fork_ = nullptr, ev_done_[2] = {nullptr, nullptr};
   bool ev_done_valid_[2] = {false, false};
   bool wgrad_side_ = false;  // CVFLOW_WGRAD_SIDE=1 (measured: no gain over PDL-chained launches on one stream)
+  float drop_p_ = 0.f;
+  unsigned long long* drop_seed_dev_ = nullptr;
+  const uint8_t* drop_dbg_ = nullptr;
+  long drop_dbg_rows_ = 0, drop_mcap_ = 0;
+  LoraDropSpec drop_spec(int blk) const;
   unsigned skip_ = 0;        // CVFLOW_SKIP bit mask (profiling aid, results become garbage): 1 attention, 2 layernorm, 4 groupnorm, 8 wgrad, 16 gemm
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
   int *kmax1_ = nullptr, *kmax2_ = nullptr;

@@ -125,6 +125,27 @@ int lora_wgrad_launch_partial(const void* plan, cudaStream_t st);
 int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
                             int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st);
 
+// lora_dropout > 0: independent keep masks per (attention block, projection, token, feature) from a counter-based hash of
+// a device-resident seed (recomputed in the backward, nothing stored), or an explicit byte mask for the parity tests.
+struct LoraDropSpec {
+  const unsigned long long* seed;  // device scalar
+  const uint8_t* dbg;              // optional explicit keep mask [nblocks][3][mcap][256] (1 = keep), else NULL
+  long mcap;                       // rows of the counter space per (block, projection): B * T
+  int blk;                         // attention block index
+  unsigned thr;                    // drop iff hash32 < thr (= p * 2^32)
+  float inv_keep;                  // 1 / (1 - p)
+};
+int launch_lora_seed_bump(unsigned long long* seed, cudaStream_t st);
+// u_d[M][64] (16-bit, columns >= 3r zero) = 1/(1-p) (keep_p o x) A_p^T for the three projections
+int launch_lora_down_dropout(const void* x16, const void* acat16, void* ud16, long M, int r, int bf16, const LoraDropSpec& d,
+                             cudaStream_t st);
+// dxe[M][320] (columns [0,256) dx, [256,256+3r) v): dx += s/(1-p) sum_p keep_p o (v_p A_p), in place
+int launch_lora_dropout_bwd(void* dxe16, const void* acat16, long M, int r, float scaling, int bf16, const LoraDropSpec& d,
+                            cudaStream_t st);
+// replaces the x^T v partials of lora_wgrad_launch_partial (same plan, run after it) by the masked ones
+int lora_wgrad_launch_a_dropout(const void* plan, const void* x16, const void* v16, long ld_v, const LoraDropSpec& d,
+                                cudaStream_t st);
+
 // ---- optim.cu ------------------------------------------------------------------------------
 // Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).
 int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cudaStream_t st);

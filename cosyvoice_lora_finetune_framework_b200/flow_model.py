@@ -306,6 +306,8 @@ class ConditionalCFM(nn.Module):
         if S > 1:
             if upstream:
                 raise NotImplementedError("num_streams > 1 does not produce dL/d(mu, spks, cond); use num_streams = 1")
+            if ne._drop_active != 0.0:
+                raise NotImplementedError("num_streams > 1 does not support lora_dropout > 0; use num_streams = 1")
             while len(self._streams) < S - 1:
                 self._streams.append(torch.cuda.Stream(device=dev))
             loss, y = _CFMLossShardedFn.apply(ne.shard_handles(S), self._streams[: S - 1], f(x1), f(mask).reshape(b, T),

@@ -153,6 +153,15 @@ typedef struct cvflow_input_grads {
 CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void* dpred16, float grad_scale,
                                                 const float* grad_scale_dev, const cvflow_input_grads* grads,
                                                 void* stream);
+/* lora_dropout of the q/k/v LoRA branches (reference lora.py:66-74: y = W x + s B (A drop(x)), one independent
+ * nn.Dropout per LoRALinear). p = 0 (default): B A is folded into the GEMM operand. p > 0: training forwards apply an
+ * independent keep mask per (attention block, projection, token, feature), drawn from a counter-based hash of `seed`
+ * (advanced on the device at every training forward; the backward recomputes the same masks), scaled by 1/(1-p).
+ * Needs the extra operand images "<block>.w0d" ([1536][320] = [W0 | s B_cat]) and "<block>.w0t_ext" ([320][1536] =
+ * [W0^T ; B_blk]) to be bound and kept current by the caller. debug_mask (optional, else NULL): explicit keep masks
+ * [n_blocks][3][debug_rows][256] bytes (1 = keep) with debug_rows = B*T, for parity tests against the reference. */
+CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, uint64_t seed, const uint8_t* debug_mask,
+                                       int64_t debug_rows);
 CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
 /* Measurement aid (bench.py roofline): when on, CUDA events bracket every tensor-core launch on
  * the launching stream. cvflow_profile_read synchronises the stream and sums per class

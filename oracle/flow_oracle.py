@@ -58,11 +58,14 @@ def sinusoidal_embedding(t: Tensor, dim: int = 320, scale: float = 1000.0) -> Te
 
 
 def _linear(P, prefix: str, x: Tensor, lora_scaling: Dict[str, float]) -> Tensor:
-    """nn.Linear or LoRALinear (lora.py:64-76; dropout is identity in the parity runs)."""
+    """nn.Linear or LoRALinear (lora.py:64-76). nn.Dropout's draw on the LoRA input is supplied by the caller as an
+    optional `<prefix>.lora_dropout_mask` entry of P (keep / (1 - p), broadcastable to x); absent = no dropout."""
     if prefix + ".lora_A" in P:
         w, b = P[prefix + ".original_layer.weight"], P.get(prefix + ".original_layer.bias")
         y = F.linear(x, w, b)
-        low = F.linear(F.linear(x, P[prefix + ".lora_A"]), P[prefix + ".lora_B"])
+        dm = P.get(prefix + ".lora_dropout_mask")
+        xl = x * dm if dm is not None else x
+        low = F.linear(F.linear(xl, P[prefix + ".lora_A"]), P[prefix + ".lora_B"])
         return y + low * lora_scaling[prefix]
     return F.linear(x, P[prefix + ".weight"], P.get(prefix + ".bias"))
 

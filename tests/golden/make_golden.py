@@ -112,6 +112,59 @@ def input_grad_case(name, src):
           float(cond.grad.norm()))
 
 
+def dropout_masks(n_tbs, rows, p, seed):
+    """Explicit keep masks [n_tbs][3][rows][256] (uint8) shared by the reference run, the oracle and the CUDA path."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(n_tbs, 3, rows, 256, generator=g) >= p).to(torch.uint8)
+
+
+def attention_blocks(est, prefix=""):
+    """(state-dict prefix, module) of every BasicTransformerBlock in execution order (= the CUDA path's block index)."""
+    out = []
+    groups = ([("down_blocks.%d" % i, b) for i, b in enumerate(est.down_blocks)] +
+              [("mid_blocks.%d" % i, b) for i, b in enumerate(est.mid_blocks)] +
+              [("up_blocks.%d" % i, b) for i, b in enumerate(est.up_blocks)])
+    for name, stage in groups:
+        for j, tb in enumerate(stage[1]):
+            out.append(("%s%s.1.%d" % (prefix, name, j), tb))
+    return out
+
+
+class FixedDropout(torch.nn.Module):
+    """Stands in for a LoRALinear's nn.Dropout: multiplies by a preset keep mask / (1 - p)."""
+
+    def __init__(self, keep, p):
+        super().__init__()
+        self.keep, self.p = keep, p
+
+    def forward(self, x):
+        b, l, c = x.shape
+        return x * (self.keep[: b * l].view(b, l, c).to(x.dtype) / (1.0 - self.p))
+
+
+def dropout_case(name, src, p, mask_seed):
+    """compute_loss + backward of the REAL reference with lora_dropout = p on the estimator's q/k/v LoRA layers, the
+    dropout draws replaced by preset masks (one independent mask per LoRALinear, like nn.Dropout)."""
+    fx = torch.load(os.path.join(HERE, src + ".pt"), map_location="cpu", weights_only=False)
+    cfm, sd, _ = build_ref(fx["n_blocks"], fx["n_mid"], targets=('to_q', 'to_k', 'to_v'))
+    cfm.train()
+    B, _, T = fx["x1"].shape
+    blocks = attention_blocks(cfm.estimator)
+    keep = dropout_masks(len(blocks), B * T, p, mask_seed)
+    for i, (_, tb) in enumerate(blocks):
+        for j, pn in enumerate(("to_q", "to_k", "to_v")):
+            getattr(tb.attn1, pn).lora_dropout = FixedDropout(keep[i, j], p)
+    step_seed = {"train_tiny": 7, "train_tiny_prompt": 8, "train_c1": 7, "train_c1_prompt": 7}[src]
+    torch.manual_seed(step_seed)
+    loss, _ = cfm.compute_loss(fx["x1"], fx["mask"], fx["mu"], fx["spks"], cond=fx["cond"], prompt_lens=fx["prompt_lens"])
+    loss.backward()
+    grads = {k: q.grad.clone() for k, q in cfm.estimator.named_parameters() if q.grad is not None}
+    torch.save(dict(kind="lora_dropout", src=src, p=p, mask_seed=mask_seed, n_tbs=len(blocks), rows=B * T,
+                    keep_sum=int(keep.sum()), loss=loss.detach(), grads=grads), os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "(no dropout: %g)" % float(fx["loss"]), "ngrads", len(grads), "keep rate",
+          float(keep.float().mean()))
+
+
 FLOW_TINY = dict(encoder_num_blocks=2, decoder_n_blocks=1, decoder_num_mid_blocks=1)
 FLOW_TARGETS = ['to_q', 'to_k', 'to_v', 'linear_q', 'linear_k', 'linear_v', 'w_1', 'w_2']     # config.py:207-216
 
@@ -231,6 +284,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["inputgrads"]:      # added later: leaves the other fixtures untouched
         input_grad_case("inputgrads_tiny_prompt", "train_tiny_prompt")
         input_grad_case("inputgrads_c1", "train_c1")
+        sys.exit(0)
+    if sys.argv[1:] == ["dropout"]:
+        dropout_case("dropout_tiny_prompt", "train_tiny_prompt", 0.25, 31)
         sys.exit(0)
     if sys.argv[1:] == ["flowmodel"]:
         flow_model_case("flowmodel_tiny", 21, 3, 5)

@@ -77,3 +77,26 @@ def test_input_gradients_match_reference(name):
     # masked frames and CFG-dropped samples get exactly zero
     pad = fx["mask"].expand_as(mu) == 0
     assert float(ig["dmu"][pad].abs().sum()) == 0.0 and float(mu.grad[pad].abs().sum()) == 0.0
+
+
+def test_lora_dropout_matches_reference():
+    """lora_dropout > 0 (lora.py:66-74) with the nn.Dropout draws replaced by preset masks in the reference run."""
+    from tests.helpers import attention_block_prefixes, dropout_masks, oracle_dropout_entries
+    dg = load_golden("dropout_tiny_prompt")
+    fx = load_golden(dg["src"])
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    B, _, T = fx["x1"].shape
+    keep = dropout_masks(dg["n_tbs"], dg["rows"], dg["p"], dg["mask_seed"])
+    assert int(keep.sum()) == dg["keep_sum"]
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    P.update(oracle_dropout_entries(keep, dg["p"], attention_block_prefixes(fx["n_blocks"], fx["n_mid"]), B, T))
+    loss, _, _ = O.cfm_compute_loss(P, fx["x1"], fx["mask"], fx["mu"], fx["spks"], fx["cond"], fx["prompt_lens"],
+                                    fx["t_rand"], fx["z"], fx["cfg_rand"], lora_scaling=lora_scaling_of(sd))
+    assert abs(float(loss) - float(dg["loss"])) <= 1e-5 * abs(float(dg["loss"]))
+    loss.backward()
+    for k, g in dg["grads"].items():
+        assert torch.allclose(P[k].grad, g, atol=1e-6 + 1e-3 * float(g.abs().max()), rtol=1e-3), k
+    # the masks matter: the no-dropout gradients of the same step are far away
+    far = sum((fx["grads"][k] - g).double().pow(2).sum() for k, g in dg["grads"].items())
+    den = sum(g.double().pow(2).sum() for g in dg["grads"].values())
+    assert float((far / den).sqrt()) > 0.1
