@@ -42,12 +42,13 @@ def parse():
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout-leg", action="store_true")
     return ap.parse_args()
 
 
 def workload_config(a, world):
     return {"workload": "configs[2]: CosyVoice-300M flow estimator (16 resnets, 64 transformer blocks), LoRA r=8 "
-                        "alpha=16 on attn1 to_q/to_k/to_v, batch %d x %d frames per GPU, ragged lengths in "
+                        "alpha=16 lora_dropout=0 on attn1 to_q/to_k/to_v, batch %d x %d frames per GPU, ragged lengths in "
                         "(0.6T, T]" % (a.batch, a.frames),
             "global_batch": a.batch * world, "frames": a.frames, "parallelism": "dp%d" % world,
             "launch": "whole optimiser step replayed as one CUDA graph (PDL edges between kernels); batch shards on %d concurrent streams" % a.streams,
@@ -118,13 +119,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_model(a, device, dtype):
+def build_model(a, device, dtype, lora_dropout=0.0):
     from cosyvoice_lora_finetune_framework_b200 import lora, modules, utils
     from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
     utils.set_all_random_seed(1234)
     est = modules.ConditionalDecoder(in_channels=320, out_channels=80, channels=(256, 256), dropout=0.0,
                                      attention_head_dim=64, n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn='gelu')
-    stats = lora.apply_lora_to_model(est, r=8, lora_alpha=16, lora_dropout=0.0,
+    stats = lora.apply_lora_to_model(est, r=8, lora_alpha=16, lora_dropout=lora_dropout,
                                      target_modules=['to_q', 'to_k', 'to_v', 'to_out'])
     est = est.to(device).train()
     est.cvflow_dtype = dtype
@@ -383,6 +384,24 @@ def run_cvflow(a):
                          "target_frames_per_s": (Ti - P_) / (ms_inf / 1e3)}
         est.train()
 
+    # ---- the same step with the reference's default lora_dropout = 0.05 (un-folded LoRA branch; informational) ----
+    dropout_leg = None
+    if rank == 0 and world == 1 and use_graph and not a.no_dropout_leg:
+        try:
+            cfm3, _, _ = build_model(a, device, dtype, lora_dropout=0.05)
+            tr3 = FlowLoRATrainer(cfm3, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0)
+            step3 = lambda: tr3.train_step_graphed(batch["x1"], batch["mask"], batch["mu"], batch["spks"], batch["cond"])
+            for _ in range(W):
+                step3()
+            ms3 = timed(step3, K)
+            dropout_leg = {"lora_dropout": 0.05, "ms_per_step": ms3 / K, "value": B * T * K / (ms3 / 1e3), "unit": UNIT,
+                           "note": "functional path (CUDA-core low-rank branch around the same GEMMs), not yet tuned"}
+            del tr3, cfm3
+            torch.cuda.empty_cache()
+        except Exception as e:      # informational leg: never lose the headline line to it
+            dropout_leg = {"lora_dropout": 0.05, "error": repr(e)[:200]}
+        _trace("dropout leg done")
+
     # ---- CPU baseline: the reference algorithm on this box's host cores ---------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -398,7 +417,7 @@ def run_cvflow(a):
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "ms_per_step": ms_e2e / K},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
-               "inference": inference, "valid_frames_per_step_rank0": int(lens.sum()),
+               "inference": inference, "lora_dropout_leg": dropout_leg, "valid_frames_per_step_rank0": int(lens.sum()),
                "lora": {"replaced_layers": stats["replaced_layers"], "lora_params": stats["lora_params"]}}
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:

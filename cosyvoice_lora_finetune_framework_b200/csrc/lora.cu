@@ -3,8 +3,8 @@
 // Forward / dgrad use the merged operand W_eff = W + (alpha/r) B A, rebuilt from the fp32 master
 // copies by one batched launch per step (both the [N][K] image for y = x W_eff^T and the [K][N]
 // image for dx = dy W_eff), so the tcgen05 GEMM sees a single 16-bit weight tile stream and the
-// low-rank update costs no extra activation traffic. (Valid for lora_dropout == 0, which is what
-// the parity and benchmark runs use; the host refuses dropout > 0 on this path.)
+// low-rank update costs no extra activation traffic. (Valid for lora_dropout == 0 and in eval();
+// with lora_dropout > 0 in training the un-folded branch of the second half of this file runs.)
 // The wgrad kernel produces dA = s (dY B)^T x and dB = s dY^T (x A^T) per projection with a
 // deterministic two-stage reduction (no atomics).
 #include "kernels.h"

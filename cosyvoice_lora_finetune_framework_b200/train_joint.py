@@ -89,11 +89,10 @@ def main(argv=None):
     lr = args.lr or cfg.get('learning_rate', 5e-5)
     accumulate = cfg.get('accumulate_grad_batches', 8)
 
-    # flow LoRA on the reference's target list (config.py:207-216): the estimator's attn1 q/k/v run on the CUDA path,
-    # the Conformer encoder's linear_q/k/v, w_1, w_2 are host-side modules trained through dL/dmu of the estimator
-    # backward. lora_dropout is forced to 0: the CUDA path folds B A into the GEMM operand.
+    # flow LoRA exactly as configured by the reference (config.py:207-216: r, alpha, lora_dropout, target list): the
+    # estimator's attn1 q/k/v run on the CUDA path (dropout included), the Conformer encoder's linear_q/k/v, w_1, w_2
+    # are host-side modules trained through dL/dmu of the estimator backward.
     flow_lora = dict(cfg.get('flow_lora', {}))
-    flow_lora['lora_dropout'] = 0.0
     model = build_joint_model(PRETRAINED_MODEL_DIR, str(device), 'flow_only', None, flow_lora)
     model.flow.decoder.estimator.cvflow_dtype = torch.float16 if args.dtype == 'fp16' else torch.bfloat16
     upstream = [p for n, p in model.flow.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]

@@ -112,3 +112,6 @@ def test_lora_dropout_training_step_r16_bf16():
     assert all(np.isfinite(losses)) and int(tr.found_inf.item()) == 0
     assert not torch.equal(tr.ne.w0d[:, :, 256:], w0[:, :, 256:])           # s B_cat refreshed after the step
     assert torch.equal(tr.ne.w0d[:, :, :256], w0[:, :, :256])              # frozen W0 untouched
+    # the whole step, mask hash and operand refresh included, is CUDA-graph capturable; masks advance per replay
+    g_losses = [float(tr.train_step_graphed(c("x1"), c("mask"), c("mu"), c("spks"), c("cond"))) for _ in range(3)]
+    assert all(np.isfinite(g_losses)) and int(tr.found_inf.item()) == 0
