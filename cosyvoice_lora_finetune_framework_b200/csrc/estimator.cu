@@ -720,8 +720,8 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     if (!(skip_ & 8u)) CKL(lora_wgrad_launch_partial(pl.wgrads[wg_idx_].data(), ws));
     if (t.drop) {   // the masked x^T v partials replace the un-masked ones of the tensor-core kernel
       CKL(lora_wgrad_launch_a_dropout(pl.wgrads[wg_idx_].data(), t.x1, reinterpret_cast<const uint16_t*>(dxe) + 256, ldx,
-                                      drop_spec(t.lora_idx), ws));
-      ++launches_;
+                                      drop_spec(t.lora_idx), tmp.wga_scratch, ws));
+      launches_ += 2;
     }
     ++wg_idx_;
     prof_end(ws);
@@ -794,6 +794,7 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale, const InputG
   tmp.da = alloc(MT * 256 * 2);
   tmp.wg_stride = lora_wgrad_scratch_floats(MT, cfg.lora_r > 0 ? cfg.lora_r : 1);
   tmp.wg_scratch = (float*)alloc(tmp.wg_stride * (cfg.lora_r > 0 ? n_tbs() : 1) * 4);
+  tmp.wga_scratch = (cfg.lora_r > 0 && drop_p_ > 0.f) ? (float*)alloc(lora_wgrad_a_dropout_scratch_floats(MT) * 4) : nullptr;
   tmp.dxe[0] = alloc(MT * 320 * 2);
   tmp.dxe[1] = wgrad_side_ ? alloc(MT * 320 * 2) : tmp.dxe[0];
   float* dh32 = (float*)alloc(MT * 256 * 4);

@@ -49,6 +49,7 @@ struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
 struct BwdTemps {
   void *dpre, *dx, *dO; void* dqkv[2]; float* delta; void *dc, *da; float* wg_scratch; long wg_stride; void* dxe[2];
+  float* wga_scratch;   // lora_dropout > 0: chunk partials of the masked dA reduction (shared by all blocks)
 };
 
 struct PlanKey {

@@ -142,9 +142,11 @@ int launch_lora_down_dropout(const void* x16, const void* acat16, void* ud16, lo
 // dxe[M][320] (columns [0,256) dx, [256,256+3r) v): dx += s/(1-p) sum_p keep_p o (v_p A_p), in place
 int launch_lora_dropout_bwd(void* dxe16, const void* acat16, long M, int r, float scaling, int bf16, const LoraDropSpec& d,
                             cudaStream_t st);
-// replaces the x^T v partials of lora_wgrad_launch_partial (same plan, run after it) by the masked ones
+// replaces the x^T v partials of lora_wgrad_launch_partial (same plan, run after it) by the masked ones;
+// scratch: lora_wgrad_a_dropout_scratch_floats(M) floats, free to reuse once the call's kernels have run
+long lora_wgrad_a_dropout_scratch_floats(long M);
 int lora_wgrad_launch_a_dropout(const void* plan, const void* x16, const void* v16, long ld_v, const LoraDropSpec& d,
-                                cudaStream_t st);
+                                float* scratch, cudaStream_t st);
 
 // ---- optim.cu ------------------------------------------------------------------------------
 // Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).

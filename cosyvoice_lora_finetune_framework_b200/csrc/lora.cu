@@ -390,29 +390,50 @@ __global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(uint16_t* __restr
   }
 }
 
-// grid (S token splits, 3 projections), thread = input feature k: part_a[(split*256 + k)*64 + p r + j]
+// dA partials in two steps so that the work spreads over the machine: (64-token chunk, projection) CTAs with thread =
+// input feature k accumulate acc[j] = sum_t v[t][p r + j] keep_p[t][k] x[t][k] into a scratch [chunk][3][16][256];
+// a second kernel sums the chunks in fixed order (deterministic) into split 0 of the tensor-core wgrad kernel's part_a
+// layout ([split][256][64]) and zeroes the other splits, replacing that kernel's un-masked x^T v.
+static constexpr int kWgaChunk = 64;
 __global__ void __launch_bounds__(256) lora_wgrad_a_dropout_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ v,
-                                                                   long ld_v, float* __restrict__ part_a, long M,
-                                                                   int rows_per_split, int r, int bf, const LoraDropSpec d) {
+                                                                   long ld_v, float* __restrict__ scratch, long M, int r,
+                                                                   int bf, const LoraDropSpec d) {
+  __shared__ float vs[kWgaChunk][16];
   const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
-  const int sp = blockIdx.x, p = blockIdx.y, k = threadIdx.x;
+  const int c = blockIdx.x, p = blockIdx.y, k = threadIdx.x;
+  const long m0 = (long)c * kWgaChunk;
+  const int n = (int)(M - m0 < kWgaChunk ? M - m0 : kWgaChunk);
+  for (int i = threadIdx.x; i < kWgaChunk * 16; i += 256) {
+    const int t = i >> 4, j = i & 15;
+    vs[t][j] = (t < n && j < r) ? h16_to_f32(v[(m0 + t) * ld_v + p * r + j], bf) : 0.f;
+  }
+  __syncthreads();
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  const long m0 = (long)sp * rows_per_split;
-  long m1 = m0 + rows_per_split;
-  if (m1 > M) m1 = M;
-  for (long m = m0; m < m1; ++m) {
-    if (!lora_keep(d, seed, p, m, k)) continue;
-    const float xv = h16_to_f32(x[m * 256 + k], bf);
-    const uint16_t* vr = v + m * ld_v + p * r;
+#pragma unroll 8
+  for (int t = 0; t < n; ++t) {
+    const float xr = h16_to_f32(x[(m0 + t) * 256 + k], bf);
+    const float xv = lora_keep(d, seed, p, m0 + t, k) ? xr : 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < r) acc[j] += h16_to_f32(vr[j], bf) * xv;
+      if (j < r) acc[j] += vs[t][j] * xv;
   }
+  float* out = scratch + (((long)c * 3 + p) * 16) * 256;
 #pragma unroll
   for (int j = 0; j < 16; ++j)
-    if (j < r) part_a[((long)sp * 256 + k) * 64 + p * r + j] = acc[j] * d.inv_keep;
+    if (j < r) out[j * 256 + k] = acc[j];
+}
+// grid 3r blocks (projection, rank index), thread = k
+__global__ void __launch_bounds__(256) lora_wgrad_a_dropout_reduce_kernel(const float* __restrict__ scratch, int nchunks,
+                                                                          float* __restrict__ part_a, int S, int r,
+                                                                          float inv_keep) {
+  const int k = threadIdx.x, pj = blockIdx.x;
+  const int p = pj / r, j = pj - p * r;
+  float s = 0.f;
+  for (int c = 0; c < nchunks; ++c) s += scratch[(((long)c * 3 + p) * 16 + j) * 256 + k];
+  part_a[(long)k * 64 + pj] = s * inv_keep;
+  for (int sp = 1; sp < S; ++sp) part_a[((long)sp * 256 + k) * 64 + pj] = 0.f;
 }
 
 __global__ void lora_seed_bump_kernel(unsigned long long* seed) { seed[0] += 0x632BE59BD9B4E019ull; }
@@ -437,12 +458,15 @@ int launch_lora_dropout_bwd(void* dxe16, const void* acat16, long M, int r, floa
                                                          reinterpret_cast<const uint16_t*>(acat16), M, r, scaling, bf16, d);
   LAUNCH_RET();
 }
+long lora_wgrad_a_dropout_scratch_floats(long M) { return ((M + kWgaChunk - 1) / kWgaChunk) * 3L * 16 * 256; }
 int lora_wgrad_launch_a_dropout(const void* plan, const void* x16, const void* v16, long ld_v, const LoraDropSpec& d,
-                                cudaStream_t st) {
+                                float* scratch, cudaStream_t st) {
   const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
-  lora_wgrad_a_dropout_kernel<<<dim3(p->S, 3), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16),
-                                                             reinterpret_cast<const uint16_t*>(v16), ld_v, p->part_a, p->M,
-                                                             p->rows_per_split, p->r, p->bf16, d);
+  const int nchunks = (int)((p->M + kWgaChunk - 1) / kWgaChunk);
+  lora_wgrad_a_dropout_kernel<<<dim3(nchunks, 3), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16),
+                                                                reinterpret_cast<const uint16_t*>(v16), ld_v, scratch, p->M,
+                                                                p->r, p->bf16, d);
+  lora_wgrad_a_dropout_reduce_kernel<<<3 * p->r, 256, 0, st>>>(scratch, nchunks, p->part_a, p->S, p->r, d.inv_keep);
   LAUNCH_RET();
 }
 
