@@ -129,5 +129,5 @@ def test_graphed_step_matches_eager_step():
     # the graphed trainer ran 2 extra warm-up steps before capture, so compare trajectories loosely:
     # both descend a stochastic objective; parameters must have moved by a similar amount
     assert s1 == s0 + 2
-    assert 0.2 < float((p1 - results[0][1]).norm()) / (float(p0.norm()) + 1e-9) < 2.0 or True
+    assert torch.isfinite(p1).all() and float((p1 - p0).abs().max()) > 0
     assert float(p1.abs().sum()) > 0
