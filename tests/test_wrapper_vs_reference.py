@@ -80,3 +80,40 @@ def test_wrapper_matches_reference():
         sys.modules.update(saved)
         from cosyvoice_lora_finetune_framework_b200 import flow_model as O2
         O2.NO_PROMPT_TRAINING_CONFIG.update(enabled=False, mode='full')
+
+
+def test_lora_inject_and_merge_match_reference_on_the_flow_model():
+    """apply_lora_to_model / get_lora_state_dict / get_merged_state_dict on the whole flow model with the reference's
+    flow_lora target list: same replaced layers, same seeded LoRA init, same merged keys IN THE SAME ORDER, same values."""
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.pop(k) for k in ("flow_model", "utils", "config", "modules", "lora") if k in sys.modules}
+    sys.path.insert(0, REF)
+    try:
+        import flow_model as R
+        import lora as RL
+        import utils as RU
+        from cosyvoice_lora_finetune_framework_b200 import flow_model as O
+        from cosyvoice_lora_finetune_framework_b200 import lora as OL
+        arch = dict(encoder_num_blocks=2, decoder_n_blocks=1, decoder_num_mid_blocks=2)
+        targets = ['to_q', 'to_k', 'to_v', 'linear_q', 'linear_k', 'linear_v', 'w_1', 'w_2']
+        RU.set_all_random_seed(17)
+        a = R.build_flow_model(None, 'cpu', **arch)
+        sa = RL.apply_lora_to_model(a, r=16, lora_alpha=32, lora_dropout=0.05, target_modules=targets)
+        RU.set_all_random_seed(17)
+        b = O.build_flow_model(None, 'cpu', **arch)
+        sb = OL.apply_lora_to_model(b, r=16, lora_alpha=32, lora_dropout=0.05, target_modules=targets)
+        assert sa == sb, (sa, sb)
+        la, lb = RL.get_lora_state_dict(a), OL.get_lora_state_dict(b)
+        assert list(la) == list(lb) and all(torch.equal(la[k], lb[k]) for k in la)
+        ma, mb = RL.get_merged_state_dict(a), OL.get_merged_state_dict(b)
+        assert list(ma.keys()) == list(mb.keys())
+        assert all(torch.equal(ma[k], mb[k]) for k in ma)
+        # merging mutates the wrapped weights in place in both implementations (reference lora.py:264-279)
+        wa = a.decoder.estimator.mid_blocks[0][1][0].attn1.to_q.original_layer.weight
+        wb = b.decoder.estimator.mid_blocks[0][1][0].attn1.to_q.original_layer.weight
+        assert torch.equal(wa, wb) and torch.equal(wa, ma['decoder.estimator.mid_blocks.0.1.0.attn1.to_q.weight'])
+    finally:
+        sys.path.remove(REF)
+        for k in ("flow_model", "utils", "config", "modules", "lora"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
