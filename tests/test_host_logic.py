@@ -116,3 +116,25 @@ def test_isolation_mask_and_schedule():
     utils.set_all_random_seed(5)
     assert torch.equal(a, torch.rand(3))
     assert utils.pad_list([torch.ones(2), torch.ones(3)], 0).tolist() == [[1, 1, 0], [1, 1, 1]]
+
+
+def test_cabi_reports_argument_errors_without_a_gpu():
+    """Entry points validate their arguments before touching the device: int status + cvflow_last_error text, no
+    exception, no exit (SURVEY section 8b 'Errors'). No compute is launched here."""
+    from cosyvoice_lora_finetune_framework_b200 import _estimator as E
+    L = E._lib()
+    null = ctypes.c_void_p(None)
+    cases = [
+        (lambda: L.cvflow_estimator_forward(null, None, null), b"cvflow_estimator_forward"),
+        (lambda: L.cvflow_estimator_backward(null, null, 1.0, null, null), b"cvflow_estimator_backward"),
+        (lambda: L.cvflow_estimator_backward_inputs(null, null, 1.0, null, None, null), b"cvflow_estimator_backward_inputs"),
+        (lambda: L.cvflow_set_lora_dropout(null, 0.1, ctypes.c_uint64(1), null, 0), b"cvflow_set_lora_dropout"),
+        (lambda: L.cvflow_lora_refresh(null, null), b"cvflow_lora_refresh"),
+        (lambda: L.cvflow_set_workspace(null, null, 0), b"cvflow_set_workspace"),
+        (lambda: L.cvflow_cfm_prep(null, null, null, null, 1, 8, 1e-6, null), b"cvflow_cfm_prep"),
+    ]
+    for call, tag in cases:
+        rc = call()
+        assert rc < 0, tag
+        assert tag in L.cvflow_last_error(), (tag, L.cvflow_last_error())
+    assert L.cvflow_workspace_bytes(null, 2, 16, 1) < 0
