@@ -1,7 +1,10 @@
 """Generate golden vectors by running the REAL reference implementation (read-only checkout at
 /root/reference) on seeded synthetic weights and inputs. Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py               # train_*, estimator_*, euler_* (the original set)
+    python tests/golden/make_golden.py inputgrads    # inputgrads_*: dL/dmu, dL/dspks, dL/dcond of compute_loss
+    python tests/golden/make_golden.py flowmodel     # flowmodel_tiny: MaskedDiffWithXvec.forward + backward, encoder LoRA
+    python tests/golden/make_golden.py dropout       # dropout_tiny_prompt: lora_dropout > 0 with preset keep masks
 
 The GPU box has no /root/reference; tests read the committed .pt files. Weights are not stored:
 they are a pure function of (parameter name, shape, seed) - oracle.flow_oracle.synth_tensor - and
