@@ -117,3 +117,57 @@ def test_lora_inject_and_merge_match_reference_on_the_flow_model():
         for k in ("flow_model", "utils", "config", "modules", "lora"):
             sys.modules.pop(k, None)
         sys.modules.update(saved)
+
+
+def test_public_signatures_match_reference():
+    """The drop-in surface of SURVEY section 8b: same parameter names, kinds, order and defaults as the reference
+    for every class / function on the path (path-valued defaults excepted: they follow the install location)."""
+    import inspect
+    sys.dont_write_bytecode = True
+    names = ("flow_model", "utils", "config", "modules", "lora", "llm_flow_model", "merge_joint_weights", "dataset")
+    saved = {k: sys.modules.pop(k) for k in names if k in sys.modules}
+    sys.path.insert(0, REF)
+    try:
+        import flow_model as RF
+        import llm_flow_model as RJ
+        import lora as RL
+        import merge_joint_weights as RMJ
+        import modules as RM
+        import utils as RU
+        from cosyvoice_lora_finetune_framework_b200 import flow_model as OF
+        from cosyvoice_lora_finetune_framework_b200 import llm_flow_model as OJ
+        from cosyvoice_lora_finetune_framework_b200 import lora as OL
+        from cosyvoice_lora_finetune_framework_b200 import merge_joint_weights as OMJ
+        from cosyvoice_lora_finetune_framework_b200 import modules as OM
+        from cosyvoice_lora_finetune_framework_b200 import utils as OU
+        table = [
+            (RF.ConditionalCFM, OF.ConditionalCFM, ["__init__", "compute_loss", "forward", "solve_euler"]),
+            (RM.ConditionalDecoder, OM.ConditionalDecoder, ["__init__", "forward"]),
+            (RF.MaskedDiffWithXvec, OF.MaskedDiffWithXvec, ["__init__", "forward", "inference", "inference_like_training",
+                                                           "normalize_mel", "denormalize_mel"]),
+            (RL.LoRALinear, OL.LoRALinear, ["__init__", "forward"]),
+            (RJ.JointLLMFlowModel, OJ.JointLLMFlowModel, ["__init__", "forward"]),
+            (RF, OF, ["build_flow_model"]),
+            (RL, OL, ["apply_lora_to_model", "get_lora_state_dict", "save_lora_weights", "load_lora_weights",
+                      "merge_lora_weights", "get_merged_state_dict"]),
+            (RU, OU, ["make_pad_mask", "mask_to_bias", "set_all_random_seed"]),
+            (RJ, OJ, ["build_joint_model", "get_joint_merged_state_dict"]),
+            (RMJ, OMJ, ["find_latest_joint_checkpoint", "merge_flow_from_checkpoint", "merge_llm_from_checkpoint",
+                        "merge_both_from_checkpoint"]),
+        ]
+
+        def sig(f):
+            return [(n, p.kind.name, None if isinstance(p.default, str) and os.sep in p.default else p.default)
+                    for n, p in inspect.signature(f).parameters.items()]
+
+        checked = 0
+        for ref_owner, our_owner, attrs in table:
+            for a in attrs:
+                assert sig(getattr(ref_owner, a)) == sig(getattr(our_owner, a)), (getattr(ref_owner, "__name__", ref_owner), a)
+                checked += 1
+        assert checked == 32
+    finally:
+        sys.path.remove(REF)
+        for k in names:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
