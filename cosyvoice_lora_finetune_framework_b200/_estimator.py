@@ -52,6 +52,8 @@ def _lib():
         L.cvflow_estimator_backward.argtypes = [vp, vp, f, vp, vp]
         L.cvflow_estimator_backward_inputs.argtypes = [vp, vp, f, vp, C.POINTER(InputGrads), vp]
         L.cvflow_set_lora_dropout.argtypes = [vp, f, C.c_uint64, vp, i64]
+        L.cvflow_lora_dropout_seed.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.cvflow_optim_advance.argtypes = [vp, vp, vp, vp, f, f, i32, i32, f, f, f, vp]
         L.cvflow_launch_count.argtypes = [vp]
         L.cvflow_launch_count.restype = i64
         L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
@@ -403,6 +405,20 @@ class NativeEstimator:
                                                    int(mk.shape[2]) if mk is not None else 0), "cvflow_set_lora_dropout")
             self._drop_active = p
             self.ws_key = None       # the training workspace holds the u_d stashes only when dropout is on
+
+    def dropout_seed_snapshot(self):
+        """Current device-side seeds of the mask hash (this handle and its stream replicas)."""
+        out = []
+        for h in [self] + self.replicas:
+            v = C.c_uint64(0)
+            N.check(self.L.cvflow_lora_dropout_seed(h.handle, C.byref(v), None), "cvflow_lora_dropout_seed")
+            out.append(int(v.value))
+        return out
+
+    def dropout_seed_restore(self, seeds):
+        for h, s in zip([self] + self.replicas, seeds):
+            v = C.c_uint64(int(s))
+            N.check(self.L.cvflow_lora_dropout_seed(h.handle, None, C.byref(v)), "cvflow_lora_dropout_seed")
 
     def _version(self):
         try:

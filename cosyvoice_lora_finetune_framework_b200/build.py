@@ -1,7 +1,11 @@
 """Build libcvflow.so (hand-written sm_100a CUDA behind the C ABI of include/cvflow.h) in-tree.
 
 nvcc cross-compiles without a GPU. Objects are rebuilt only when a source or header is newer.
-Usage: python -m cosyvoice_lora_finetune_framework_b200.build [--force]
+Usage: python -m cosyvoice_lora_finetune_framework_b200.build [--force] [--profiling]
+
+--profiling additionally builds libcvflow_prof.so (-DCVFLOW_PROFILING_BUILD: honours CVFLOW_SKIP, which drops kernel
+classes from the step so that profiles/prof_marginals.py can time their in-graph share; never loaded by the product,
+select it explicitly with CVFLOW_LIB_PATH).
 """
 import os
 import subprocess
@@ -27,7 +31,10 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, profiling: bool = False) -> str:
+    OBJ = os.path.join(CSRC, "build_prof" if profiling else "build")
+    LIB = os.path.join(HERE, "libcvflow_prof.so" if profiling else "libcvflow.so")
+    FLAGS = globals()["FLAGS"] + (["-DCVFLOW_PROFILING_BUILD"] if profiling else [])
     os.makedirs(OBJ, exist_ok=True)
     hm = _headers_mtime()
     jobs = []
@@ -63,3 +70,5 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    if "--profiling" in sys.argv:
+        build(force="--force" in sys.argv, profiling=True)

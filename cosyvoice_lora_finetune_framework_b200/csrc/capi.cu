@@ -43,6 +43,7 @@ extern "C" CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* d, void* stream) {
   a.col_off = d->col_off; a.n_valid = d->n_valid; a.alpha = d->alpha; a.act = d->act;
   a.bias = d->bias; a.aux_out = d->aux_out; a.mul_src = d->mul_src; a.ld_aux = d->ld_aux;
   a.rowmask = d->rowmask; a.resid = d->resid; a.ldr = d->ldr; a.dbg = (long long*)d->dbg;
+  a.gn_part = d->gn_part;
   GemmParams p;
   if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return CVFLOW_ERR_ARG;
   int r = gemm_launch(p, (cudaStream_t)stream);
@@ -134,6 +135,13 @@ extern "C" CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, 
   if (!h) { set_error("cvflow_set_lora_dropout: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->set_lora_dropout(p, (unsigned long long)seed, debug_mask, (long)debug_rows) ? CVFLOW_ERR_ARG : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_lora_dropout_seed(cvflow_estimator* h, uint64_t* out, const uint64_t* in) {
+  if (!h) { set_error("cvflow_lora_dropout_seed: null handle"); return CVFLOW_ERR_ARG; }
+  unsigned long long o = 0ull, i = in ? (unsigned long long)*in : 0ull;
+  if (h->e->lora_dropout_seed(out ? &o : nullptr, in ? &i : nullptr)) return CVFLOW_ERR_CUDA;
+  if (out) *out = (uint64_t)o;
+  return CVFLOW_OK;
+}
 extern "C" CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h) { return h ? h->e->launches() : 0; }
 
 #define RET_LAUNCH(call, what)                                                                       \
@@ -172,6 +180,15 @@ extern "C" CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, 
   if (!p || !g || !m || !v || !sumsq) { set_error("cvflow_adamw_step: null argument"); return CVFLOW_ERR_ARG; }
   RET_LAUNCH(launch_adamw(p, g, m, v, (long)n, sumsq, grad_unscale, max_norm, lr, beta1, beta2, eps, weight_decay, step,
                           found_inf, hyper_dev, (cudaStream_t)stream), "cvflow_adamw_step");
+}
+
+extern "C" CVFLOW_API int cvflow_optim_advance(int32_t* state, float* hyper, const float* sumsq, const float* sumsq2,
+                                               float grad_unscale, float base_lr, int32_t warmup_steps, int32_t total_steps,
+                                               float min_lr, float beta1, float beta2, void* stream) {
+  if (!state || !hyper || !sumsq) { set_error("cvflow_optim_advance: null argument"); return CVFLOW_ERR_ARG; }
+  if (!(base_lr > 0.f)) { set_error("cvflow_optim_advance: base_lr must be positive"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_optim_advance(state, hyper, sumsq, sumsq2, grad_unscale, base_lr, warmup_steps, total_steps, min_lr, beta1,
+                                  beta2, (cudaStream_t)stream), "cvflow_optim_advance");
 }
 
 extern "C" CVFLOW_API int cvflow_set_profile(cvflow_estimator* h, int32_t on) {

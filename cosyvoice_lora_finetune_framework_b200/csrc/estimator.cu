@@ -35,8 +35,12 @@ Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {
   fused_mlp_ = e && e[0] == '1';
   const char* e2 = getenv("CVFLOW_WGRAD_SIDE");
   wgrad_side_ = e2 && e2[0] == '1';
+#ifdef CVFLOW_PROFILING_BUILD
+  // profiling build only (python -m ...build --profiling -> libcvflow_prof.so): drop whole kernel classes from the step to
+  // measure their marginal cost inside the PDL-chained graph. Results are garbage; the product library has no such switch.
   const char* e3 = getenv("CVFLOW_SKIP");
   skip_ = e3 ? (unsigned)atoi(e3) : 0u;
+#endif
   if (wgrad_side_) {
     if (cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking) != cudaSuccess) { side_ = nullptr; wgrad_side_ = false; }
     else {
@@ -67,11 +71,23 @@ int Estimator::set_lora_dropout(float p, unsigned long long seed, const uint8_t*
   plans_.clear();
   return 0;
 }
+int Estimator::lora_dropout_seed(unsigned long long* out, const unsigned long long* in) {
+  if (!drop_seed_dev_) { if (out) *out = 0ull; return 0; }
+  if (out && cudaMemcpy(out, drop_seed_dev_, sizeof(*out), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("cudaMemcpy(dropout seed, D2H) failed");
+    return -1;
+  }
+  if (in && cudaMemcpy(drop_seed_dev_, in, sizeof(*in), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("cudaMemcpy(dropout seed, H2D) failed");
+    return -1;
+  }
+  return 0;
+}
 LoraDropSpec Estimator::drop_spec(int blk) const {
   LoraDropSpec d;
   d.seed = drop_seed_dev_; d.dbg = drop_dbg_; d.mcap = drop_mcap_; d.blk = blk;
-  const double t = (double)drop_p_ * 4294967296.0;
-  d.thr = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+  const double t = (double)drop_p_ * 65536.0 + 0.5;
+  d.thr16 = t >= 65535.0 ? 65535u : (unsigned)t;
   d.inv_keep = 1.f / (1.f - drop_p_);
   return d;
 }
@@ -169,9 +185,9 @@ int Estimator::run_gemm(GemmArgs& a) {
     if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return -1;
   }
   // per-call pointers at the API edge may move between calls
-  p.out = a.out; p.rowmask = a.rowmask;
+  p.out = a.out; p.rowmask = a.rowmask; p.gn_part = a.gn_part;
   prof_begin(0, 2.0 * (double)a.nbatch * a.R * (double)a.n_valid * a.Ktot);
-  int r = (skip_ & 16u) ? 0 : gemm_launch(p, stream_);
+  int r = (kSkip(skip_) & 16u) ? 0 : gemm_launch(p, stream_);
   prof_end();
   if (r) { set_error("gemm launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); return -1; }
   ++launches_;
@@ -240,17 +256,20 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
   {
     GemmArgs g = conv3_args(xin, B, L, ld_in, col0, cin, get(P + ".block1.w", cfg.bf16, 256L * 3 * cin), 256, c1, 256, 0);
     g.bias = (const float*)get(P + ".block1.b", 2, 256);
+    g.gn_part = gn_partials_;     // GroupNorm statistics from the conv epilogue: no separate pass over c1
     CK(run_gemm(g));
   }
   if (!dry_) {
-    if (!(skip_ & 4u)) CKL(launch_gn_stats(c1, gn_partials_, st1, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c1, gn_partials_, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
+    prof_begin(5, (double)M * 1024);
+    if (!(kSkip(skip_) & 4u)) CKL(launch_gn_apply(c1, gn_partials_, st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256), mask,
                        tb, tb_stride, nullptr, a1, 0, B, L, cfg.bf16, stream_));
-    launches_ += 2;
+    prof_end();
+    launches_ += 1;
   }
   {
     GemmArgs g = conv3_args(a1, B, L, 256, 0, 256, get(P + ".block2.w", cfg.bf16, 256L * 768), 256, c2, 256, 0);
     g.bias = (const float*)get(P + ".block2.b", 2, 256);
+    g.gn_part = gn_partials_;
     CK(run_gemm(g));
   }
   {
@@ -263,10 +282,11 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
     CK(run_gemm(g));
   }
   if (!dry_) {
-    if (!(skip_ & 4u)) CKL(launch_gn_stats(c2, gn_partials_, st2, B, L, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(c2, gn_partials_, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
+    prof_begin(5, (double)M * 2048);
+    if (!(kSkip(skip_) & 4u)) CKL(launch_gn_apply(c2, gn_partials_, st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256), mask,
                        nullptr, 0, r, h, 1, B, L, cfg.bf16, stream_));
-    launches_ += 3;
+    prof_end();
+    launches_ += 1;
   }
   *h_out = h;
   if (rec) *rec = ResnetRec{P, cin, B, L, c1, c2, st1, st2, mask};
@@ -285,6 +305,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   const long ldq = ext ? 1600 : 1536;
   void* x1 = alloc(M * 256 * 2);
   void* ud = drop ? alloc(M * 64 * 2) : nullptr;
+  uint32_t* bits = drop ? (uint32_t*)alloc(M * 24 * 4) : nullptr;
   void* qkv = alloc(M * ldq * 2);
   void* o = alloc(M * 512 * 2);
   float* lse = (float*)alloc((long)B * 8 * L * 4);
@@ -294,16 +315,18 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   void* g16 = fused_mlp_ ? nullptr : alloc(M * 1024 * 2);
   float* h2 = (float*)alloc(M * 256 * 4);
   if (!dry_) {
-    if (!(skip_ & 2u)) CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
-                            M, cfg.bf16, stream_));
+    prof_begin(3, (double)M * (drop ? 1536 + 128 + 96 : 1536));   // algorithmic bytes: fp32 row in, 16-bit row out (+ u_d, bits)
+    if (drop)    // LayerNorm, mask draw and the masked down-projection u_d in one pass over the residual stream
+      CKL(launch_ln_lora_drop_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256),
+                                  get(Q + ".acat16", cfg.bf16, 64L * 256), x1, ud, bits, M, cfg.lora_r, cfg.bf16,
+                                  drop_spec(lora_idx), stream_));
+    else
+      CKL(launch_layernorm_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256), x1,
+                               M, cfg.bf16, stream_));
+    prof_end();
     ++launches_;
   }
   if (drop) {
-    if (!dry_) {
-      CKL(launch_lora_down_dropout(x1, get(Q + ".acat16", cfg.bf16, 64L * 256), ud, M, cfg.lora_r, cfg.bf16,
-                                   drop_spec(lora_idx), stream_));
-      ++launches_;
-    }
     GemmArgs g = linear_args(x1, M, 256, get(Q + ".w0d", cfg.bf16, 1536L * 320), 1536, qkv, 0);
     g.A[1] = ud; g.a_rows[1] = (int)M; g.a_cols[1] = 64; g.a_ld[1] = 64; g.a_bstride[1] = M * 64L;
     g.Ktot = 320; g.nseg = 2;
@@ -321,7 +344,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       if (attn_fwd_prepare(pl.attn.back().data(), qkv, ldq, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
     }
     prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
-    if (!(skip_ & 1u)) CKL(attn_fwd_launch(pl.attn[attn_idx_].data(), kmax, iso_p, o, lse, stream_));
+    if (!(kSkip(skip_) & 1u)) CKL(attn_fwd_launch(pl.attn[attn_idx_].data(), kmax, iso_p, o, lse, stream_));
     ++attn_idx_;
     prof_end();
     ++launches_;
@@ -333,8 +356,10 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     CK(run_gemm(g));
   }
   if (!dry_) {
-    if (!(skip_ & 2u)) CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
+    prof_begin(3, (double)M * 1536);
+    if (!(kSkip(skip_) & 2u)) CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
                             M, cfg.bf16, stream_));
+    prof_end();
     ++launches_;
   }
   if (fused_mlp_) {
@@ -356,7 +381,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     }
   }
   *h_out = h2;
-  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p, ud, drop ? 1 : 0};
+  if (rec) *rec = TBRec{Q, lora_idx, B, L, ldq, h0, x1, qkv, o, lse, h1, pre, mask, kmax, iso_p, ud, drop ? 1 : 0, bits};
   return 0;
 }
 
@@ -490,7 +515,10 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   float* te1 = (float*)alloc((long)B * 1024 * 4);
   float* te2 = (float*)alloc((long)B * 1024 * 4);
   tb_all_ = (float*)alloc((long)B * nres * 256 * 4);
-  gn_partials_ = (float*)alloc(((long)B * 64 * 8 * 3 + (long)B * 16) * 4);
+  {   // GroupNorm partials: forward {n, mean, M2} per 32-row slice (from the conv epilogues), backward split sums
+    const long fwd = (long)B * gn_fwd_splits(T) * 8 * 3, bwd = (long)B * 64 * 8 * 2;
+    gn_partials_ = (float*)alloc((fwd > bwd ? fwd : bwd) * 4);
+  }
   void* xin0 = alloc((long)B * T * 320 * 2);
   void* cat1 = alloc((long)B * T * 512 * 2);
   void* cat0 = alloc((long)B * T2 * 512 * 2);
@@ -592,13 +620,15 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   {
     GemmArgs g = conv3_args(xf, B, T, 256, 0, 256, get("final_block.w", cfg.bf16, 256L * 768), 256, cf, 256, 0);
     g.bias = (const float*)get("final_block.b", 2, 256);
+    g.gn_part = gn_partials_;
     CK(run_gemm(g));
   }
   if (!dry_) {
-    if (!(skip_ & 4u)) CKL(launch_gn_stats(cf, gn_partials_, stf, B, T, cfg.bf16, stream_));
-    if (!(skip_ & 4u)) CKL(launch_gn_apply(cf, gn_partials_, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
+    prof_begin(5, (double)B * T * 1024);
+    if (!(kSkip(skip_) & 4u)) CKL(launch_gn_apply(cf, gn_partials_, stf, (const float*)get("final_block.gn.w", 2, 256), (const float*)get("final_block.gn.b", 2, 256),
                        mask1, nullptr, 0, nullptr, af, 0, B, T, cfg.bf16, stream_));
-    launches_ += 3;
+    prof_end();
+    launches_ += 1;
   }
   final_ = FinalRec{cf, stf};
   {
@@ -661,8 +691,10 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     }
   }
   if (!dry_) {
-    if (!(skip_ & 2u)) CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+    prof_begin(3, (double)M * 4096);
+    if (!(kSkip(skip_) & 2u)) CKL(launch_layernorm_bwd(tmp.dx, 256, t.h1, (const float*)get(Q + ".norm3.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
                              stream_));
+    prof_end();
     ++launches_;
   }
   {
@@ -681,7 +713,7 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
       cudaStreamWaitEvent(stream_, ev_done_[par], 0);
       ev_done_valid_[par] = false;
     }
-    if (!(skip_ & 1u)) CKL(attn_bwd_launch(pl.attn[attn_idx_].data(), tmp.dO, t.kmax, t.iso_p, t.o, t.lse, tmp.delta, dqkv, stream_));
+    if (!(kSkip(skip_) & 1u)) CKL(attn_bwd_launch(pl.attn[attn_idx_].data(), tmp.dO, t.kmax, t.iso_p, t.o, t.lse, tmp.delta, dqkv, stream_));
     ++attn_idx_;
     prof_end();
     launches_ += 2;
@@ -694,11 +726,6 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
                                     320, dxe, 0)
                       : linear_args(dqkv, M, 1536, get(Q + ".weff_t", cfg.bf16, 256L * 1536), 256, dxe, 0);
     CK(run_gemm(g));
-  }
-  if (t.drop && !dry_) {   // dx1 += s/(1-p) sum_p keep_p o (v_p A_p)
-    CKL(launch_lora_dropout_bwd(dxe, get(Q + ".acat16", cfg.bf16, 64L * 256), M, cfg.lora_r, cfg.lora_scaling, cfg.bf16,
-                                drop_spec(t.lora_idx), stream_));
-    ++launches_;
   }
   if (lora && !dry_) {
     Plan& pl = *plan_;
@@ -717,10 +744,12 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
       ws = side_;
     }
     prof_begin(4, 2.0 * M * 64.0 * (1536 + 256), ws);
-    if (!(skip_ & 8u)) CKL(lora_wgrad_launch_partial(pl.wgrads[wg_idx_].data(), ws));
+    if (!(kSkip(skip_) & 8u)) CKL(lora_wgrad_launch_partial(pl.wgrads[wg_idx_].data(), ws));
     if (t.drop) {   // the masked x^T v partials replace the un-masked ones of the tensor-core kernel
-      CKL(lora_wgrad_launch_a_dropout(pl.wgrads[wg_idx_].data(), t.x1, reinterpret_cast<const uint16_t*>(dxe) + 256, ldx,
-                                      drop_spec(t.lora_idx), tmp.wga_scratch, ws));
+      int S = 0;
+      float* part_a = lora_wgrad_plan_part_a(pl.wgrads[wg_idx_].data(), &S);
+      CKL(launch_lora_wgrad_a_drop(t.x1, reinterpret_cast<const uint16_t*>(dxe) + 256, ldx, t.bits, tmp.wga_scratch, part_a, S,
+                                   M, cfg.lora_r, drop_spec(t.lora_idx).inv_keep, cfg.bf16, ws));
       launches_ += 2;
     }
     ++wg_idx_;
@@ -732,8 +761,15 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
     ++launches_;
   }
   if (need_input_grad && !dry_) {
-    if (!(skip_ & 2u)) CKL(launch_layernorm_bwd(dxe, ldx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
-                             stream_));
+    prof_begin(3, (double)M * (t.drop ? 4096 + 128 + 96 : 4096));
+    if (t.drop)   // dx1 += s/(1-p) sum_p keep_p o (v_p A_p) and the LayerNorm backward in one pass
+      CKL(launch_ln_lora_drop_bwd(dxe, get(Q + ".acat16", cfg.bf16, 64L * 256), t.bits, t.h0,
+                                  (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.lora_r, cfg.lora_scaling,
+                                  drop_spec(t.lora_idx).inv_keep, cfg.bf16, stream_));
+    else
+      CKL(launch_layernorm_bwd(dxe, ldx, t.h0, (const float*)get(Q + ".norm1.w", 2, 256), dh32, dh32, dh16, M, cfg.bf16,
+                               stream_));
+    prof_end();
     ++launches_;
   }
   return 0;
@@ -744,18 +780,22 @@ int Estimator::resnet_bwd(const ResnetRec& r, const float* dout32, const void* d
   const std::string& P = r.prefix;
   const int B = r.B, L = r.L;
   if (!dry_) {
-    if (!(skip_ & 4u)) CKL(launch_gn_bwd(dout32, 1, r.c2, r.st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256),
+    prof_begin(5, (double)B * L * (2 * (1024 + 512) + 512));
+    if (!(kSkip(skip_) & 4u)) CKL(launch_gn_bwd(dout32, 1, r.c2, r.st2, (const float*)get(P + ".gn2.w", 2, 256), (const float*)get(P + ".gn2.b", 2, 256),
                      r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
-    launches_ += 3;
+    prof_end();
+    launches_ += 2;
   }
   {
     GemmArgs g = conv3_args(tmp.dc, B, L, 256, 0, 256, get(P + ".block2.wd", cfg.bf16, 256L * 768), 256, tmp.da, 256, 0);
     CK(run_gemm(g));
   }
   if (!dry_) {
-    if (!(skip_ & 4u)) CKL(launch_gn_bwd(tmp.da, 0, r.c1, r.st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256),
+    prof_begin(5, (double)B * L * (2 * (512 + 512) + 512));
+    if (!(kSkip(skip_) & 4u)) CKL(launch_gn_bwd(tmp.da, 0, r.c1, r.st1, (const float*)get(P + ".gn1.w", 2, 256), (const float*)get(P + ".gn1.b", 2, 256),
                      r.mask, gn_partials_, tmp.dc, B, L, cfg.bf16, stream_));
-    launches_ += 3;
+    prof_end();
+    launches_ += 2;
   }
   {
     GemmArgs g;
@@ -821,9 +861,11 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale, const InputG
     g.R = T; g.out_rows = T; g.out = tmp.da; g.ldc = 256; g.n_valid = 256;
     CK(run_gemm(g));
   }
-  if (!(skip_ & 4u)) CKL(launch_gn_bwd(tmp.da, 0, final_.cf, final_.st, (const float*)get("final_block.gn.w", 2, 256),
+  prof_begin(5, (double)B * T * (2 * (512 + 512) + 512));
+  if (!(kSkip(skip_) & 4u)) CKL(launch_gn_bwd(tmp.da, 0, final_.cf, final_.st, (const float*)get("final_block.gn.w", 2, 256),
                    (const float*)get("final_block.gn.b", 2, 256), mask1, gn_partials_, tmp.dc, B, T, cfg.bf16, stream_));
-  launches_ += 3;
+  prof_end();
+  launches_ += 2;
   {
     GemmArgs g = conv3_args(tmp.dc, B, T, 256, 0, 256, get("final_block.wd", cfg.bf16, 256L * 768), 256, g16a, 256, 0);
     g.rowmask = mask1;

@@ -44,6 +44,7 @@ struct TBRec {
   std::string prefix; int lora_idx, B, L; long ldq; float* h0; void *x1, *qkv, *o; float* lse; float* h1; void* pre;
   const float* mask; const int* kmax; int iso_p;
   void* ud; int drop;   // lora_dropout > 0: u_d = (drop(x) A^T) stash [M][64], and the flag
+  uint32_t* bits;       // lora_dropout > 0: keep decisions of the forward, [M][3][8 words]
 };
 struct StageRec { ResnetRec resnet; std::vector<TBRec> tbs; float* h_out; };
 struct FinalRec { void* cf; float* st; };
@@ -80,9 +81,12 @@ class Estimator {
   // lora_dropout p of the q/k/v LoRA branches in training forwards (0 = off: B A is folded into the GEMM operand);
   // dbg_mask: optional explicit keep masks [n_tbs][3][dbg_rows][256] bytes for parity tests (dbg_rows must be B*T)
   int set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows);
+  // device-resident seed of the mask hash (advanced by every training forward): read / overwrite (host-synchronous)
+  int lora_dropout_seed(unsigned long long* out, const unsigned long long* in);
   long launches() const { return launches_; }
   void set_profile(int on);
-  // class ids: 0 gemm, 1 attn_fwd, 2 attn_bwd, 3 norm/elementwise, 4 lora_wgrad
+  // class ids: 0 gemm, 1 attn_fwd, 2 attn_bwd, 3 layernorm (fwd + bwd, incl. the fused LoRA-dropout forms), 4 lora_wgrad,
+  // 5 groupnorm + mish (apply, bwd). Work is FLOPs for the tensor-core classes, algorithmic bytes for 3 and 5.
   int profile_read(double* ms, long* counts, double* flops, int n);
   EstimatorConfig cfg;
 
@@ -146,7 +150,12 @@ class Estimator {
   const uint8_t* drop_dbg_ = nullptr;
   long drop_dbg_rows_ = 0, drop_mcap_ = 0;
   LoraDropSpec drop_spec(int blk) const;
-  unsigned skip_ = 0;        // CVFLOW_SKIP bit mask (profiling aid, results become garbage): 1 attention, 2 layernorm, 4 groupnorm, 8 wgrad, 16 gemm
+  unsigned skip_ = 0;        // profiling build only (CVFLOW_PROFILING_BUILD): CVFLOW_SKIP bit mask, 1 attention, 2 layernorm, 4 groupnorm, 8 wgrad, 16 gemm
+#ifdef CVFLOW_PROFILING_BUILD
+  static unsigned kSkip(unsigned m) { return m; }
+#else
+  static constexpr unsigned kSkip(unsigned) { return 0u; }   // product build: every launch always runs
+#endif
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
   int *kmax1_ = nullptr, *kmax2_ = nullptr;
   void *cat0_ = nullptr, *cat1_ = nullptr;

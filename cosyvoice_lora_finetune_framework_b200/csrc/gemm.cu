@@ -104,6 +104,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   pdl_wait();     // everything above overlapped the previous kernel's tail; global memory from here on
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -147,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         for (int kb = 0; kb < p.nkb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) stamp(2);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::kABytes);
@@ -161,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
+        stamp(3);   // overwritten per tile: the last one stays
       }
     }
   } else {
@@ -230,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       prefetch(half, pf);
       mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (it == 0 && threadIdx.x == 64) stamp(4);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
@@ -255,6 +259,22 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (nn + j < p.n_valid) x[j] += __ldg(p.bias + nn + j);
+          }
+        }
+        if (p.gn_part) {   // GroupNorm partial statistics of this 32-row x 32-channel (= one group) slice
+          float s1 = 0.f, s2 = 0.f;
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1 += x[j]; s2 += x[j] * x[j]; }
+          }
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          const float cnt = 32.f * (float)__popc(__ballot_sync(0xffffffffu, valid));
+          if (lane == 0) {
+            const int tib = mt - b * p.tiles_per_batch;
+            float* o = p.gn_part + ((((long)b * p.tiles_per_batch + tib) * 4 + q) * (p.n_valid >> 5) + (nn >> 5)) * 3;
+            const float mean = cnt > 0.f ? s1 / cnt : 0.f;
+            o[0] = cnt; o[1] = mean; o[2] = cnt > 0.f ? fmaxf(s2 - s1 * mean, 0.f) : 0.f;
           }
         }
         if (p.tma_out && is_gelu && p.aux_out) {   // pre-activation stash through the staging tile
@@ -342,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       // all of this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+      if (threadIdx.x == 64) { stamp(5); if (dbg) dbg[7] = it + 1; }
     }
   }
   pdl_launch();   // dependents are released late: CTAs of the next kernel that spin at their grid-dependency wait next to the working ones cost more than their prologue overlap gains (same-box A/B)
@@ -474,6 +495,8 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->alpha = a.alpha; p->bias = a.bias; p->act = a.act; p->aux_out = a.aux_out;
   p->mul_src = a.mul_src; p->ld_aux = a.ld_aux; p->rowmask = a.rowmask; p->resid = a.resid;
   p->ldr = a.ldr;
+  p->gn_part = a.gn_part;
+  if (a.gn_part && (a.transposed_out || a.n_valid % 32)) GEMM_FAIL("gemm: gn_part needs a row-major output with n_valid %% 32 == 0");
   // tile shape: 256-wide tiles only when N divides evenly and there is more than a wave of them
   const long mtiles = (long)p->tiles_per_batch * a.nbatch;
   // tile width: these GEMMs are short (K = 256..1536) and latency-bound, so prefer enough CTAs to

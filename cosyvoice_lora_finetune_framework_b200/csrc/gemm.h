@@ -60,6 +60,10 @@ struct GemmArgs {
   const float* rowmask = nullptr;  // [nbatch*out_rows]
   const float* resid = nullptr;    // fp32 [nbatch*out_rows][ldr] (may alias out)
   long ldr = 0;
+  // GroupNorm statistics of the output (groups of 32 channels) taken in the epilogue, before the 16-bit rounding:
+  // gn_part[((b * gn_nsplit + tile_in_batch * 4 + lane_quadrant) * (n_valid / 32) + group) * 3] = {n, mean, M2} over the
+  // valid rows of that 32-row slice (Chan-mergeable partials; the consumer merges them). gn_nsplit = 4 * ceil(R / 128).
+  float* gn_part = nullptr;
   long long* dbg = nullptr;        // optional per-CTA phase timestamps (8 x int64 per CTA), profiling aid
 };
 
@@ -76,6 +80,7 @@ struct alignas(64) GemmParams {
   void* out; int out_f32; long ldc; int col_off; int n_valid; int transposed_out;
   float alpha; const float* bias; int act; void* aux_out; const void* mul_src; long ld_aux;
   const float* rowmask; const float* resid; long ldr;
+  float* gn_part;
   long long* dbg;
   const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
   int block_n;   // 64, 128 or 256

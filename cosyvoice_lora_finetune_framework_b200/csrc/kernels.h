@@ -53,9 +53,10 @@ int launch_layernorm_fwd(const float* h, const float* gamma, const float* beta, 
 // dh = dres + LN'(dxn16; h_in); also writes the 16-bit copy dh16 (nullable)
 int launch_layernorm_bwd(const void* dxn16, long ld_dxn, const float* h_in, const float* gamma, const float* dres, float* dh,
                          void* dh16, long M, int bf16, cudaStream_t st);
-// GroupNorm(8 groups of 32 channels, C=256) over the padded extent L of [B][L][256]
-int gn_num_splits(int B, int L);
-int launch_gn_stats(const void* c16, float* partials, float* stats, int B, int L, int bf16, cudaStream_t st);
+// GroupNorm(8 groups of 32 channels, C=256) over the padded extent L of [B][L][256]. Forward statistics arrive as
+// partials {n, mean, M2} [B][gn_fwd_splits(L)][8][3] written by the epilogue of the conv GEMM (GemmArgs::gn_part).
+int gn_num_splits(int B, int L);     // backward split count: partials [B][gn_num_splits][8][2]
+int gn_fwd_splits(int L);
 // mode 0: out16 = (mish(gn(c)) + tb[b][c]) * mask        (tb nullable)
 // mode 1: out32 = mish(gn(c)) * mask + add16             (resnet output, fp32 residual stream)
 int launch_gn_apply(const void* c16, const float* partials, float* stats, const float* gamma, const float* beta,
@@ -125,28 +126,34 @@ int lora_wgrad_launch_partial(const void* plan, cudaStream_t st);
 int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
                             int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st);
 
+// ---- lora_dropout.cu -------------------------------------------------------------------------
 // lora_dropout > 0: independent keep masks per (attention block, projection, token, feature) from a counter-based hash of
-// a device-resident seed (recomputed in the backward, nothing stored), or an explicit byte mask for the parity tests.
+// a device-resident seed, drawn once by the forward and kept bit-packed (24 words per token) for the backward; or an
+// explicit byte mask for the parity tests.
 struct LoraDropSpec {
   const unsigned long long* seed;  // device scalar
   const uint8_t* dbg;              // optional explicit keep mask [nblocks][3][mcap][256] (1 = keep), else NULL
   long mcap;                       // rows of the counter space per (block, projection): B * T
   int blk;                         // attention block index
-  unsigned thr;                    // drop iff hash32 < thr (= p * 2^32)
+  unsigned thr16;                  // drop iff the feature's 16-bit hash field < thr16 (= round(p * 2^16))
   float inv_keep;                  // 1 / (1 - p)
 };
 int launch_lora_seed_bump(unsigned long long* seed, cudaStream_t st);
-// u_d[M][64] (16-bit, columns >= 3r zero) = 1/(1-p) (keep_p o x) A_p^T for the three projections
-int launch_lora_down_dropout(const void* x16, const void* acat16, void* ud16, long M, int r, int bf16, const LoraDropSpec& d,
-                             cudaStream_t st);
-// dxe[M][320] (columns [0,256) dx, [256,256+3r) v): dx += s/(1-p) sum_p keep_p o (v_p A_p), in place
-int launch_lora_dropout_bwd(void* dxe16, const void* acat16, long M, int r, float scaling, int bf16, const LoraDropSpec& d,
+// x~ = LayerNorm(h) (16-bit), keep bits [M][3][8 words], u_d[M][64] (16-bit, columns >= 3r zero) =
+// 1/(1-p) (keep_p o x~) A_p^T for the three projections -- one pass over the residual stream
+int launch_ln_lora_drop_fwd(const float* h, const float* gamma, const float* beta, const void* acat16, void* x16, void* ud16,
+                            uint32_t* bits, long M, int r, int bf16, const LoraDropSpec& d, cudaStream_t st);
+// dxe[M][320] (columns [0,256) dx, [256,256+3r) v): dx~ = dx + s/(1-p) sum_p keep_p o (v_p A_p), then the LayerNorm backward
+// of dx~ (h_in, gamma) + residual gradient dres -> dh (fp32) / dh16
+int launch_ln_lora_drop_bwd(const void* dxe16, const void* acat16, const uint32_t* bits, const float* h_in, const float* gamma,
+                            const float* dres, float* dh, void* dh16, long M, int r, float scaling, float inv_keep, int bf16,
                             cudaStream_t st);
-// replaces the x^T v partials of lora_wgrad_launch_partial (same plan, run after it) by the masked ones;
+// replaces the x~^T v partials of lora_wgrad_launch_partial (run after it) by the masked ones;
 // scratch: lora_wgrad_a_dropout_scratch_floats(M) floats, free to reuse once the call's kernels have run
 long lora_wgrad_a_dropout_scratch_floats(long M);
-int lora_wgrad_launch_a_dropout(const void* plan, const void* x16, const void* v16, long ld_v, const LoraDropSpec& d,
-                                float* scratch, cudaStream_t st);
+int launch_lora_wgrad_a_drop(const void* x16, const void* v16, long ld_v, const uint32_t* bits, float* scratch, float* part_a,
+                             int S, long M, int r, float inv_keep, int bf16, cudaStream_t st);
+float* lora_wgrad_plan_part_a(const void* plan, int* S);
 
 // ---- optim.cu ------------------------------------------------------------------------------
 // Fused global-norm clip + AdamW over a flat fp32 bucket (train_joint.py:198-226,353-355).
@@ -154,5 +161,8 @@ int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cuda
 int launch_adamw(float* p, const float* g, float* m, float* v, long n, const float* sumsq, float grad_unscale,
                  float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step,
                  int* found_inf, const float* hyper_dev, cudaStream_t st);
+// device-resident step counter / LR schedule / Adam bias corrections (see optim.cu)
+int launch_optim_advance(int* state, float* hyper, const float* sumsq, const float* sumsq2, float grad_unscale, float base_lr,
+                         int warmup_steps, int total_steps, float min_lr, float beta1, float beta2, cudaStream_t st);
 
 }  // namespace cvflow

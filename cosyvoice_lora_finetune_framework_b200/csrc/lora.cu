@@ -4,7 +4,7 @@
 // copies by one batched launch per step (both the [N][K] image for y = x W_eff^T and the [K][N]
 // image for dx = dy W_eff), so the tcgen05 GEMM sees a single 16-bit weight tile stream and the
 // low-rank update costs no extra activation traffic. (Valid for lora_dropout == 0 and in eval();
-// with lora_dropout > 0 in training the un-folded branch of the second half of this file runs.)
+// with lora_dropout > 0 in training the un-folded branch of lora_dropout.cu runs.)
 // The wgrad kernel produces dA = s (dY B)^T x and dB = s dY^T (x A^T) per projection with a
 // deterministic two-stage reduction (no atomics).
 #include "kernels.h"
@@ -265,6 +265,12 @@ int lora_wgrad_prepare(void* plan, const void* dqkv, const void* xn, const void*
   return 0;
 }
 
+float* lora_wgrad_plan_part_a(const void* plan, int* S) {
+  const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
+  if (S) *S = p->S;
+  return p->part_a;
+}
+
 int lora_wgrad_launch_partial(const void* plan, cudaStream_t st) {
   const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
   static bool attr_done = false;
@@ -284,190 +290,5 @@ int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, 
   LAUNCH_RET();
 }
 
-
-// ------------------------------------------------------------------------------------------
-// lora_dropout > 0 (reference lora.py:66-74: y = W x + s B (A drop(x)), one independent nn.Dropout per
-// LoRALinear, i.e. three masks per attention block). The low-rank branch cannot be folded into the frozen
-// operand then; it stays rank-r work on the CUDA cores around the tensor-core GEMMs:
-//   forward   u_d[m][p r + j] = 1/(1-p) sum_k keep_p[m][k] x[m][k] A_p[j][k]   -> second K segment of the q/k/v GEMM,
-//                                                                               whose operand is [W0 | s B_cat]
-//   backward  dx[m][k] += s/(1-p) sum_p keep_p[m][k] sum_j v[m][p r + j] A_p[j][k]   (v = dY B_blk^T, from the dgrad GEMM)
-//   wgrad     dA_p[j][k] = s/(1-p) sum_m v[m][p r + j] keep_p[m][k] x[m][k]   (partials in the layout of the tensor-core
-//             wgrad kernel, whose un-masked x^T v result they replace); dB = s dY^T u_d comes from that kernel as is.
-// keep masks are a counter-based hash of (seed, block, projection, token, feature) recomputed wherever needed
-// (nothing is stored), or an explicit byte mask for the parity tests.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool lora_keep(const LoraDropSpec& d, unsigned long long seed, int p, long m, int k) {
-  const unsigned long long idx =
-      (((unsigned long long)(d.blk * 3 + p)) * (unsigned long long)d.mcap + (unsigned long long)m) * 256ull + (unsigned)k;
-  if (d.dbg) return d.dbg[idx] != 0;
-  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;   // splitmix64 finaliser
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (unsigned)(z >> 32) >= d.thr;
-}
-__device__ __forceinline__ void unpack8_h16(const uint4& v, int bf, float* f) {
-  unpack2_h16(v.x, bf, f[0], f[1]);
-  unpack2_h16(v.y, bf, f[2], f[3]);
-  unpack2_h16(v.z, bf, f[4], f[5]);
-  unpack2_h16(v.w, bf, f[6], f[7]);
-}
-// stage the 3r rows of A_cat (16-bit [64][256]) in shared memory
-__device__ __forceinline__ void load_acat(uint16_t* As, const uint16_t* __restrict__ acat, int r) {
-  for (int i = threadIdx.x; i < 3 * r * 32; i += blockDim.x)
-    reinterpret_cast<uint4*>(As)[i] = reinterpret_cast<const uint4*>(acat)[i];
-  __syncthreads();
-}
-
-// warp per token; lane = 8 consecutive features; u_d row written as 32 packed pairs (128 bytes per warp)
-__global__ void __launch_bounds__(256) lora_down_dropout_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ acat,
-                                                                uint32_t* __restrict__ ud, long M, int r, int bf,
-                                                                const LoraDropSpec d) {
-  __shared__ __align__(16) uint16_t As[48 * 256];
-  load_acat(As, acat, r);
-  const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (long m = (long)blockIdx.x * 8 + warp; m < M; m += (long)gridDim.x * 8) {
-    float xv[8];
-    unpack8_h16(*reinterpret_cast<const uint4*>(x + m * 256 + lane * 8), bf, xv);
-    float o0 = 0.f, o1 = 0.f;
-    for (int p = 0; p < 3; ++p) {
-      float xm[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) xm[e] = lora_keep(d, seed, p, m, lane * 8 + e) ? xv[e] : 0.f;
-      for (int j = 0; j < r; ++j) {
-        const int c = p * r + j;
-        float a[8];
-        unpack8_h16(*reinterpret_cast<const uint4*>(As + c * 256 + lane * 8), bf, a);
-        float acc = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc += xm[e] * a[e];
-        acc = warp_sum(acc);
-        if ((c >> 1) == lane) { if (c & 1) o1 = acc; else o0 = acc; }
-      }
-    }
-    ud[m * 32 + lane] = pack2_h16(o0 * d.inv_keep, o1 * d.inv_keep, bf);
-  }
-}
-
-// dxe: [M][320] 16-bit, columns [0,256) dx (updated in place), columns [256, 256+3r) v
-__global__ void __launch_bounds__(256) lora_dropout_bwd_kernel(uint16_t* __restrict__ dxe, const uint16_t* __restrict__ acat,
-                                                               long M, int r, float scaling, int bf, const LoraDropSpec d) {
-  __shared__ __align__(16) uint16_t As[48 * 256];
-  load_acat(As, acat, r);
-  const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float sc = scaling * d.inv_keep;
-  for (long m = (long)blockIdx.x * 8 + warp; m < M; m += (long)gridDim.x * 8) {
-    uint16_t* row = dxe + m * 320;
-    float v0, v1;
-    unpack2_h16(reinterpret_cast<const uint32_t*>(row + 256)[lane], bf, v0, v1);
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int p = 0; p < 3; ++p) {
-      float t[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t[e] = 0.f;
-      for (int j = 0; j < r; ++j) {
-        const int c = p * r + j;
-        const float vj = __shfl_sync(0xffffffffu, (c & 1) ? v1 : v0, c >> 1);
-        float a[8];
-        unpack8_h16(*reinterpret_cast<const uint4*>(As + c * 256 + lane * 8), bf, a);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] += vj * a[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (lora_keep(d, seed, p, m, lane * 8 + e)) acc[e] += t[e];
-    }
-    float dx[8];
-    unpack8_h16(*reinterpret_cast<const uint4*>(row + lane * 8), bf, dx);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dx[e] += sc * acc[e];
-    *reinterpret_cast<uint4*>(row + lane * 8) = pack8_h16(dx, bf);
-  }
-}
-
-// dA partials in two steps so that the work spreads over the machine: (64-token chunk, projection) CTAs with thread =
-// input feature k accumulate acc[j] = sum_t v[t][p r + j] keep_p[t][k] x[t][k] into a scratch [chunk][3][16][256];
-// a second kernel sums the chunks in fixed order (deterministic) into split 0 of the tensor-core wgrad kernel's part_a
-// layout ([split][256][64]) and zeroes the other splits, replacing that kernel's un-masked x^T v.
-static constexpr int kWgaChunk = 64;
-__global__ void __launch_bounds__(256) lora_wgrad_a_dropout_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ v,
-                                                                   long ld_v, float* __restrict__ scratch, long M, int r,
-                                                                   int bf, const LoraDropSpec d) {
-  __shared__ float vs[kWgaChunk][16];
-  const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
-  const int c = blockIdx.x, p = blockIdx.y, k = threadIdx.x;
-  const long m0 = (long)c * kWgaChunk;
-  const int n = (int)(M - m0 < kWgaChunk ? M - m0 : kWgaChunk);
-  for (int i = threadIdx.x; i < kWgaChunk * 16; i += 256) {
-    const int t = i >> 4, j = i & 15;
-    vs[t][j] = (t < n && j < r) ? h16_to_f32(v[(m0 + t) * ld_v + p * r + j], bf) : 0.f;
-  }
-  __syncthreads();
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll 8
-  for (int t = 0; t < n; ++t) {
-    const float xr = h16_to_f32(x[(m0 + t) * 256 + k], bf);
-    const float xv = lora_keep(d, seed, p, m0 + t, k) ? xr : 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < r) acc[j] += vs[t][j] * xv;
-  }
-  float* out = scratch + (((long)c * 3 + p) * 16) * 256;
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (j < r) out[j * 256 + k] = acc[j];
-}
-// grid 3r blocks (projection, rank index), thread = k
-__global__ void __launch_bounds__(256) lora_wgrad_a_dropout_reduce_kernel(const float* __restrict__ scratch, int nchunks,
-                                                                          float* __restrict__ part_a, int S, int r,
-                                                                          float inv_keep) {
-  const int k = threadIdx.x, pj = blockIdx.x;
-  const int p = pj / r, j = pj - p * r;
-  float s = 0.f;
-  for (int c = 0; c < nchunks; ++c) s += scratch[(((long)c * 3 + p) * 16 + j) * 256 + k];
-  part_a[(long)k * 64 + pj] = s * inv_keep;
-  for (int sp = 1; sp < S; ++sp) part_a[((long)sp * 256 + k) * 64 + pj] = 0.f;
-}
-
-__global__ void lora_seed_bump_kernel(unsigned long long* seed) { seed[0] += 0x632BE59BD9B4E019ull; }
-
-int launch_lora_seed_bump(unsigned long long* seed, cudaStream_t st) {
-  lora_seed_bump_kernel<<<1, 1, 0, st>>>(seed);
-  LAUNCH_RET();
-}
-static unsigned drop_grid(long M) { long g = (M + 7) / 8; return (unsigned)(g < 148 * 8 ? g : 148 * 8); }
-int launch_lora_down_dropout(const void* x16, const void* acat16, void* ud16, long M, int r, int bf16, const LoraDropSpec& d,
-                             cudaStream_t st) {
-  if (r > 16 || M <= 0) return -(int)cudaErrorInvalidValue;
-  lora_down_dropout_kernel<<<drop_grid(M), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16),
-                                                          reinterpret_cast<const uint16_t*>(acat16),
-                                                          reinterpret_cast<uint32_t*>(ud16), M, r, bf16, d);
-  LAUNCH_RET();
-}
-int launch_lora_dropout_bwd(void* dxe16, const void* acat16, long M, int r, float scaling, int bf16, const LoraDropSpec& d,
-                            cudaStream_t st) {
-  if (r > 16 || M <= 0) return -(int)cudaErrorInvalidValue;
-  lora_dropout_bwd_kernel<<<drop_grid(M), 256, 0, st>>>(reinterpret_cast<uint16_t*>(dxe16),
-                                                         reinterpret_cast<const uint16_t*>(acat16), M, r, scaling, bf16, d);
-  LAUNCH_RET();
-}
-long lora_wgrad_a_dropout_scratch_floats(long M) { return ((M + kWgaChunk - 1) / kWgaChunk) * 3L * 16 * 256; }
-int lora_wgrad_launch_a_dropout(const void* plan, const void* x16, const void* v16, long ld_v, const LoraDropSpec& d,
-                                float* scratch, cudaStream_t st) {
-  const WgradParams* p = reinterpret_cast<const WgradParams*>(plan);
-  const int nchunks = (int)((p->M + kWgaChunk - 1) / kWgaChunk);
-  lora_wgrad_a_dropout_kernel<<<dim3(nchunks, 3), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(x16),
-                                                                reinterpret_cast<const uint16_t*>(v16), ld_v, scratch, p->M,
-                                                                p->r, p->bf16, d);
-  lora_wgrad_a_dropout_reduce_kernel<<<3 * p->r, 256, 0, st>>>(scratch, nchunks, p->part_a, p->S, p->r, d.inv_keep);
-  LAUNCH_RET();
-}
 
 }  // namespace cvflow

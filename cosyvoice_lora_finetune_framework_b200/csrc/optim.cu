@@ -43,13 +43,57 @@ int launch_sumsq(const float* g, long n, float* partials, float* out_sumsq, cuda
   LAUNCH_RET();
 }
 
+// Per-step optimiser scalars advanced ON THE DEVICE, inside the captured step (no host write can race a replay):
+//   state[0] = optimiser steps applied so far (k), state[1] = steps skipped because the gradient norm was not finite
+//   hyper    = {lr of this step, 1 - beta1^t, sqrt(1 - beta2^t), 1 = apply / 0 = skip}, t = k + 1
+// The learning rate follows the reference's LambdaLR with interval 'step' (train_joint.py:210-226): the (k+1)-th
+// optimiser step runs with base_lr * lambda(k) -- linear warm-up, then cosine decay to min_lr (the reference's
+// literal 3.14159). A skipped step (GradScaler semantics of the '16-mixed' run) advances neither k nor the schedule.
+__global__ void optim_advance_kernel(int* __restrict__ state, float* __restrict__ hyper, const float* __restrict__ sumsq,
+                                     const float* __restrict__ sumsq2, float grad_unscale, float base_lr, int warmup_steps,
+                                     int total_steps, float min_lr, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float ss = sumsq[0] + (sumsq2 ? sumsq2[0] : 0.f);
+  const float total = sqrtf(ss) * grad_unscale;
+  if (!isfinite(total)) {
+    state[1] += 1;
+    hyper[3] = 0.f;
+    return;
+  }
+  const int k = state[0];
+  float lam = 1.f;
+  if (total_steps > 0) {
+    if (k < warmup_steps) lam = (float)k / (float)max(1, warmup_steps);
+    else {
+      const float progress = (float)(k - warmup_steps) / (float)max(1, total_steps - warmup_steps);
+      lam = fmaxf(min_lr / base_lr, 0.5f * (1.f + cosf(progress * 3.14159f)));
+    }
+  }
+  const float t = (float)(k + 1);
+  hyper[0] = base_lr * lam;
+  hyper[1] = 1.f - powf(beta1, t);
+  hyper[2] = sqrtf(1.f - powf(beta2, t));
+  hyper[3] = 1.f;
+  state[0] = k + 1;
+}
+int launch_optim_advance(int* state, float* hyper, const float* sumsq, const float* sumsq2, float grad_unscale, float base_lr,
+                         int warmup_steps, int total_steps, float min_lr, float beta1, float beta2, cudaStream_t st) {
+  optim_advance_kernel<<<1, 32, 0, st>>>(state, hyper, sumsq, sumsq2, grad_unscale, base_lr, warmup_steps, total_steps, min_lr,
+                                         beta1, beta2);
+  LAUNCH_RET();
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long n, const float* __restrict__ sumsq,
                                                     float grad_unscale, float max_norm, float lr, float beta1, float beta2,
                                                     float eps, float wd, float bc1, float bc2_sqrt, int* __restrict__ found_inf,
                                                     const float* __restrict__ hyper) {
-  if (hyper) {   // {lr, 1-beta1^t, sqrt(1-beta2^t)} refreshed by the host before each CUDA-graph replay
+  if (hyper) {   // {lr, 1-beta1^t, sqrt(1-beta2^t), apply flag} written by optim_advance_kernel earlier in the same step
     lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2];
+    if (hyper[3] == 0.f) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && found_inf) *found_inf = 1;
+      return;
+    }
   }
   const float total = sqrtf(sumsq[0]) * grad_unscale;
   if (!isfinite(total)) {

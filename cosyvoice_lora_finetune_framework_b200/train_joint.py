@@ -58,9 +58,11 @@ def _data_iter(args, batch_size, rank, world):
 
 
 def save_checkpoint(model, trainer, path, epoch, loss):
+    """Lightning-layout checkpoint (`state_dict` keys prefixed `model.`) plus the optimiser state needed for an exact
+    resume: Adam moments of both flat buckets, the step counter (= schedule position) and the loss scale."""
     sd = {'model.' + k: v.detach().cpu() for k, v in model.state_dict().items()}
-    torch.save({'state_dict': sd, 'epoch': epoch, 'train_loss': loss, 'global_step': trainer.step_count,
-                'optimizer': {'m': trainer.m.cpu(), 'v': trainer.v.cpu()}}, path)
+    opt = trainer.state_dict()
+    torch.save({'state_dict': sd, 'epoch': epoch, 'train_loss': loss, 'global_step': opt['step'], 'optimizer': opt}, path)
 
 
 def main(argv=None):
@@ -96,9 +98,12 @@ def main(argv=None):
     model = build_joint_model(PRETRAINED_MODEL_DIR, str(device), 'flow_only', None, flow_lora)
     model.flow.decoder.estimator.cvflow_dtype = torch.float16 if args.dtype == 'fp16' else torch.bfloat16
     upstream = [p for n, p in model.flow.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]
-    if args.resume:
-        state = torch.load(args.resume, map_location='cpu').get('state_dict', {})
+    resume, start_epoch = None, 0
+    if args.resume:      # Lightning's ckpt_path semantics: parameters, optimiser moments, schedule position, epoch
+        resume = torch.load(args.resume, map_location='cpu', weights_only=False)
+        state = resume.get('state_dict', {})
         model.load_state_dict({k[len('model.'):]: v for k, v in state.items() if k.startswith('model.')}, strict=False)
+        start_epoch = int(resume.get('epoch', -1)) + 1
     data = _data_iter(args, batch_size, rank, world)
     steps_per_epoch = max(1, len(data) // accumulate)
     trainer = FlowLoRATrainer(model.flow.decoder, lr=lr, weight_decay=TRAIN_CONFIG.get('weight_decay', 0.01),
@@ -106,9 +111,11 @@ def main(argv=None):
                               warmup_steps=TRAIN_CONFIG.get('warmup_steps', 50), total_steps=epochs * steps_per_epoch,
                               min_lr=TRAIN_CONFIG.get('min_learning_rate', 1e-6), accumulate=accumulate,
                               extra_params=upstream)
+    if resume is not None and isinstance(resume.get('optimizer'), dict) and 'm' in resume['optimizer']:
+        trainer.load_state_dict(resume['optimizer'])
     model.train()
     os.makedirs(args.output_dir, exist_ok=True)
-    for epoch in range(epochs):
+    for epoch in range(start_epoch, epochs):
         t0, losses = time.time(), []
         for batch in data:
             out = model(batch, device)
@@ -117,9 +124,16 @@ def main(argv=None):
             if trainer.micro >= accumulate:
                 trainer.optimizer_step()
             losses.append(out['flow_loss'].detach())
-        mean = float(torch.stack(losses).mean())
+        if trainer.micro > 0:      # Lightning steps the optimiser on the last batch of an epoch: no carry-over
+            trainer.optimizer_step()
+        skipped = trainer.poll_overflow()      # fp16: steps skipped on a non-finite gradient norm -> loss scale halved
+        mean_t = torch.stack(losses).mean()
+        if world > 1:             # every rank must take the same early-stop decision (else the others hang in all_reduce)
+            dist.all_reduce(mean_t, op=dist.ReduceOp.AVG)
+        mean = float(mean_t)
         if rank == 0:
-            print(f"epoch {epoch}: flow_loss {mean:.4f} lr {trainer.current_lr():.2e} ({time.time() - t0:.1f}s)")
+            print(f"epoch {epoch}: flow_loss {mean:.4f} lr {trainer.current_lr():.2e} ({time.time() - t0:.1f}s)"
+                  + (f" [{skipped} step(s) skipped on overflow, loss scale now {trainer.ne.loss_scale:g}]" if skipped else ""))
             save_checkpoint(model, trainer, os.path.join(args.output_dir, f'joint_{args.mode}_last.ckpt'), epoch, mean)
         if mean <= 0.3:   # LossThresholdCallback(flow <= 0.3), reference train_joint.py:336-340
             break

@@ -82,6 +82,10 @@ typedef struct cvflow_gemm_desc {
   const float* resid;
   int64_t ldr;
   int64_t* dbg;         /* optional: 8 x int64 globaltimer stamps per CTA (profiling aid), else NULL */
+  float* gn_part;       /* optional: GroupNorm partial statistics of the output taken in the epilogue (before the 16-bit
+                         * rounding): {n, mean, M2} per (batch, 32-row slice, 32-channel group),
+                         * [nbatch][4 * ceil(R / 128)][n_valid / 32][3] floats, Chan-mergeable (replaces the separate
+                         * statistics pass of nn.GroupNorm after nn.Conv1d, modules.py:60-73); else NULL */
 } cvflow_gemm_desc;
 
 CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* desc, void* stream);
@@ -156,12 +160,16 @@ CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void*
 /* lora_dropout of the q/k/v LoRA branches (reference lora.py:66-74: y = W x + s B (A drop(x)), one independent
  * nn.Dropout per LoRALinear). p = 0 (default): B A is folded into the GEMM operand. p > 0: training forwards apply an
  * independent keep mask per (attention block, projection, token, feature), drawn from a counter-based hash of `seed`
- * (advanced on the device at every training forward; the backward recomputes the same masks), scaled by 1/(1-p).
+ * (advanced on the device at every training forward; the decisions are kept bit-packed, 96 B per token and block, for
+ * the backward), scaled by 1/(1-p). p is quantised to 16 bits (a feature is dropped iff its hash field < round(p 2^16)).
  * Needs the extra operand images "<block>.w0d" ([1536][320] = [W0 | s B_cat]) and "<block>.w0t_ext" ([320][1536] =
  * [W0^T ; B_blk]) to be bound and kept current by the caller. debug_mask (optional, else NULL): explicit keep masks
  * [n_blocks][3][debug_rows][256] bytes (1 = keep) with debug_rows = B*T, for parity tests against the reference. */
 CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, uint64_t seed, const uint8_t* debug_mask,
                                        int64_t debug_rows);
+/* Read (out != NULL) and / or overwrite (in != NULL) the device-resident seed of the mask hash; host-synchronous.
+ * Lets a caller rewind the dropout stream (e.g. after the warm-up executions that precede a CUDA-graph capture). */
+CVFLOW_API int cvflow_lora_dropout_seed(cvflow_estimator* h, uint64_t* out, const uint64_t* in);
 CVFLOW_API int64_t cvflow_launch_count(cvflow_estimator* h);
 /* Measurement aid (bench.py roofline): when on, CUDA events bracket every tensor-core launch on
  * the launching stream. cvflow_profile_read synchronises the stream and sums per class
@@ -236,6 +244,15 @@ CVFLOW_API int cvflow_adamw_step(float* p, const float* g, float* m, float* v, i
                                  float weight_decay, int32_t step, int32_t* found_inf,
                                  const float* hyper_dev /* optional {lr, 1-b1^t, sqrt(1-b2^t)} on device, NULL = use args */,
                                  void* stream);
+/* Step counter, LR schedule and Adam bias corrections kept ON THE DEVICE so that a captured whole-step CUDA graph
+ * needs no per-replay host write (replaces Lightning's LambdaLR.step + optimizer bookkeeping, train_joint.py:198-226):
+ *   state[0] = optimiser steps applied (k), state[1] = steps skipped on a non-finite gradient norm;
+ *   hyper[4] = {base_lr * lambda(k), 1-b1^(k+1), sqrt(1-b2^(k+1)), apply flag}; total_steps <= 0: constant lr.
+ * sumsq2 (nullable): squared norm of a second bucket sharing the same global norm. Call between cvflow_sumsq and
+ * cvflow_adamw_step(hyper_dev = hyper). */
+CVFLOW_API int cvflow_optim_advance(int32_t* state, float* hyper, const float* sumsq, const float* sumsq2,
+                                    float grad_unscale, float base_lr, int32_t warmup_steps, int32_t total_steps,
+                                    float min_lr, float beta1, float beta2, void* stream);
 
 #ifdef __cplusplus
 }

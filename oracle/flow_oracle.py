@@ -59,12 +59,16 @@ def sinusoidal_embedding(t: Tensor, dim: int = 320, scale: float = 1000.0) -> Te
 
 def _linear(P, prefix: str, x: Tensor, lora_scaling: Dict[str, float]) -> Tensor:
     """nn.Linear or LoRALinear (lora.py:64-76). nn.Dropout's draw on the LoRA input is supplied by the caller as an
-    optional `<prefix>.lora_dropout_mask` entry of P (keep / (1 - p), broadcastable to x); absent = no dropout."""
+    optional `<prefix>.lora_dropout_mask` entry of P (keep / (1 - p), broadcastable to x); absent = no dropout.
+    For TIMING runs (bench.py's CPU baseline at the reference's default lora_dropout = 0.05) a float entry
+    P["__lora_dropout_p__"] makes every LoRA layer draw its own mask with F.dropout, like the reference's nn.Dropout."""
     if prefix + ".lora_A" in P:
         w, b = P[prefix + ".original_layer.weight"], P.get(prefix + ".original_layer.bias")
         y = F.linear(x, w, b)
         dm = P.get(prefix + ".lora_dropout_mask")
         xl = x * dm if dm is not None else x
+        if dm is None and P.get("__lora_dropout_p__"):
+            xl = F.dropout(x, float(P["__lora_dropout_p__"]), training=True)
         low = F.linear(F.linear(xl, P[prefix + ".lora_A"]), P[prefix + ".lora_B"])
         return y + low * lora_scaling[prefix]
     return F.linear(x, P[prefix + ".weight"], P.get(prefix + ".bias"))

@@ -11,7 +11,8 @@ from tests.test_gemm_gpu import _desc  # noqa: E402
 
 dt = torch.bfloat16
 L = N.lib()
-names = ["start", "prologue done", "first stage landed", "last MMA issued", "accumulator ready", "epilogue done", "exit"]
+names = ["start", "grid-dependency wait passed", "first stage landed (MMA warp)", "last tile's MMAs issued", "first accumulator ready (epilogue)",
+         "last epilogue done", "exit"]
 for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6400, 1024, 256, "gelu"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (6400, 256, 1024, "h16"), (6400, 512, 256, "h16"), (6400, 256, 1536, "h16"), (6400, 64, 1536, "h16"), (12800, 1536, 256, "h16"), (12800, 256, 1024, "resid")]:
     A = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
     W = (torch.randn(Nn, K, device="cuda") * 0.1).to(dt)
@@ -40,3 +41,9 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6
     print("== M=%d N=%d K=%d %s: %d persistent CTAs, kernel span %.1f us (%.0f TFLOP/s), CTA start spread %.2f us, "
           "CTA lifetime mean %.2f / max %.2f us" % (M, Nn, K, mode, t.shape[0], span, fl / span / 1e6,
           float((t[:, 0].max() - t0) / 1e3), float((t[:, 6] - t[:, 0]).mean()) / 1e3, float((t[:, 6] - t[:, 0]).max()) / 1e3))
+    # mean / max over CTAs of every stamp, in us after the first CTA's start; CTAs grouped by the number of tiles they ran
+    for nt in sorted(set(t[:, 7].tolist())):
+        g = t[t[:, 7] == nt]
+        print("   %3d CTAs with %d tile(s): " % (g.shape[0], int(nt)) + " | ".join(
+            "%s %.2f/%.2f" % (names[k].split(" (")[0], float((g[:, k] - t0).mean()) / 1e3, float((g[:, k] - t0).max()) / 1e3)
+            for k in range(1, 7)))

@@ -5,6 +5,10 @@
     python tests/golden/make_golden.py inputgrads    # inputgrads_*: dL/dmu, dL/dspks, dL/dcond of compute_loss
     python tests/golden/make_golden.py flowmodel     # flowmodel_tiny: MaskedDiffWithXvec.forward + backward, encoder LoRA
     python tests/golden/make_golden.py dropout       # dropout_tiny_prompt: lora_dropout > 0 with preset keep masks
+    python tests/golden/make_golden.py bench         # the BENCHMARKED shapes: train_c3 (300M, 32 x 400 ragged, + the reference's
+                                                     # own bf16 / fp16 autocast error at that shape), euler_c2 (300M, T=700,
+                                                     # P=200, 10 steps), train_tiny_padprompt (boundary window running into the
+                                                     # padding), dropout_c1 (300M, lora_dropout = 0.05 with preset masks)
 
 The GPU box has no /root/reference; tests read the committed .pt files. Weights are not stored:
 they are a pure function of (parameter name, shape, seed) - oracle.flow_oracle.synth_tensor - and
@@ -168,6 +172,131 @@ def dropout_case(name, src, p, mask_seed):
           float(keep.float().mean()))
 
 
+# ------------------------------------------------------------------------------------------------------
+# Fixtures at the benchmarked shapes. The big input tensors are NOT stored: they are regenerated from the
+# seeds with the same torch.Generator call sequence (bench.py::make_batch), and the fixture keeps checksums.
+# ------------------------------------------------------------------------------------------------------
+def bench_batch(B, T, seed):
+    """Exactly bench.py::make_batch (configs[2] synthetic batch)."""
+    g = torch.Generator().manual_seed(seed)
+    x1 = torch.randn(B, 80, T, generator=g)
+    mu = torch.randn(B, 80, T, generator=g)
+    spks = torch.randn(B, 80, generator=g)
+    cond = torch.zeros(B, 80, T)
+    lens = torch.randint(int(0.6 * T) + 1, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
+    return x1, mu, spks, cond, mask, lens
+
+
+def step_draws(B, T, step_seed):
+    torch.manual_seed(step_seed)
+    t_rand = torch.rand([B, 1, 1])
+    z = torch.randn(B, 80, T)
+    cfg_rand = torch.rand(B)
+    return t_rand, z, cfg_rand
+
+
+def csum(t):
+    return [float(t.double().sum()), float(t.double().abs().sum())]
+
+
+def _grad_errors(grads, ref):
+    num = sum((grads[k] - ref[k]).double().pow(2).sum() for k in ref)
+    den = sum(ref[k].double().pow(2).sum() for k in ref)
+    per = sorted(float((grads[k] - ref[k]).double().norm() / (ref[k].double().norm() + 1e-30)) for k in ref)
+    return dict(bucket_rel_l2=float((num / den).sqrt()), tensor_rel_l2_median=per[len(per) // 2], tensor_rel_l2_max=per[-1])
+
+
+def train_bench_case(name, B, T, batch_seed, step_seed, keep_grads, autocast=True):
+    cfm, sd, stats = build_ref(4, 12)
+    cfm.train()
+    x1, mu, spks, cond, mask, lens = bench_batch(B, T, batch_seed)
+    t_rand, z, cfg_rand = step_draws(B, T, step_seed)
+    torch.manual_seed(step_seed)
+    loss, y = cfm.compute_loss(x1, mask, mu, spks, cond=cond, prompt_lens=None)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in cfm.estimator.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        t = 1 - torch.cos(t_rand * 0.5 * 3.14159265359)
+        assert torch.equal(y, (1 - (1 - 1e-6) * t) * z + t * x1)      # the recorded draws are the ones compute_loss made
+    floors = {}
+    if autocast:      # the reference's own reduced-precision error at this exact shape (its noise floor)
+        for dn, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+            for p in cfm.estimator.parameters():
+                p.grad = None
+            torch.manual_seed(step_seed)
+            with torch.autocast("cpu", dtype=dt):
+                l2, _ = cfm.compute_loss(x1, mask, mu, spks, cond=cond, prompt_lens=None)
+            scale = 4096.0 if dn == "fp16" else 1.0     # fp16 gradients need the GradScaler's loss scale ('16-mixed')
+            (l2 * scale).backward()
+            g2 = {k: p.grad.float().clone() / scale for k, p in cfm.estimator.named_parameters() if p.grad is not None}
+            floors[dn] = dict(loss_rel=abs(float(l2) - float(loss)) / abs(float(loss)), **_grad_errors(g2, grads))
+            print(name, "reference under", dn, "autocast:", floors[dn])
+    fx = dict(kind="train_bench", n_blocks=4, n_mid=12, wseed=WSEED, wsum=wsum(sd), lora_stats=stats, B=B, T=T,
+              batch_seed=batch_seed, step_seed=step_seed, lengths=lens,
+              checks=dict(x1=csum(x1), mu=csum(mu), spks=csum(spks), z=csum(z), t_rand=csum(t_rand), cfg_rand=csum(cfg_rand),
+                          y=csum(y.detach())),
+              loss=loss.detach(), grad_norms={k: float(v.norm()) for k, v in grads.items()},
+              grad_total_norm=float(torch.sqrt(sum(v.double().pow(2).sum() for v in grads.values()))),
+              grads={k: v for k, v in grads.items() if keep_grads(k)}, ref_autocast=floors)
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "gradnorm", fx["grad_total_norm"], "ngrads", len(grads), "kept", len(fx["grads"]),
+          "valid frames", int(lens.sum()))
+
+
+def euler_bench_case(name, T, prompt, n_steps, seed):
+    """bench.py's inference leg (configs[1]): same generator sequence for mu / spks / cond prompt."""
+    cfm, sd, _ = build_ref(4, 12, r=0)
+    cfm.eval()
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(1, 80, T, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    cond = torch.zeros(1, 80, T)
+    cond[:, :, :prompt] = torch.randn(1, 80, prompt, generator=g)
+    mask = torch.ones(1, 1, T)
+    torch.manual_seed(seed + 1)
+    z = torch.randn_like(mu)
+    torch.manual_seed(seed + 1)
+    mel, cache = cfm(mu=mu.clone(), mask=mask, n_timesteps=n_steps, temperature=1.0, spks=spks, cond=cond,
+                     prompt_len=prompt, cache=None)
+    floors = {}
+    for dn, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        torch.manual_seed(seed + 1)
+        with torch.autocast("cpu", dtype=dt):
+            m2, _ = cfm(mu=mu.clone(), mask=mask, n_timesteps=n_steps, temperature=1.0, spks=spks, cond=cond,
+                        prompt_len=prompt, cache=None)
+        floors[dn] = dict(max_abs=float((m2.float() - mel).abs().max()), mean_abs=float((m2.float() - mel).abs().mean()))
+        print(name, "reference under", dn, "autocast:", floors[dn], "abs-max of mel", float(mel.abs().max()))
+    torch.save(dict(kind="euler_bench", n_blocks=4, n_mid=12, wseed=WSEED, wsum=wsum(sd), T=T, prompt=prompt, n_steps=n_steps,
+                    seed=seed, checks=dict(mu=csum(mu), spks=csum(spks), cond=csum(cond), z=csum(z)), mel=mel.clone(),
+                    cache=cache.clone(), ref_autocast=floors), os.path.join(HERE, name + ".pt"))
+    print(name, "mel sum", float(mel.sum()), "absmax", float(mel.abs().max()), tuple(cache.shape))
+
+
+def dropout_bench_case(name, src, p, mask_seed, keep_grads):
+    """300M-scale lora_dropout fixture (the reference's default p = 0.05): like dropout_case, full grads only for a few
+    layers, masks regenerated from the seed by the test."""
+    fx = torch.load(os.path.join(HERE, src + ".pt"), map_location="cpu", weights_only=False)
+    cfm, sd, _ = build_ref(fx["n_blocks"], fx["n_mid"], targets=('to_q', 'to_k', 'to_v'))
+    cfm.train()
+    B, _, T = fx["x1"].shape
+    blocks = attention_blocks(cfm.estimator)
+    keep = dropout_masks(len(blocks), B * T, p, mask_seed)
+    for i, (_, tb) in enumerate(blocks):
+        for j, pn in enumerate(("to_q", "to_k", "to_v")):
+            getattr(tb.attn1, pn).lora_dropout = FixedDropout(keep[i, j], p)
+    torch.manual_seed(7)
+    loss, _ = cfm.compute_loss(fx["x1"], fx["mask"], fx["mu"], fx["spks"], cond=fx["cond"], prompt_lens=fx["prompt_lens"])
+    loss.backward()
+    grads = {k: q.grad.clone() for k, q in cfm.estimator.named_parameters() if q.grad is not None}
+    torch.save(dict(kind="lora_dropout", src=src, p=p, mask_seed=mask_seed, n_tbs=len(blocks), rows=B * T,
+                    keep_sum=int(keep.sum()), loss=loss.detach(), grad_norms={k: float(v.norm()) for k, v in grads.items()},
+                    grads={k: v for k, v in grads.items() if keep_grads(k)}), os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "(no dropout: %g)" % float(fx["loss"]), "ngrads", len(grads), "keep rate",
+          float(keep.float().mean()))
+
+
 FLOW_TINY = dict(encoder_num_blocks=2, decoder_n_blocks=1, decoder_num_mid_blocks=1)
 FLOW_TARGETS = ['to_q', 'to_k', 'to_v', 'linear_q', 'linear_k', 'linear_v', 'w_1', 'w_2']     # config.py:207-216
 
@@ -290,6 +419,18 @@ if __name__ == "__main__":
         sys.exit(0)
     if sys.argv[1:] == ["dropout"]:
         dropout_case("dropout_tiny_prompt", "train_tiny_prompt", 0.25, 31)
+        sys.exit(0)
+    if sys.argv[1:] == ["bench"]:
+        fml = lambda k: any(s in k for s in ("down_blocks.0.1.0.", "mid_blocks.5.1.2.", "up_blocks.1.1.3."))
+        only = os.environ.get("CVFLOW_GOLDEN_ONLY", "")
+        if not only or only == "padprompt":
+            train_case("train_tiny_padprompt", 1, 1, 3, 64, [64, 40, 33], [50, 30, 25], 101, 9, lambda k: True)
+        if not only or only == "dropout":
+            dropout_bench_case("dropout_c1", "train_c1", 0.05, 33, fml)
+        if not only or only == "euler":
+            euler_bench_case("euler_c2", 700, 200, 10, 5)
+        if not only or only == "train":
+            train_bench_case("train_c3", 32, 400, 99, 7, fml)
         sys.exit(0)
     if sys.argv[1:] == ["flowmodel"]:
         flow_model_case("flowmodel_tiny", 21, 3, 5)

@@ -59,3 +59,56 @@ def oracle_dropout_entries(keep, p, prefixes, B, T):
         for j, pn in enumerate(("to_q", "to_k", "to_v")):
             out["%s.attn1.%s.lora_dropout_mask" % (q, pn)] = keep[i, j, : B * L].view(B, L, 256).float() / (1.0 - p)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Fixtures at the benchmarked shapes (train_c3, euler_c2) do not store their big inputs: they are regenerated
+# from the seeds with the same torch.Generator call sequence as bench.py / make_golden.py and verified against
+# the checksums the fixture recorded from the reference run.
+# ------------------------------------------------------------------------------------------------------
+def csum(t):
+    return [float(t.double().sum()), float(t.double().abs().sum())]
+
+
+def check_sums(tensors, checks):
+    for k, t in tensors.items():
+        s = csum(t)
+        assert abs(s[0] - checks[k][0]) <= 1e-6 * (1.0 + abs(checks[k][1])) and \
+            abs(s[1] - checks[k][1]) <= 1e-6 * (1.0 + abs(checks[k][1])), ("regenerated input differs from the fixture", k)
+
+
+def bench_train_inputs(fx):
+    """(x1, mask, mu, spks, cond, t_rand, z, cfg_rand) of a `train_bench` fixture: bench.py::make_batch + the three
+    draws of compute_loss under torch.manual_seed(step_seed)."""
+    import bench
+    B, T = fx["B"], fx["T"]
+    batch, lens = bench.make_batch(B, T, fx["batch_seed"], "cpu")
+    assert torch.equal(lens, fx["lengths"])
+    torch.manual_seed(fx["step_seed"])
+    t_rand = torch.rand([B, 1, 1])
+    z = torch.randn(B, 80, T)
+    cfg_rand = torch.rand(B)
+    check_sums(dict(x1=batch["x1"], mu=batch["mu"], spks=batch["spks"], z=z, t_rand=t_rand, cfg_rand=cfg_rand), fx["checks"])
+    return batch["x1"], batch["mask"], batch["mu"], batch["spks"], batch["cond"], t_rand, z, cfg_rand
+
+
+def bench_euler_inputs(fx):
+    """(mu, spks, cond, mask, z) of an `euler_bench` fixture (bench.py's inference leg, seed 5)."""
+    T, P = fx["T"], fx["prompt"]
+    g = torch.Generator().manual_seed(fx["seed"])
+    mu = torch.randn(1, 80, T, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    cond = torch.zeros(1, 80, T)
+    cond[:, :, :P] = torch.randn(1, 80, P, generator=g)
+    torch.manual_seed(fx["seed"] + 1)
+    z = torch.randn_like(mu)
+    check_sums(dict(mu=mu, spks=spks, cond=cond, z=z), fx["checks"])
+    return mu, spks, cond, torch.ones(1, 1, T), z
+
+
+def grad_errors(grads, ref):
+    """bucket rel-L2 and per-tensor rel-L2 (median, max) of `grads` against `ref` over the tensors in `ref`."""
+    num = sum((grads[k].cpu() - ref[k]).double().pow(2).sum() for k in ref)
+    den = sum(ref[k].double().pow(2).sum() for k in ref)
+    per = sorted(float((grads[k].cpu() - ref[k]).double().norm() / (ref[k].double().norm() + 1e-30)) for k in ref)
+    return dict(bucket_rel_l2=float((num / den).sqrt()), tensor_rel_l2_median=per[len(per) // 2], tensor_rel_l2_max=per[-1])

@@ -126,8 +126,62 @@ def test_graphed_step_matches_eager_step():
         results.append((losses, tr.ne.param_bucket.clone(), tr.step_count))
     (l0, p0, s0), (l1, p1, s1) = results
     assert all(torch.isfinite(torch.tensor(l0 + l1)))
-    # the graphed trainer ran 2 extra warm-up steps before capture, so compare trajectories loosely:
-    # both descend a stochastic objective; parameters must have moved by a similar amount
-    assert s1 == s0 + 2
-    assert torch.isfinite(p1).all() and float((p1 - p0).abs().max()) > 0
-    assert float(p1.abs().sum()) > 0
+    # one call == one optimiser step in both forms: the warm-up executions that precede the capture are rolled back
+    # (parameters, Adam moments, device-side step counter, RNG), so the two trajectories coincide
+    assert s1 == s0 == 5
+    assert torch.allclose(torch.tensor(l1), torch.tensor(l0), rtol=2e-3, atol=1e-5), (l0, l1)
+    assert torch.allclose(p1, p0, rtol=1e-3, atol=2e-5), float((p1 - p0).abs().max())
+
+
+def test_optimizer_schedule_state_and_resume():
+    """Device-side step counter / LR schedule (LambdaLR semantics: the first warm-up step runs with lr = 0), skipped
+    steps on a non-finite gradient norm, and trainer.state_dict() / load_state_dict() round trip."""
+    from cosyvoice_lora_finetune_framework_b200.train_joint import synthetic_batches  # noqa: F401
+    from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer, lr_lambda
+    model = _model(seed=11)
+    model.eval()
+    cfm = model.flow.decoder
+    cfm.estimator.train()
+    tr = FlowLoRATrainer(cfm, lr=1e-3, warmup_steps=4, total_steps=20)
+    g = torch.Generator().manual_seed(2)
+    B, T = 2, 48
+    x1, mu = torch.randn(B, 80, T, generator=g).cuda(), torch.randn(B, 80, T, generator=g).cuda()
+    spks, cond, mask = torch.randn(B, 80, generator=g).cuda(), torch.zeros(B, 80, T).cuda(), torch.ones(B, 1, T).cuda()
+    p_init = tr.ne.param_bucket.clone()
+    tr.train_step(x1, mask, mu, spks, cond)
+    torch.cuda.synchronize()
+    # step 1 of a warm-up: lambda(0) = 0 -> parameters unchanged (AdamW decay is lr-scaled too), counter advanced
+    assert torch.equal(tr.ne.param_bucket, p_init)
+    assert tr.opt_state.tolist() == [1, 0] and float(tr.hyper[0]) == 0.0
+    tr.train_step(x1, mask, mu, spks, cond)
+    assert abs(float(tr.hyper[0]) - 1e-3 * lr_lambda(1, 4, 20, 1e-3, 1e-6)) < 1e-9
+    assert not torch.equal(tr.ne.param_bucket, p_init)
+    # a non-finite gradient: the step is skipped, neither the counter nor the parameters move, the skip is counted
+    p_before = tr.ne.param_bucket.clone()
+    loss, _ = cfm.compute_loss(x1, mask, mu, spks, cond=cond)
+    loss.backward()
+    tr.ne.grad_bucket[0] = float("inf")
+    tr.micro = 1
+    tr.optimizer_step()
+    torch.cuda.synchronize()
+    assert tr.opt_state.tolist() == [2, 1] and int(tr.found_inf.item()) == 1
+    assert torch.equal(tr.ne.param_bucket, p_before)
+    scale0 = tr.ne.loss_scale
+    assert tr.poll_overflow() == 1 and tr.step_count == 2 and int(tr.found_inf.item()) == 0
+    assert tr.ne.loss_scale == max(1.0, scale0 * 0.5)
+    # resume: a fresh trainer with the saved optimiser state continues exactly like the original
+    sd_model = {k: v.clone() for k, v in model.state_dict().items()}
+    sd_opt = tr.state_dict()
+    torch.manual_seed(5)
+    tr.train_step(x1, mask, mu, spks, cond)
+    want = tr.ne.param_bucket.clone()
+    model2 = _model(seed=12)
+    model2.eval()
+    model2.load_state_dict(sd_model)
+    model2.flow.decoder.estimator.train()
+    tr2 = FlowLoRATrainer(model2.flow.decoder, lr=1e-3, warmup_steps=4, total_steps=20)
+    tr2.load_state_dict(sd_opt)
+    assert tr2.step_count == 2
+    torch.manual_seed(5)
+    tr2.train_step(x1, mask, mu, spks, cond)
+    assert torch.allclose(tr2.ne.param_bucket, want, rtol=1e-4, atol=1e-7), float((tr2.ne.param_bucket - want).abs().max())

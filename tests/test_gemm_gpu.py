@@ -38,7 +38,7 @@ def _desc(A, W, out, *, segs, R, nbatch=1, a_rows=None, dtype=torch.float16, **k
     d.n_valid = kw.get("n_valid", W.shape[0])
     d.alpha = kw.get("alpha", 1.0)
     d.act = kw.get("act", 0)
-    for name in ("bias", "aux_out", "mul_src", "rowmask", "resid"):
+    for name in ("bias", "aux_out", "mul_src", "rowmask", "resid", "gn_part"):
         t = kw.get(name)
         setattr(d, name, t.data_ptr() if t is not None else None)
     d.ld_aux = kw.get("ld_aux", 0)
@@ -153,3 +153,35 @@ def test_cluster_multicast_path_matches():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "not cluster_multicast"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,L", [(3, 77), (2, 400), (1, 1500), (5, 128)])
+def test_conv_k3_groupnorm_partials(B, L, dtype):
+    """GroupNorm statistics taken in the conv GEMM's epilogue (gn_part): Chan-merging the {n, mean, M2} partials of a
+    sample gives the biased mean / variance of the fp32 conv output over ALL L rows x 32 channels of each group
+    (what nn.GroupNorm(8, 256) reduces over, modules.py:60-73, padded positions included)."""
+    torch.manual_seed(1)
+    C_in, C_out = 256, 256
+    x = (torch.randn(B, L, C_in, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(C_out, 3 * C_in, device="cuda") * 0.05).to(dtype)
+    bias = torch.randn(C_out, device="cuda") * 2.0 + 3.0          # a large mean stresses the one-pass partials
+    out = torch.empty(B, L, C_out, device="cuda", dtype=dtype)
+    nsplit = 4 * ((L + 127) // 128)
+    part = torch.full((B, nsplit, C_out // 32, 3), float("nan"), device="cuda")
+    d = _desc(x, w, out, segs=[(0, t - 1, 0, C_in // 64) for t in range(3)], R=L, nbatch=B, dtype=dtype, bias=bias,
+              gn_part=part)
+    _run(d)
+    xp = torch.nn.functional.pad(x.float(), (0, 0, 1, 1))
+    cols = torch.cat([xp[:, t:t + L] for t in range(3)], dim=2)
+    ref = cols @ w.float().t() + bias
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=2e-2)
+    assert torch.isfinite(part).all()
+    n = part[..., 0].double()
+    assert torch.equal(n.sum(1), torch.full((B, 8), 32.0 * L, device="cuda", dtype=torch.float64))
+    mean = (n * part[..., 1].double()).sum(1) / n.sum(1)
+    m2 = part[..., 2].double().sum(1) + (n * (part[..., 1].double() - mean[:, None]) ** 2).sum(1)
+    var = m2 / n.sum(1)
+    g = ref.double().view(B, L, 8, 32)
+    assert torch.allclose(mean, g.mean(dim=(1, 3)), atol=2e-3, rtol=1e-3)
+    assert torch.allclose(var, g.var(dim=(1, 3), unbiased=False), rtol=3e-3)

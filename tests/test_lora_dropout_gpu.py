@@ -60,15 +60,17 @@ def test_lora_dropout_explicit_masks_vs_reference():
 
 
 def _host_keep(seed, n_tbs, rows, p):
-    """Replica of lora_keep() in csrc/lora.cu (splitmix64 finaliser over a flat (block, projection, token, feature) counter)."""
+    """Replica of lora_keep4() in csrc/lora_dropout.cu: one splitmix64 finaliser per (block, projection, token, feature
+    quad) counter; its four 16-bit fields decide the quad's four features (dropped iff field < round(p 2^16))."""
     with np.errstate(over="ignore"):
-        idx = np.arange(n_tbs * 3 * rows * 256, dtype=np.uint64)
+        idx = np.arange(n_tbs * 3 * rows * 64, dtype=np.uint64)
         z = np.uint64(seed) + (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z ^= z >> np.uint64(31)
-    thr = min(int(float(np.float32(p)) * 4294967296.0), 4294967295)
-    keep = ((z >> np.uint64(32)) >= np.uint64(thr)).astype(np.uint8)
+    thr = min(int(float(np.float32(p)) * 65536.0 + 0.5), 65535)
+    fields = np.stack([(z >> np.uint64(16 * j)) & np.uint64(0xFFFF) for j in range(4)], axis=1)     # [quads][4]
+    keep = (fields >= np.uint64(thr)).astype(np.uint8)
     return torch.from_numpy(keep.reshape(n_tbs, 3, rows, 256))
 
 
@@ -115,3 +117,41 @@ def test_lora_dropout_training_step_r16_bf16():
     # the whole step, mask hash and operand refresh included, is CUDA-graph capturable; masks advance per replay
     g_losses = [float(tr.train_step_graphed(c("x1"), c("mask"), c("mu"), c("spks"), c("cond"))) for _ in range(3)]
     assert all(np.isfinite(g_losses)) and int(tr.found_inf.item()) == 0
+
+
+def test_lora_dropout_300m_default_rate_vs_reference():
+    """300M estimator at the reference's default lora_dropout = 0.05 (config.py:207-216), preset masks: loss, the stored
+    gradients and every gradient norm of the real reference (fp16 operands: <= 1e-2)."""
+    dg = load_golden("dropout_c1")
+    fx = load_golden(dg["src"])
+    est, _, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8, lora_dropout=dg["p"])
+    est = est.cuda().train()
+    keep = dropout_masks(dg["n_tbs"], dg["rows"], dg["p"], dg["mask_seed"])
+    assert int(keep.sum()) == dg["keep_sum"]
+    loss, grads, _ = _run(fx, est, mask=keep)
+    assert abs(loss - float(dg["loss"])) <= 1e-2 * float(dg["loss"])
+    assert _rel(grads, dg["grads"]) <= 1e-2, _rel(grads, dg["grads"])
+    worst = max(abs(float(grads[k].norm()) - n) / (n + 1e-12) for k, n in dg["grad_norms"].items())
+    assert worst <= 2e-2, worst
+
+
+def test_lora_dropout_r16_explicit_masks_vs_oracle():
+    """Rank 16 (the reference's flow_lora rank) exercises the 48-value reduction of the fused LayerNorm + masked
+    down-projection kernel: CUDA path vs the CPU oracle on the same preset masks."""
+    from oracle import flow_oracle as O
+    from tests.helpers import attention_block_prefixes, lora_scaling_of, oracle_dropout_entries
+    fx = load_golden("train_tiny_prompt")
+    p = 0.2
+    est, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=16, lora_alpha=32, lora_dropout=p)
+    B, _, T = fx["x1"].shape
+    prefixes = attention_block_prefixes(fx["n_blocks"], fx["n_mid"])
+    keep = dropout_masks(len(prefixes), B * T, p, 77)
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    P.update(oracle_dropout_entries(keep, p, prefixes, B, T))
+    ref_loss, _, _ = O.cfm_compute_loss(P, fx["x1"], fx["mask"], fx["mu"], fx["spks"], fx["cond"], fx["prompt_lens"],
+                                        fx["t_rand"], fx["z"], fx["cfg_rand"], lora_scaling=lora_scaling_of(sd, alpha=32))
+    ref_loss.backward()
+    ref = {k: P[k].grad for k in P if k.endswith(("lora_A", "lora_B"))}
+    loss, grads, _ = _run(fx, est.cuda().train(), mask=keep)
+    assert abs(loss - float(ref_loss)) <= 1e-2 * float(ref_loss)
+    assert _rel(grads, ref) <= 1e-2, _rel(grads, ref)

@@ -18,7 +18,7 @@ def test_make_pad_mask_docstring_kat():
     assert b.tolist() == [0.0, -1.0e10]
 
 
-@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_prompt", "train_c1", "train_c1_prompt"])
+@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_prompt", "train_tiny_padprompt", "train_c1", "train_c1_prompt"])
 def test_train_step_matches_reference(name):
     fx = load_golden(name)
     est, sd, stats = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
@@ -100,3 +100,64 @@ def test_lora_dropout_matches_reference():
     far = sum((fx["grads"][k] - g).double().pow(2).sum() for k, g in dg["grads"].items())
     den = sum(g.double().pow(2).sum() for g in dg["grads"].values())
     assert float((far / den).sqrt()) > 0.1
+
+
+def test_padprompt_fixture_hits_the_padding():
+    """train_tiny_padprompt: the boundary window (25 frames after the prompt, weight 5) of two samples runs past their
+    length, so padded frames carry loss weight (reference flow_model.py:184-193 does not re-mask them)."""
+    fx = load_golden("train_tiny_padprompt")
+    w = O.cfm_loss_weights(fx["mask"], fx["prompt_lens"])
+    pad = fx["mask"] == 0
+    assert float(w[pad].sum()) > 0
+    assert float(w[1, 0, 40:55].min()) == 5.0 and float(w[0, 0, 50:64].min()) == 5.0 and float(w[0, 0, :50].max()) == 0.0
+
+
+def test_benchmarked_train_shape_matches_reference():
+    """The oracle at the BENCHMARKED shape (300M estimator, 32 x 400 ragged, bench.py's batch): loss and the stored
+    gradients of the real reference. This is also the workload `bench.py --impl reference` times."""
+    from tests.helpers import bench_train_inputs
+    fx = load_golden("train_c3")
+    _, sd, stats = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    assert abs(wsum(sd) - fx["wsum"]) <= 1e-6 * fx["wsum"]
+    x1, mask, mu, spks, cond, t_rand, z, cfg = bench_train_inputs(fx)
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    loss, y, _ = O.cfm_compute_loss(P, x1, mask, mu, spks, cond, None, t_rand, z, cfg, lora_scaling=lora_scaling_of(sd))
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+    loss.backward()
+    for k, g in fx["grads"].items():
+        assert torch.allclose(P[k].grad, g, atol=1e-6 + 1e-3 * float(g.abs().max()), rtol=1e-3), k
+    worst = max(abs(float(P[k].grad.norm()) - n) / (n + 1e-12) for k, n in fx["grad_norms"].items())
+    assert worst <= 2e-3, worst
+
+
+def test_benchmarked_euler_shape_matches_reference():
+    """configs[1]: 10 Euler steps + CFG at T = 700 with a 200-frame prompt."""
+    from tests.helpers import bench_euler_inputs
+    fx = load_golden("euler_c2")
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"])
+    mu, spks, cond, mask, z = bench_euler_inputs(fx)
+    with torch.no_grad():
+        mel, cache = O.cfm_forward(sd, mu, mask, fx["n_steps"], z.clone(), spks, cond, prompt_len=fx["prompt"])
+    assert cache.shape == fx["cache"].shape and torch.equal(cache, fx["cache"])
+    assert torch.allclose(mel, fx["mel"], atol=2e-3, rtol=1e-3)
+
+
+def test_lora_dropout_300m_matches_reference():
+    """300M-scale lora_dropout fixture at the reference's default p = 0.05 (config.py:207-216)."""
+    from tests.helpers import attention_block_prefixes, dropout_masks, oracle_dropout_entries
+    dg = load_golden("dropout_c1")
+    fx = load_golden(dg["src"])
+    _, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    B, _, T = fx["x1"].shape
+    keep = dropout_masks(dg["n_tbs"], dg["rows"], dg["p"], dg["mask_seed"])
+    assert int(keep.sum()) == dg["keep_sum"]
+    P = {k: v.clone().requires_grad_(k.endswith(("lora_A", "lora_B"))) for k, v in sd.items()}
+    P.update(oracle_dropout_entries(keep, dg["p"], attention_block_prefixes(fx["n_blocks"], fx["n_mid"]), B, T))
+    loss, _, _ = O.cfm_compute_loss(P, fx["x1"], fx["mask"], fx["mu"], fx["spks"], fx["cond"], fx["prompt_lens"],
+                                    fx["t_rand"], fx["z"], fx["cfg_rand"], lora_scaling=lora_scaling_of(sd))
+    assert abs(float(loss) - float(dg["loss"])) <= 1e-5 * abs(float(dg["loss"]))
+    loss.backward()
+    for k, g in dg["grads"].items():
+        assert torch.allclose(P[k].grad, g, atol=1e-6 + 1e-3 * float(g.abs().max()), rtol=1e-3), k
+    worst = max(abs(float(P[k].grad.norm()) - n) / (n + 1e-12) for k, n in dg["grad_norms"].items())
+    assert worst <= 2e-3, worst

@@ -26,7 +26,7 @@ def _step(fx, dtype):
     return loss.item(), y.cpu(), grads, est
 
 
-@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_prompt", "train_c1", "train_c1_prompt"])
+@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_prompt", "train_tiny_padprompt", "train_c1", "train_c1_prompt"])
 def test_train_step_fp16(name):
     fx = load_golden(name)
     loss, y, grads, est = _step(fx, torch.float16)
@@ -52,8 +52,87 @@ def test_train_step_bf16_noise_floor():
     assert abs(loss - float(fx["loss"])) <= 1e-2 * float(fx["loss"])
     num = sum((grads[k] - g).double().pow(2).sum() for k, g in fx["grads"].items())
     den = sum(g.double().pow(2).sum() for g in fx["grads"].values())
-    # the reference's own bf16 autocast sits at 1.6e-2 rel-L2 vs its fp32
-    assert float((num / den).sqrt()) <= 6e-2
+    # the reference's own bf16 autocast sits at 1.6e-2 rel-L2 vs its fp32 at this shape:
+    # bf16 operands are held to 1.5x the reference's own floor
+    rel = float((num / den).sqrt())
+    print("train_c1 bf16: LoRA-grad bucket rel-L2 %.3e (reference under bf16 autocast: 1.6e-2)" % rel)
+    assert rel <= 1.5 * 1.6e-2, rel
+
+
+# ------------------------------------------------------------------------------------------------------
+# The BENCHMARKED shape: 300M estimator, 32 x 400 ragged frames (bench.py's batch, seed 99), against the real
+# reference's fp32 step (tests/golden/train_c3.pt; inputs regenerated from the seeds and checksum-verified).
+# ------------------------------------------------------------------------------------------------------
+def _bench_step(fx, dtype, graphed):
+    from cosyvoice_lora_finetune_framework_b200.flow_model import ConditionalCFM
+    from tests.helpers import bench_train_inputs
+    x1, mask, mu, spks, cond, t_rand, z, cfg = (v.cuda() for v in bench_train_inputs(fx))
+    est, sd, _ = build_estimator(fx["n_blocks"], fx["n_mid"], lora_r=8)
+    est = est.cuda().train()
+    est.cvflow_dtype = dtype
+    cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
+    t = 1 - torch.cos(t_rand * 0.5 * 3.14159265359)
+    keep = cfg > 0.2
+
+    def body():
+        loss, _ = cfm._loss_with_noise(x1, mask, mu, spks, cond, None, t, z, keep)
+        loss.backward()
+        return loss.detach()
+
+    if not graphed:
+        loss = body()
+    else:       # the same launches captured into one CUDA graph and replayed (the form bench.py times)
+        from cosyvoice_lora_finetune_framework_b200 import _estimator as E
+        ne = E.native_of(est)
+        ne.attach_grads()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ne.grad_bucket.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = body()
+        ne.grad_bucket.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu().clone() for k, p in est.named_parameters() if p.requires_grad}
+    return float(loss), grads
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_benchmarked_shape_fp16(graphed):
+    from tests.helpers import grad_errors
+    fx = load_golden("train_c3")
+    loss, grads = _bench_step(fx, torch.float16, graphed)
+    ref = float(fx["loss"])
+    e = grad_errors(grads, fx["grads"])
+    worst = max(abs(float(grads[k].norm()) - n) / (n + 1e-12) for k, n in fx["grad_norms"].items())
+    print("train_c3 fp16 graphed=%s: loss rel %.2e, %s, worst norm rel %.2e" % (graphed, abs(loss - ref) / ref, e, worst))
+    assert abs(loss - ref) <= 1e-2 * ref, (loss, ref)
+    assert e["bucket_rel_l2"] <= 1e-2, e
+    assert worst <= 2e-2, worst
+    tot = float(torch.sqrt(sum(g.double().pow(2).sum() for g in grads.values())))
+    assert abs(tot - fx["grad_total_norm"]) <= 1e-2 * fx["grad_total_norm"]
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_benchmarked_shape_bf16(graphed):
+    """bf16 operands (the dtype bench.py runs): loss <= 1e-2; LoRA gradients within 1.5x the error the REFERENCE ITSELF
+    makes under bf16 autocast at this exact shape (recorded in the fixture from the real reference: bucket rel-L2
+    1.3e-2, per-tensor max 3.9e-2), because bf16's 8-bit mantissa puts the reference's own gradients above 1e-2."""
+    from tests.helpers import grad_errors
+    fx = load_golden("train_c3")
+    floor = fx["ref_autocast"]["bf16"]
+    loss, grads = _bench_step(fx, torch.bfloat16, graphed)
+    ref = float(fx["loss"])
+    e = grad_errors(grads, fx["grads"])
+    print("train_c3 bf16 graphed=%s: loss rel %.2e, %s; reference's own bf16 floor %s" % (graphed, abs(loss - ref) / ref, e, floor))
+    assert abs(loss - ref) <= 1e-2 * ref, (loss, ref)
+    assert e["bucket_rel_l2"] <= 1.5 * floor["bucket_rel_l2"], (e, floor)
+    assert e["tensor_rel_l2_max"] <= 1.5 * floor["tensor_rel_l2_max"], (e, floor)
 
 
 def test_grad_accumulation_and_generic_autograd():
