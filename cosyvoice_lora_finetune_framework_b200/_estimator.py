@@ -54,6 +54,10 @@ def _lib():
         L.cvflow_set_lora_dropout.argtypes = [vp, f, C.c_uint64, vp, i64]
         L.cvflow_lora_dropout_seed.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cvflow_optim_advance.argtypes = [vp, vp, vp, vp, f, f, i32, i32, f, f, f, vp]
+        L.cvflow_solve_capture.argtypes = [vp, i32, i32, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.cvflow_solve_replay.argtypes = [vp, i32, i32, vp]
+        L.cvflow_solve_release.argtypes = [vp]
+        L.cvflow_time_embed.argtypes = [vp, vp, i32, vp, vp, i32, vp]
         L.cvflow_launch_count.argtypes = [vp]
         L.cvflow_launch_count.restype = i64
         L.cvflow_cfm_prep.argtypes = [vp, vp, vp, vp, i32, i32, f, vp]
@@ -470,6 +474,16 @@ class NativeEstimator:
         io.out = out.data_ptr()
         io.B, io.T, io.iso_len, io.training = B, T, int(iso_len), int(training)
         N.check(self.L.cvflow_estimator_forward(self.handle, C.byref(io), _stream()), "cvflow_estimator_forward")
+        return out
+
+    def time_embed(self, t):
+        """time_mlp(SinusoidalPosEmb(t)) [B][1024] through cvflow_time_embed (modules.py:27-57)."""
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        B = t.shape[0]
+        out = torch.empty(B, 1024, device=self.device, dtype=torch.float32)
+        scratch = torch.empty(B * 1344, device=self.device, dtype=torch.float32)
+        N.check(self.L.cvflow_time_embed(self.handle, t.data_ptr(), B, out.data_ptr(), scratch.data_ptr(), B, _stream()),
+                "cvflow_time_embed")
         return out
 
     def backward(self, dpred16, grad_scale=1.0, grad_scale_dev=None, input_grads=None):

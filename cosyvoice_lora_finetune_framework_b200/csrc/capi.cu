@@ -135,6 +135,28 @@ extern "C" CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, 
   if (!h) { set_error("cvflow_set_lora_dropout: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->set_lora_dropout(p, (unsigned long long)seed, debug_mask, (long)debug_rows) ? CVFLOW_ERR_ARG : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_solve_capture(cvflow_estimator* h, int32_t T, int32_t n_steps, float cfg_rate, float* x,
+                                               const float* mask, const float* mu, const float* spks, const float* cond,
+                                               const float* t, const float* dt, float* d_scratch, void* stream) {
+  if (!h) { set_error("cvflow_solve_capture: null handle"); return CVFLOW_ERR_ARG; }
+  if (!stream) { set_error("cvflow_solve_capture: stream capture needs a non-default stream"); return CVFLOW_ERR_ARG; }
+  return h->e->solve_capture(T, n_steps, cfg_rate, x, mask, mu, spks, cond, t, dt, d_scratch, (cudaStream_t)stream)
+             ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_solve_replay(cvflow_estimator* h, int32_t T, int32_t n_steps, void* stream) {
+  if (!h) { set_error("cvflow_solve_replay: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->solve_replay(T, n_steps, (cudaStream_t)stream) ? CVFLOW_ERR_ARG : CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_solve_release(cvflow_estimator* h) {
+  if (!h) { set_error("cvflow_solve_release: null handle"); return CVFLOW_ERR_ARG; }
+  h->e->solve_release();
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API int cvflow_time_embed(cvflow_estimator* h, const float* t, int32_t t_nb, float* out, float* scratch,
+                                            int32_t B, void* stream) {
+  if (!h || !t || !out || !scratch || B < 1 || t_nb < 1) { set_error("cvflow_time_embed: null/invalid argument"); return CVFLOW_ERR_ARG; }
+  return h->e->time_embed(t, t_nb, out, scratch, B, (cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int cvflow_lora_dropout_seed(cvflow_estimator* h, uint64_t* out, const uint64_t* in) {
   if (!h) { set_error("cvflow_lora_dropout_seed: null handle"); return CVFLOW_ERR_ARG; }
   unsigned long long o = 0ull, i = in ? (unsigned long long)*in : 0ull;

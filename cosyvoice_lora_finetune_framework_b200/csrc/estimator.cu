@@ -54,6 +54,102 @@ Estimator::~Estimator() {
   if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_done_[0]); cudaEventDestroy(ev_done_[1]); }
   if (lora_table_dev_) cudaFree(lora_table_dev_);
   if (drop_seed_dev_) cudaFree(drop_seed_dev_);
+  solve_release();
+  if (solve_keep_dev_) cudaFree(solve_keep_dev_);
+}
+
+// ------------------------------------------------------------------------------------------
+// Euler solve as one CUDA graph (reference flow_model.py:94-125; the reference's own precedent for a non-PyTorch
+// estimator is the TensorRT hook of cosyvoice/flow/flow_matching.py:125-152, which this entry point stands in for)
+// ------------------------------------------------------------------------------------------
+void Estimator::solve_release() {
+  for (auto& kv : solves_) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  solves_.clear();
+}
+int Estimator::solve_capture(int T, int n_steps, float cfg_rate, float* x, const float* mask, const float* mu,
+                             const float* spks, const float* cond, const float* t_arr, const float* dt_arr, float* d_scratch,
+                             cudaStream_t st) {
+  if (T < 1 || n_steps < 1 || !x || !mask || !mu || !t_arr || !dt_arr || !d_scratch) {
+    set_error("solve_capture: null/invalid argument");
+    return -1;
+  }
+  {
+    auto it = solves_.find({T, n_steps});
+    if (it != solves_.end()) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      if (it->second.graph) cudaGraphDestroy(it->second.graph);
+      solves_.erase(it);
+    }
+  }
+  if (!solve_keep_dev_) {
+    const float keep[2] = {1.f, 0.f};
+    if (cudaMalloc(&solve_keep_dev_, sizeof(keep)) != cudaSuccess ||
+        cudaMemcpy(solve_keep_dev_, keep, sizeof(keep), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("solve_capture: cudaMalloc/cudaMemcpy(keep) failed");
+      return -1;
+    }
+  }
+  auto io_at = [&](int k) {
+    EstimatorIO io{};
+    io.x = x; io.x_nb = 1; io.mask = mask; io.mask_nb = 1; io.mu = mu; io.mu_nb = 1; io.t = t_arr + k; io.t_nb = 1;
+    io.spks = spks; io.spks_nb = 1; io.cond = cond; io.cond_nb = 1; io.keep = solve_keep_dev_; io.out = d_scratch;
+    io.B = 2; io.T = T; io.iso_len = 0; io.training = 0;
+    return io;
+  };
+  // warm-up outside the capture: builds the launch plan (tensor maps, function attributes) for (2, T, eval); writes only d
+  if (forward(io_at(0), st)) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("solve_capture: warm-up forward failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    set_error("solve_capture: cudaStreamBeginCapture failed (a non-default stream is required): %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  int rc = 0;
+  for (int k = 0; k < n_steps && rc == 0; ++k) {
+    rc = forward(io_at(k), st);
+    if (rc == 0) {
+      const int r = launch_euler_update(x, d_scratch, dt_arr, k, cfg_rate, 80L * T, st);
+      if (r) { set_error("solve_capture: euler update launch failed: %s", cudaGetErrorString((cudaError_t)(-r))); rc = -1; }
+      ++launches_;
+    }
+  }
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  if (rc != 0 || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    if (rc == 0) set_error("solve_capture: cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  cudaGraphExec_t ex = nullptr;
+  if (cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+    set_error("solve_capture: cudaGraphInstantiate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaGraphDestroy(g);
+    return -1;
+  }
+  solves_[{T, n_steps}] = SolveGraph{g, ex};
+  return 0;
+}
+int Estimator::solve_replay(int T, int n_steps, cudaStream_t st) {
+  auto it = solves_.find({T, n_steps});
+  if (it == solves_.end()) { set_error("solve_replay: no captured solve for T=%d, n_steps=%d (call cvflow_solve_capture first)", T, n_steps); return -1; }
+  const cudaError_t e = cudaGraphLaunch(it->second.exec, st);
+  if (e != cudaSuccess) { set_error("solve_replay: cudaGraphLaunch failed: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+int Estimator::time_embed(const float* t, int t_nb, float* out, float* scratch, int B, cudaStream_t st) {
+  dry_ = false; missing_ = false;
+  float* emb = scratch;
+  float* te1 = scratch + (long)B * 320;
+  CKL(launch_sinus_embed(t, t_nb, emb, B, st));
+  CKL(launch_small_linear(emb, (const float*)get("time.w1", 2, 1024L * 320), (const float*)get("time.b1", 2, 1024), te1, B, 320,
+                          1024, 0, 1, st));
+  CKL(launch_small_linear(te1, (const float*)get("time.w2", 2, 1024L * 1024), (const float*)get("time.b2", 2, 1024), out, B, 1024,
+                          1024, 0, 0, st));
+  if (missing_) return -1;
+  launches_ += 3;
+  return 0;
 }
 
 int Estimator::set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows) {
@@ -491,6 +587,7 @@ long Estimator::workspace_bytes(int B, int T, int training) {
 
 int Estimator::forward(const EstimatorIO& io, cudaStream_t st) {
   if (!ws_) { set_error("estimator: no workspace set"); return -1; }
+  if (io.T > 4096) { set_error("estimator: T = %d frames exceeds the supported 4096 (GroupNorm partial table)", io.T); return -1; }
   if (!lora_table_ready_) { set_error("estimator: call cvflow_lora_refresh before the first forward"); return -1; }
   stream_ = st;
   dry_ = false; missing_ = false; oom_ = false;

@@ -81,6 +81,16 @@ class Estimator {
   // lora_dropout p of the q/k/v LoRA branches in training forwards (0 = off: B A is folded into the GEMM operand);
   // dbg_mask: optional explicit keep masks [n_tbs][3][dbg_rows][256] bytes for parity tests (dbg_rows must be B*T)
   int set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows);
+  // N-step CFG Euler solve (flow_model.py:94-125) captured ONCE into a CUDA graph owned by the handle and replayed:
+  // per step one batch-2 (cond / uncond) estimator forward + the guidance / Euler update. All pointers are the caller's
+  // static device buffers; `stream` must be a capturing-capable (non-legacy) stream. The workspace for (B=2, T,
+  // training=0) must have been set.
+  int solve_capture(int T, int n_steps, float cfg_rate, float* x, const float* mask, const float* mu, const float* spks,
+                    const float* cond, const float* t_arr, const float* dt_arr, float* d_scratch, cudaStream_t st);
+  int solve_replay(int T, int n_steps, cudaStream_t st);
+  void solve_release();     // drops every captured solve
+  // t [t_nb] -> time_mlp(SinusoidalPosEmb(t)) [B][1024] (modules.py:27-57); scratch: B * (320 + 1024) floats
+  int time_embed(const float* t, int t_nb, float* out, float* scratch, int B, cudaStream_t st);
   // device-resident seed of the mask hash (advanced by every training forward): read / overwrite (host-synchronous)
   int lora_dropout_seed(unsigned long long* out, const unsigned long long* in);
   long launches() const { return launches_; }
@@ -145,6 +155,9 @@ class Estimator {
   cudaEvent_t ev_fork_ = nullptr, ev_done_[2] = {nullptr, nullptr};
   bool ev_done_valid_[2] = {false, false};
   bool wgrad_side_ = false;  // CVFLOW_WGRAD_SIDE=1 (measured: no gain over PDL-chained launches on one stream)
+  struct SolveGraph { cudaGraph_t graph; cudaGraphExec_t exec; };
+  std::map<std::pair<int, int>, SolveGraph> solves_;   // (T, n_steps) -> captured solve
+  float* solve_keep_dev_ = nullptr;     // {1, 0}: CFG keep factors of the (cond, uncond) rows
   float drop_p_ = 0.f;
   unsigned long long* drop_seed_dev_ = nullptr;
   const uint8_t* drop_dbg_ = nullptr;

@@ -73,7 +73,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   constexpr int kSliceRows = BM / CL;
-  long long* dbg = p.dbg ? p.dbg + (long)blockIdx.x * 8 : nullptr;
+  long long* dbg = p.dbg ? p.dbg + (long)blockIdx.x * 16 : nullptr;
   auto stamp = [&](int k) {
     if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
   };
@@ -200,6 +200,32 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       __syncwarp();
       if (lane == 0) { tma_store_3d(tm, stg, col, row0, b); tma_store_commit(); }
     };
+    // epi_direct: the warp's 32 x 64-byte slice is transposed through the staging tile (row-wise st.shared.v4, then
+    // ld.shared.v4 with lane -> (row i*8 + lane/4, 16-byte unit lane%4)) and leaves as st.global.v4 that cover 8 rows x 64
+    // contiguous bytes per instruction: 8 L1 wavefronts instead of 32, and no TMA round trip between chunks (the
+    // 2 KB TMA stores made the epilogue a chain of ~1 us store latencies: 2.2 us per 128x128 tile against 0.9 us of MMA).
+    auto lds_unit = [&](int r, int u) {
+      uint4 v;
+      const uint32_t addr = stg + (uint32_t)r * 64u + (uint32_t)((u ^ ((r >> 1) & 3)) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
+    // rows of this warp's slice: slice row r <-> tile row q*32 + r; writes 64 bytes per valid row at byte offset col_bytes
+    auto store_slice = [&](void* base, long ld_bytes, long col_bytes, int b, int i0) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2), u = lane & 3;
+        const uint4 v = lds_unit(r, u);
+        const int ii = i0 + q * 32 + r;
+        const int orow = ii * p.rmul + p.roff;
+        if (ii < p.R && orow < p.out_rows) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(base) + ((long)b * p.out_rows + orow) * ld_bytes + col_bytes + u * 16;
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
+      }
+      __syncwarp();   // the staging tile may be overwritten
+    };
     int it = 0;
     for (int st = cluster_id; st < total_super; st += n_clusters, ++it) {
       const int acc = it & 1;
@@ -244,6 +270,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         __syncwarp();
         tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
         tmem_ld_wait();
+        if (it == 0 && threadIdx.x == 64) stamp(cc == 0 ? 8 : 11);
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
@@ -277,14 +304,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             o[0] = cnt; o[1] = mean; o[2] = cnt > 0.f ? fmaxf(s2 - s1 * mean, 0.f) : 0.f;
           }
         }
-        if (p.tma_out && is_gelu && p.aux_out) {   // pre-activation stash through the staging tile
+        if (p.epi_direct && is_gelu && p.aux_out) {   // pre-activation stash through the staging tile
+          stage_h16(x);
+          store_slice(p.aux_out, p.ld_aux * 2, (long)nn * 2, b, i0);
+        } else if (p.tma_out && is_gelu && p.aux_out) {
           stage_release();
           stage_h16(x);
           stage_store(&p.tmAux, nn, i0 + q * 32, b);
         }
-        if (valid || p.tma_out) {
+        if (valid || p.tma_out || p.epi_direct) {
           if (is_gelu) {
-            if (p.aux_out && !p.tma_out) {
+            if (p.aux_out && !p.tma_out && !p.epi_direct) {
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.aux_out) + frow * p.ld_aux + nn);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
@@ -328,7 +358,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             }
           }
           if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
-          if (p.tma_out) {
+          if (it == 0 && threadIdx.x == 64 && cc == 0) stamp(9);
+          if (p.epi_direct == 2) {
+            // diagnostic build of the launch (CVFLOW_GEMM_EPI=2): no stores at all
+          } else if (p.epi_direct) {
+            if (p.out_f32) {   // two passes of 16 columns (64 bytes per row) through the 2 KB staging tile
+              stage_f32_half(x);
+              store_slice(p.out, p.ldc * 4, (long)(p.col_off + nn) * 4, b, i0);
+              stage_f32_half(x + 16);
+              store_slice(p.out, p.ldc * 4, (long)(p.col_off + nn + 16) * 4, b, i0);
+            } else {
+              stage_h16(x);
+              store_slice(p.out, p.ldc * 2, (long)(p.col_off + nn) * 2, b, i0);
+            }
+          } else if (p.tma_out) {
             if (p.out_f32) {   // two passes of 16 columns through the 2 KB staging tile
               stage_release();
               stage_f32_half(x);
@@ -357,11 +400,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
           }
+          if (it == 0 && threadIdx.x == 64) stamp(cc == 0 ? 10 : 12);
         }
       }
       // all of this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+      if (it == 0 && threadIdx.x == 64) stamp(13);
       if (threadIdx.x == 64) { stamp(5); if (dbg) dbg[7] = it + 1; }
     }
   }
@@ -533,7 +578,17 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   if (!use1) p->tmA[1] = p->tmA[0];
   // output tensor maps for the TMA-store epilogue: rows i -> i*rmul + roff as a strided row view
   p->tma_out = 0;
-  if (!a.transposed_out) {
+  p->epi_direct = 0;
+  static int epi_env = -1;
+  if (epi_env < 0) { const char* e = getenv("CVFLOW_GEMM_EPI"); epi_env = e ? atoi(e) : 0; }   // measured on B200: the TMA-store epilogue is faster (q/k/v 10.2 vs 12.5 us)
+  if (!a.transposed_out && epi_env >= 1) {
+    const int esz = p->out_f32 ? 4 : 2;
+    const bool ok = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && ((a.ldc * esz) % 16 == 0) &&
+                    (!a.aux_out || (((reinterpret_cast<uintptr_t>(a.aux_out) & 15) == 0) && (a.ld_aux % 8 == 0)));
+    if (a.aux_out && (a.rmul != 1 || a.roff != 0)) GEMM_FAIL("gemm: aux_out needs contiguous output rows");
+    p->epi_direct = ok ? epi_env : 0;
+  }
+  if (!a.transposed_out && !p->epi_direct) {
     const int esz = p->out_f32 ? 4 : 2;
     long rows_view = (a.out_rows - a.roff + a.rmul - 1) / a.rmul;
     if (rows_view > a.R) rows_view = a.R;

@@ -72,7 +72,8 @@ struct alignas(64) GemmParams {
   CUtensorMap tmW;
   CUtensorMap tmOut;    // row-major output, box {32 cols, 32 rows, 1} (TMA store from the epilogue)
   CUtensorMap tmAux;    // pre-activation stash, same box
-  int tma_out;          // 1: epilogue stores through TMA
+  int tma_out;          // 1: epilogue stores through TMA (CVFLOW_GEMM_EPI=0: the round-1 path, kept for A/B timing)
+  int epi_direct;       // 1: epilogue stores as coalesced st.global.v4 after a transposition through the staging tile
   GemmSeg seg[8];
   int nseg, nkb_total;
   int bf16;

@@ -125,27 +125,36 @@ __device__ __forceinline__ float mish_grad_fast(float x) {
   return tsp + x * sig * (1.f - tsp * tsp);
 }
 
-// merge the partials of (sample b, group = threadIdx.x < 8) into sm[g] = {mean, rstd}; call with all threads, then sync
-__device__ __forceinline__ void gn_merge_to_smem(const float* __restrict__ partials, int b, int nsplit, float (*sm)[2]) {
+// merge the partials of sample b into sm[g] = {mean, rstd}: the {n, mean, M2} triples are fetched by all threads in
+// parallel (one L2 round trip instead of a dependent chain of nsplit of them), then 8 threads run the Chan merge from
+// shared memory. Call with all 256 threads; ends with a __syncthreads.
+static constexpr int kGnMaxSplits = 128;   // 4 * ceil(L / 128): L <= 4096
+__device__ __forceinline__ void gn_merge_to_smem(const float* __restrict__ partials, int b, int nsplit, float (*part)[3],
+                                                 float (*sm)[2]) {
+  for (int i = threadIdx.x; i < nsplit * 8; i += blockDim.x) {
+    const float* p = partials + ((long)b * nsplit * 8 + i) * 3;
+    part[i][0] = p[0]; part[i][1] = p[1]; part[i][2] = p[2];
+  }
+  __syncthreads();
   if (threadIdx.x < 8) {
     const int g = threadIdx.x;
     float n = 0.f, mu = 0.f, m2 = 0.f;
     for (int s = 0; s < nsplit; ++s) {
-      const float* p = partials + (((long)b * nsplit + s) * 8 + g) * 3;
-      const float nb = p[0];
+      const float nb = part[s * 8 + g][0];
       if (nb <= 0.f) continue;
-      const float delta = p[1] - mu;
+      const float delta = part[s * 8 + g][1] - mu;
       const float nn = n + nb;
       mu += delta * nb / nn;
-      m2 += p[2] + delta * delta * n * nb / nn;
+      m2 += part[s * 8 + g][2] + delta * delta * n * nb / nn;
       n = nn;
     }
     sm[g][0] = mu;
     sm[g][1] = rsqrtf(m2 / n + 1e-5f);
   }
+  __syncthreads();
 }
 
-static constexpr int kGnRows = 32;   // rows of one sample per CTA (8 warps x 4 rows)
+static constexpr int kGnRows = 16;   // rows of one sample per CTA (8 warps x 2 rows, both rows' loads in flight together)
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restrict__ c, const float* __restrict__ partials,
                                                        int nsplit, float* __restrict__ stats,
@@ -154,11 +163,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
                                                        const uint16_t* __restrict__ add16, void* __restrict__ out, int mode,
                                                        int L, int bf) {
   __shared__ float sm[8][2];
+  __shared__ float part[kGnMaxSplits * 8][3];
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.y;
-  gn_merge_to_smem(partials, b, nsplit, sm);
-  __syncthreads();
+  gn_merge_to_smem(partials, b, nsplit, part, sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c8 = lane * 8, grp = lane >> 2;
   const float mean = sm[grp][0], rstd = sm[grp][1];
@@ -173,14 +182,25 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
   for (int k = 0; k < 8; ++k) { sc[k] *= rstd; sh[k] -= mean * sc[k]; }
   if (mode == 0 && tb) load8_f32(tb + (long)b * tb_stride + c8, t8);
   const int l0 = blockIdx.x * kGnRows;
+  constexpr int NR = kGnRows / 8;
+  uint4 cv[NR], av[NR];
+  float m[NR];
+  long row[NR];
 #pragma unroll
-  for (int r = 0; r < kGnRows / 8; ++r) {
+  for (int r = 0; r < NR; ++r) {        // every load of the CTA's rows is issued before any of the math
     const int l = l0 + r * 8 + warp;
-    if (l >= L) break;
-    const long row = (long)b * L + l;
-    const float m = mask[row];
+    row[r] = l < L ? (long)b * L + l : -1;
+    if (row[r] >= 0) {
+      cv[r] = *reinterpret_cast<const uint4*>(c + row[r] * 256 + c8);
+      m[r] = mask[row[r]];
+      if (mode != 0) av[r] = *reinterpret_cast<const uint4*>(add16 + row[r] * 256 + c8);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if (row[r] < 0) continue;
     float x[8];
-    load8_h16(c + row * 256 + c8, bf, x);
+    unpack8_h16(cv[r], bf, x);
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = mish_fast(x[k] * sc[k] + sh[k]);
     if (mode == 0) {
@@ -189,14 +209,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint16_t* __restric
         for (int k = 0; k < 8; ++k) x[k] += t8[k];
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] *= m;
-      store8_h16(reinterpret_cast<uint16_t*>(out) + row * 256 + c8, bf, x);
+      for (int k = 0; k < 8; ++k) x[k] *= m[r];
+      store8_h16(reinterpret_cast<uint16_t*>(out) + row[r] * 256 + c8, bf, x);
     } else {
       float a[8];
-      load8_h16(add16 + row * 256 + c8, bf, a);
+      unpack8_h16(av[r], bf, a);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = x[k] * m + a[k];
-      store8_f32(reinterpret_cast<float*>(out) + row * 256 + c8, x);
+      for (int k = 0; k < 8; ++k) x[k] = x[k] * m[r] + a[k];
+      store8_f32(reinterpret_cast<float*>(out) + row[r] * 256 + c8, x);
     }
   }
 }
@@ -284,13 +304,16 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
   __shared__ float sm[8][2];
   pdl_wait();
   pdl_launch();
+  __shared__ float part[64 * 8][2];
   const int b = blockIdx.y;
-  if (threadIdx.x < 8) {      // group means of dxhat and dxhat * xhat from the split partials, once per CTA
+  for (int i = threadIdx.x; i < nsplit * 8; i += blockDim.x) {   // all split partials in one L2 round trip
+    const float* pp = partials + ((long)b * nsplit * 8 + i) * 2;
+    part[i][0] = pp[0]; part[i][1] = pp[1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {      // group means of dxhat and dxhat * xhat, fixed summation order
     float m1 = 0.f, m2 = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) {
-      const float* pp = partials + (((long)b * nsplit + sp) * 8 + threadIdx.x) * 2;
-      m1 += pp[0]; m2 += pp[1];
-    }
+    for (int sp = 0; sp < nsplit; ++sp) { m1 += part[sp * 8 + threadIdx.x][0]; m2 += part[sp * 8 + threadIdx.x][1]; }
     sm[threadIdx.x][0] = m1 * inv_n; sm[threadIdx.x][1] = m2 * inv_n;
   }
   __syncthreads();
@@ -303,13 +326,14 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
 #pragma unroll
   for (int r = 0; r < kGnRows / 8; ++r) {
     const int l = l0 + r * 8 + warp;
-    if (l >= L) break;
-    const long row = (long)b * L + l;
-    float xh[8], dxh[8];
-    gn_bwd_load(dy, dy_f32, c, k, mask[row], row * 256 + c8, bf, xh, dxh);
+    if (l < L) {
+      const long row = (long)b * L + l;
+      float xh[8], dxh[8];
+      gn_bwd_load(dy, dy_f32, c, k, mask[row], row * 256 + c8, bf, xh, dxh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dxh[i] = k.a1[i] * (dxh[i] - m1 - xh[i] * m2);
-    store8_h16(dc + row * 256 + c8, bf, dxh);
+      for (int i = 0; i < 8; ++i) dxh[i] = k.a1[i] * (dxh[i] - m1 - xh[i] * m2);
+      store8_h16(dc + row * 256 + c8, bf, dxh);
+    }
   }
 }
 int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stats, const float* gamma,

@@ -218,7 +218,7 @@ class ConditionalCFM(nn.Module):
                       mask=torch.empty(1, T, device=dev), spks=torch.zeros(1, 80, device=dev),
                       cond=torch.zeros(1, 80, T, device=dev), t=torch.empty(n_steps, device=dev),
                       dt=torch.empty(n_steps, device=dev), d=torch.empty(2, 80, T, device=dev),
-                      keep=torch.tensor([1.0, 0.0], device=dev), graph=None)
+                      keep=torch.tensor([1.0, 0.0], device=dev))
         st["x"].copy_(x.float())
         st["mu"].copy_(mu.float())
         st["mask"].copy_(mask.float().reshape(1, T))
@@ -228,7 +228,7 @@ class ConditionalCFM(nn.Module):
         st["dt"].copy_(dt_arr)
         L = E._lib()
 
-        def run():
+        def run():      # eager form: 2 launches of the C ABI per step
             for k in range(n_steps):
                 ne.forward(st["x"], st["mask"], st["mu"], st["t"][k:k + 1], st["spks"], st["cond"], keep=st["keep"],
                            iso_len=0, training=False, B=2, out=st["d"])
@@ -237,20 +237,30 @@ class ConditionalCFM(nn.Module):
 
         if not self.use_cuda_graph:
             run()
-        elif st["graph"] is None:
-            x0 = st["x"].clone()
-            run()                                  # warm-up: builds plans, workspace, function attributes
-            torch.cuda.synchronize()
-            st["x"].copy_(x0)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                run()
-            st["graph"] = g
-            self._graphs[key] = st
-            st["x"].copy_(x0)
-            g.replay()
         else:
-            st["graph"].replay()
+            # The whole N-step solve is ONE CUDA graph built and owned by the library (cvflow_solve_capture /
+            # cvflow_solve_replay): any binder of the C ABI gets the same graph-replayed solve, no Python in the loop.
+            # The handle keeps one captured solve per (T, n_steps); they share the workspace arena (every solve writes
+            # what it reads), so they stay valid until the arena is re-allocated.
+            ne.sync_lora()
+            ne._workspace(2, T, False)
+            if getattr(ne, "_solve_ws", None) != ne.ws.data_ptr():
+                N.check(L.cvflow_solve_release(ne.handle), "cvflow_solve_release")
+                ne._solve_ws, ne._solve_keys = ne.ws.data_ptr(), {}
+            if ne._solve_keys.get((T, n_steps)) != id(st):
+                x0 = st["x"].clone()
+                cap = torch.cuda.Stream(device=dev)            # capture needs a non-default stream
+                cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cap):
+                    N.check(L.cvflow_solve_capture(ne.handle, T, n_steps, float(self.inference_cfg_rate), st["x"].data_ptr(),
+                                                   st["mask"].data_ptr(), st["mu"].data_ptr(), st["spks"].data_ptr(),
+                                                   st["cond"].data_ptr(), st["t"].data_ptr(), st["dt"].data_ptr(),
+                                                   st["d"].data_ptr(), C.c_void_p(cap.cuda_stream)), "cvflow_solve_capture")
+                torch.cuda.current_stream().wait_stream(cap)
+                st["x"].copy_(x0)
+                ne._solve_keys[(T, n_steps)] = id(st)
+                self._graphs[key] = st
+            N.check(L.cvflow_solve_replay(ne.handle, T, n_steps, E._stream()), "cvflow_solve_replay")
         return st["x"].clone().float()
 
     # ------------------------------------------------------------------------------------------

@@ -81,7 +81,7 @@ typedef struct cvflow_gemm_desc {
   const float* rowmask;
   const float* resid;
   int64_t ldr;
-  int64_t* dbg;         /* optional: 8 x int64 globaltimer stamps per CTA (profiling aid), else NULL */
+  int64_t* dbg;         /* optional: 16 x int64 globaltimer stamps per CTA (profiling aid), else NULL */
   float* gn_part;       /* optional: GroupNorm partial statistics of the output taken in the epilogue (before the 16-bit
                          * rounding): {n, mean, M2} per (batch, 32-row slice, 32-channel group),
                          * [nbatch][4 * ceil(R / 128)][n_valid / 32][3] floats, Chan-mergeable (replaces the separate
@@ -167,6 +167,30 @@ CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void*
  * [n_blocks][3][debug_rows][256] bytes (1 = keep) with debug_rows = B*T, for parity tests against the reference. */
 CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, uint64_t seed, const uint8_t* debug_mask,
                                        int64_t debug_rows);
+/* ---------------------------------------------------------------------------------------------
+ * Euler-ODE solve with classifier-free guidance as ONE CUDA graph owned by the handle
+ * (replaces ConditionalCFM.solve_euler's Python loop, flow_model.py:94-125; stands where the reference's TensorRT
+ * estimator hook stands, cosyvoice/flow/flow_matching.py:125-152: raw device pointers, caller's stream).
+ *   per step k:  d = estimator([x; x], mask, [mu; 0], t[k], [spks; 0], [cond; 0])      (batch 2 = cond / uncond)
+ *                x += dt[k] * ((1 + cfg_rate) d[0] - cfg_rate d[1])
+ * cvflow_solve_capture records n_steps of that on `stream` (must be a non-default stream; one un-captured warm-up
+ * forward runs first and writes only d_scratch) and instantiates the graph, kept per (T, n_steps);
+ * cvflow_solve_replay launches the one for (T, n_steps); cvflow_solve_release drops them all. The
+ * buffers are the caller's and must stay alive and in place: x [1][80][T] (in: noise z, out: mel), mask [1][T],
+ * mu / cond [1][80][T], spks [1][80] (spks / cond nullable), t / dt [n_steps] (the reference's accumulated time grid),
+ * d_scratch [2][80][T]. Refill x / mu / ... between replays for a new utterance of the same T. The workspace for
+ * (B = 2, T, training = 0) must be set; binding new weights or moving the workspace invalidates the captures
+ * (release and capture again).
+ * ------------------------------------------------------------------------------------------- */
+CVFLOW_API int cvflow_solve_capture(cvflow_estimator* h, int32_t T, int32_t n_steps, float cfg_rate, float* x,
+                                    const float* mask, const float* mu, const float* spks, const float* cond,
+                                    const float* t, const float* dt, float* d_scratch, void* stream);
+CVFLOW_API int cvflow_solve_replay(cvflow_estimator* h, int32_t T, int32_t n_steps, void* stream);
+CVFLOW_API int cvflow_solve_release(cvflow_estimator* h);
+/* time_mlp(SinusoidalPosEmb(320, scale 1000)(t)) -> out [B][1024]   (modules.py:27-57, the estimator's timestep path);
+ * t has t_nb entries (row b uses t[b % t_nb]); scratch: B * 1344 floats. */
+CVFLOW_API int cvflow_time_embed(cvflow_estimator* h, const float* t, int32_t t_nb, float* out, float* scratch, int32_t B,
+                                 void* stream);
 /* Read (out != NULL) and / or overwrite (in != NULL) the device-resident seed of the mask hash; host-synchronous.
  * Lets a caller rewind the dropout stream (e.g. after the warm-up executions that precede a CUDA-graph capture). */
 CVFLOW_API int cvflow_lora_dropout_seed(cvflow_estimator* h, uint64_t* out, const uint64_t* in);

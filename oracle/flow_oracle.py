@@ -30,7 +30,7 @@ Tensor = torch.Tensor
 # ----------------------------------------------------------------------------------------------
 def make_pad_mask(lengths: Tensor, max_len: int = 0) -> Tensor:
     n = max_len if max_len > 0 else int(lengths.max())
-    return torch.arange(n, dtype=torch.int64)[None, :] >= lengths.to(torch.int64)[:, None]
+    return torch.arange(n, dtype=torch.int64, device=lengths.device)[None, :] >= lengths.to(torch.int64)[:, None]
 
 
 def mask_to_bias(mask: Tensor, dtype=torch.float32) -> Tensor:
@@ -52,7 +52,7 @@ def isolation_bias(seq_len: int, p: int) -> Tensor:
 def sinusoidal_embedding(t: Tensor, dim: int = 320, scale: float = 1000.0) -> Tensor:
     """modules.py:27-42 -- [sin | cos] of scale * t * exp(-i ln(1e4)/(half-1))."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, device=t.device).float() * -(math.log(10000) / (half - 1)))
     arg = scale * t[:, None] * freq[None, :]
     return torch.cat([arg.sin(), arg.cos()], dim=-1)
 
@@ -123,7 +123,7 @@ def _stage(P, prefix, x, mask, temb, full_T, iso_len, iso_enabled, lora_scaling,
     if iso_enabled and iso_len > 0:
         p = max(1, int(iso_len * (L / full_T)))
         if p < L:
-            bias = bias + isolation_bias(L, p)
+            bias = bias + isolation_bias(L, p).to(bias.device)
     for j in range(_count(P, prefix + ".1.%d.")):
         h = transformer_block(P, "%s.1.%d" % (prefix, j), h, bias, lora_scaling,
                               gelu_approximate=gelu_approximate)
@@ -222,7 +222,7 @@ def cfm_compute_loss(P, x1: Tensor, mask: Tensor, mu: Tensor, spks: Tensor, cond
     w = cfm_loss_weights(mask, prompt_lens, boundary_frames, boundary_weight)
     diff = (pred - u) * w
     denom = w.sum() * u.shape[1]
-    loss = (diff ** 2).sum() / denom if denom > 0 else torch.zeros((), requires_grad=True)
+    loss = (diff ** 2).sum() / denom if denom > 0 else torch.zeros((), requires_grad=True, device=diff.device)
     return loss, y, pred
 
 

@@ -24,7 +24,7 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6
         kw = dict(act=N.ACT_GELU_TANH, aux_out=torch.empty(M, Nn, device="cuda", dtype=dt), ld_aux=Nn, bias=torch.randn(Nn, device="cuda"))
     if mode == "mulgrad":
         kw = dict(act=N.ACT_MUL_GELU_TANH_GRAD, mul_src=torch.randn(M, Nn, device="cuda").to(dt), ld_aux=Nn)
-    dbg = torch.zeros(4096 * 8, device="cuda", dtype=torch.int64)
+    dbg = torch.zeros(4096 * 16, device="cuda", dtype=torch.int64)
     d = _desc(A, W, out, segs=[(0, 0, 0, K // 64)], R=M, dtype=dt, **kw)
     d.dbg = dbg.data_ptr()
     for _ in range(3):
@@ -33,7 +33,7 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6
     dbg.zero_()
     L.cvflow_gemm(C.byref(d), N.current_stream())
     torch.cuda.synchronize()
-    t = dbg.view(-1, 8).cpu()
+    t = dbg.view(-1, 16).cpu()
     t = t[t[:, 0] > 0].double()
     t0 = t[:, 0].min()
     span = (t[:, 6].max() - t0) / 1e3
@@ -47,3 +47,7 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6
         print("   %3d CTAs with %d tile(s): " % (g.shape[0], int(nt)) + " | ".join(
             "%s %.2f/%.2f" % (names[k].split(" (")[0], float((g[:, k] - t0).mean()) / 1e3, float((g[:, k] - t0).max()) / 1e3)
             for k in range(1, 7)))
+        e = {8: "chunk0 tmem-ld done", 9: "chunk0 math done", 10: "chunk0 stored", 11: "chunk1 tmem-ld done", 12: "chunk1 stored",
+             13: "tile0 acc released"}
+        print("        first tile's epilogue (warp 2), us after its accumulator was ready: " + " | ".join(
+            "%s %.2f" % (e[k], float((g[:, k] - g[:, 4])[g[:, k] > 0].mean()) / 1e3) for k in sorted(e) if (g[:, k] > 0).any()))

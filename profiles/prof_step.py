@@ -34,7 +34,7 @@ if "PROF_BLOCKS" in os.environ:
     est.cvflow_dtype = torch.bfloat16
     cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
 else:
-    cfm, est, _ = bench.build_model(A, dev, torch.bfloat16, lora_dropout=drop)
+    cfm, est, _ = bench.build_model(dev, torch.bfloat16, drop)
 if mode == "train":
     tr = FlowLoRATrainer(cfm)
     batch, _ = bench.make_batch(B, T, 99, dev)

@@ -109,10 +109,18 @@ def test_benchmarked_shape_fp16(graphed):
     loss, grads = _bench_step(fx, torch.float16, graphed)
     ref = float(fx["loss"])
     e = grad_errors(grads, fx["grads"])
-    worst = max(abs(float(grads[k].norm()) - n) / (n + 1e-12) for k, n in fx["grad_norms"].items())
-    print("train_c3 fp16 graphed=%s: loss rel %.2e, %s, worst norm rel %.2e" % (graphed, abs(loss - ref) / ref, e, worst))
+    # per-tensor norms: tensors that carry >= 1 % of the largest gradient norm must be within 2e-2; the few tensors with
+    # vanishing gradients (16-bit operands underflow there) are held to 1.5x what the REFERENCE ITSELF loses on its worst
+    # tensor under fp16 autocast + loss scale at this shape (recorded in the fixture: 0.42)
+    nmax = max(fx["grad_norms"].values())
+    worst = max(abs(float(grads[k].norm()) - n) / (n + 1e-12) for k, n in fx["grad_norms"].items() if n >= 1e-2 * nmax)
+    floor = fx["ref_autocast"]["fp16"]
+    print("train_c3 fp16 graphed=%s: loss rel %.2e, %s, worst norm rel (significant tensors) %.2e; reference's own fp16 "
+          "floor %s" % (graphed, abs(loss - ref) / ref, e, worst, floor))
     assert abs(loss - ref) <= 1e-2 * ref, (loss, ref)
     assert e["bucket_rel_l2"] <= 1e-2, e
+    assert e["tensor_rel_l2_median"] <= 1e-2, e
+    assert e["tensor_rel_l2_max"] <= 1.5 * floor["tensor_rel_l2_max"], (e, floor)
     assert worst <= 2e-2, worst
     tot = float(torch.sqrt(sum(g.double().pow(2).sum() for g in grads.values())))
     assert abs(tot - fx["grad_total_norm"]) <= 1e-2 * fx["grad_total_norm"]
