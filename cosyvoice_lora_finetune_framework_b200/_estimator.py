@@ -54,6 +54,7 @@ def _lib():
         L.cvflow_set_lora_dropout.argtypes = [vp, f, C.c_uint64, vp, i64]
         L.cvflow_lora_dropout_seed.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cvflow_optim_advance.argtypes = [vp, vp, vp, vp, f, f, i32, i32, f, f, f, vp]
+        L.cvflow_set_grad_chunks.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(vp)]
         L.cvflow_solve_capture.argtypes = [vp, i32, i32, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.cvflow_solve_replay.argtypes = [vp, i32, i32, vp]
         L.cvflow_solve_release.argtypes = [vp]

@@ -135,6 +135,10 @@ extern "C" CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, 
   if (!h) { set_error("cvflow_set_lora_dropout: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->set_lora_dropout(p, (unsigned long long)seed, debug_mask, (long)debug_rows) ? CVFLOW_ERR_ARG : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_set_grad_chunks(cvflow_estimator* h, int32_t n, const int32_t* first_block, void** events) {
+  if (!h) { set_error("cvflow_set_grad_chunks: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->set_grad_chunks(n, first_block, reinterpret_cast<cudaEvent_t*>(events)) ? CVFLOW_ERR_ARG : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int cvflow_solve_capture(cvflow_estimator* h, int32_t T, int32_t n_steps, float cfg_rate, float* x,
                                                const float* mask, const float* mu, const float* spks, const float* cond,
                                                const float* t, const float* dt, float* d_scratch, void* stream) {

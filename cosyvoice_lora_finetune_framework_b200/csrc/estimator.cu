@@ -167,6 +167,46 @@ int Estimator::set_lora_dropout(float p, unsigned long long seed, const uint8_t*
   plans_.clear();
   return 0;
 }
+int Estimator::set_grad_chunks(int n, const int* lo, cudaEvent_t* events) {
+  chunk_lo_.clear();
+  chunk_ev_.clear();
+  if (n <= 0) return 0;
+  if (!lo || !events || lo[0] != 0) { set_error("set_grad_chunks: chunk 0 must start at block 0"); return -1; }
+  for (int k = 0; k < n; ++k) {
+    if (lo[k] < 0 || lo[k] >= n_tbs() || (k > 0 && lo[k] <= lo[k - 1])) {
+      set_error("set_grad_chunks: chunk starts must be increasing block indices in [0, %d)", n_tbs());
+      chunk_lo_.clear(); chunk_ev_.clear();
+      return -1;
+    }
+    chunk_lo_.push_back(lo[k]);
+    chunk_ev_.push_back(events[k]);
+  }
+  return 0;
+}
+// called after the backward of attention block `lora_idx`: when that block is the lowest of a gradient chunk, every block
+// of the chunk has produced its split partials -> reduce them into the gradient bucket and signal the chunk's event
+int Estimator::finalize_blocks_from(int lora_idx, const BwdTemps& tmp, float grad_scale, long MT, long MH) {
+  if (cfg.lora_r <= 0 || dry_) return 0;
+  int lo = -1, hi = -1, k = -1;
+  if (chunk_lo_.empty() || wgrad_side_) {
+    if (lora_idx != 0) return 0;
+    lo = 0; hi = n_tbs();
+  } else {
+    for (size_t c = 0; c < chunk_lo_.size(); ++c)
+      if (chunk_lo_[c] == lora_idx) { k = (int)c; lo = lora_idx; hi = c + 1 < chunk_lo_.size() ? chunk_lo_[c + 1] : n_tbs(); }
+    if (k < 0) return 0;
+  }
+  for (int par = 0; par < 2; ++par)
+    if (wgrad_side_ && ev_done_valid_[par]) { cudaStreamWaitEvent(stream_, ev_done_[par], 0); ev_done_valid_[par] = false; }
+  CKL(launch_lora_wgrad_final(lora_table_dev_, n_tbs(), cfg.n_blocks, tmp.wg_scratch, tmp.wg_stride, lora_wgrad_splits(MT),
+                              lora_wgrad_splits(MH), cfg.lora_r, grad_scale, grad_scale_dev_, lo, hi - lo, stream_));
+  ++launches_;
+  if (k >= 0 && cudaEventRecord(chunk_ev_[k], stream_) != cudaSuccess) {
+    set_error("backward: cudaEventRecord(gradient chunk %d) failed: %s", k, cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  return 0;
+}
 int Estimator::lora_dropout_seed(unsigned long long* out, const unsigned long long* in) {
   if (!drop_seed_dev_) { if (out) *out = 0ull; return 0; }
   if (out && cudaMemcpy(out, drop_seed_dev_, sizeof(*out), cudaMemcpyDeviceToHost) != cudaSuccess) {
@@ -912,6 +952,8 @@ int Estimator::stage_bwd(const StageRec& s, float* dh32, void* dh16, void* dxin1
   for (int j = (int)s.tbs.size() - 1; j >= 0; --j) {
     const bool need = !(first_stage && j == 0);
     CK(tb_bwd(s.tbs[j], dh32, dh16, need, grad_scale, tmp));
+    CK(finalize_blocks_from(s.tbs[j].lora_idx, tmp, grad_scale, (long)last_io_.B * last_io_.T,
+                            (long)last_io_.B * ((last_io_.T + 1) / 2)));
   }
   if (!first_stage) CK(resnet_bwd(s.resnet, dh32, dh16, dxin16, tmp));
   return 0;
@@ -1041,13 +1083,6 @@ int Estimator::backward_impl(const void* dpred16, float grad_scale, const InputG
     CKL(launch_unpack_input_grads(dxin0, last_io_.keep, grad_scale, grad_scale_dev_, in_grads->dx, in_grads->dmu,
                                   in_grads->dspks, in_grads->dcond, spk_part, B, T, cfg.bf16, stream_));
     launches_ += in_grads->dspks ? 2 : 1;
-  }
-  if (cfg.lora_r > 0) {   // join the side stream, then one final reduction of every block's split partials into the grads
-    for (int par = 0; par < 2; ++par)
-      if (wgrad_side_ && ev_done_valid_[par]) { cudaStreamWaitEvent(stream_, ev_done_[par], 0); ev_done_valid_[par] = false; }
-    CKL(launch_lora_wgrad_final(lora_table_dev_, n_tbs(), cfg.n_blocks, tmp.wg_scratch, tmp.wg_stride, lora_wgrad_splits(MT),
-                                lora_wgrad_splits(MH), cfg.lora_r, grad_scale, grad_scale_dev_, stream_));
-    ++launches_;
   }
   if (missing_) return -1;
   return 0;

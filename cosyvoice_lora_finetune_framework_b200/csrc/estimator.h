@@ -81,6 +81,11 @@ class Estimator {
   // lora_dropout p of the q/k/v LoRA branches in training forwards (0 = off: B A is folded into the GEMM operand);
   // dbg_mask: optional explicit keep masks [n_tbs][3][dbg_rows][256] bytes for parity tests (dbg_rows must be B*T)
   int set_lora_dropout(float p, unsigned long long seed, const uint8_t* dbg_mask, long dbg_rows);
+  // Gradient chunks for overlapping the data-parallel allreduce with the rest of the backward: chunk k covers attention
+  // blocks [lo[k], lo[k+1]) (execution order = position in the flat LoRA bucket; lo[0] = 0, the last chunk ends at n_tbs).
+  // The backward finalises a chunk's gradients as soon as its lowest block is done (blocks are visited last to first)
+  // and records events[k] on the stream; the caller makes a side stream wait on it and reduces that slice of the bucket.
+  int set_grad_chunks(int n, const int* lo, cudaEvent_t* events);
   // N-step CFG Euler solve (flow_model.py:94-125) captured ONCE into a CUDA graph owned by the handle and replayed:
   // per step one batch-2 (cond / uncond) estimator forward + the guidance / Euler update. All pointers are the caller's
   // static device buffers; `stream` must be a capturing-capable (non-legacy) stream. The workspace for (B=2, T,
@@ -158,6 +163,9 @@ class Estimator {
   struct SolveGraph { cudaGraph_t graph; cudaGraphExec_t exec; };
   std::map<std::pair<int, int>, SolveGraph> solves_;   // (T, n_steps) -> captured solve
   float* solve_keep_dev_ = nullptr;     // {1, 0}: CFG keep factors of the (cond, uncond) rows
+  std::vector<int> chunk_lo_;
+  std::vector<cudaEvent_t> chunk_ev_;
+  int finalize_blocks_from(int lora_idx, const BwdTemps& tmp, float grad_scale, long MT, long MH);
   float drop_p_ = 0.f;
   unsigned long long* drop_seed_dev_ = nullptr;
   const uint8_t* drop_dbg_ = nullptr;

@@ -124,7 +124,7 @@ int lora_wgrad_splits(long M);
 int lora_wgrad_launch_partial(const void* plan, cudaStream_t st);
 // ... and one final reduction for all nb blocks (block i: scratch + i*stride; the first / last nfull blocks are full-rate)
 int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
-                            int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st);
+                            int S_half, int r, float grad_scale, const float* gs_dev, int bi0, int count, cudaStream_t st);
 
 // ---- lora_dropout.cu -------------------------------------------------------------------------
 // lora_dropout > 0: independent keep masks per (attention block, projection, token, feature) from a counter-based hash of

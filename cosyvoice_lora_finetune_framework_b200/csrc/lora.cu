@@ -206,13 +206,13 @@ __global__ void __launch_bounds__(192, 2) lora_wgrad_tc_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) lora_wgrad_final_kernel(const LoraBlockPtrs* __restrict__ blocks, int nb, int nfull,
                                                                const float* __restrict__ scratch, long stride, int S_full,
                                                                int S_half, int r, float grad_scale,
-                                                               const float* __restrict__ gs_dev) {
+                                                               const float* __restrict__ gs_dev, int bi0) {
   pdl_wait();
   pdl_launch();
   const int nbw = 1536 * r, na = 3 * r * 256;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= nbw + na) return;
-  const int bi = blockIdx.y;
+  const int bi = bi0 + blockIdx.y;      // blocks [bi0, bi0 + gridDim.y) of the step
   const int S = (bi < nfull || bi >= nb - nfull) ? S_full : S_half;   // full-rate stages come first and last
   const float* part_b = scratch + (long)bi * stride;
   const float* part_a = part_b + (long)S * 1536 * r;
@@ -283,10 +283,10 @@ int lora_wgrad_launch_partial(const void* plan, cudaStream_t st) {
 }
 
 int launch_lora_wgrad_final(const LoraBlockPtrs* blocks_dev, int nb, int nfull, const float* scratch, long stride, int S_full,
-                            int S_half, int r, float grad_scale, const float* gs_dev, cudaStream_t st) {
+                            int S_half, int r, float grad_scale, const float* gs_dev, int bi0, int count, cudaStream_t st) {
   const int total = 1536 * r + 3 * r * 256;
-  launch_pdl(lora_wgrad_final_kernel, dim3((total + 255) / 256, nb), 256, 0, st, blocks_dev, nb, nfull, scratch, stride, S_full,
-             S_half, r, grad_scale, gs_dev);
+  launch_pdl(lora_wgrad_final_kernel, dim3((total + 255) / 256, count), 256, 0, st, blocks_dev, nb, nfull, scratch, stride,
+             S_full, S_half, r, grad_scale, gs_dev, bi0);
   LAUNCH_RET();
 }
 

@@ -82,25 +82,31 @@ __global__ void __launch_bounds__(256) ln_lora_drop_fwd_kernel(const float* __re
                                                                uint16_t* __restrict__ x1, uint32_t* __restrict__ ud,
                                                                uint32_t* __restrict__ bits, long M, int bf, const LoraDropSpec d) {
   constexpr int NV = 3 * R;
-  constexpr int TOK = R <= 8 ? 2 : 1;
+  constexpr int TOK = 1;     // measured: two tokens per pass (shared A-row fetches) is no faster, registers cost occupancy
   __shared__ __align__(16) uint16_t As[NV * 256];
   pdl_wait();
-  load_acat<R>(As, acat);
-  pdl_launch();
-  const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[8], b[8];
+  const long stride = (long)gridDim.x * 8;
+  // the first pass's row, gamma / beta and the seed are requested before the A_cat staging: one L2 round trip, not three
+  float g[8], b[8], xfirst[8];
+  const long mfirst = (long)blockIdx.x * 8 + warp;
+  if (mfirst < M) load8_f32(h + mfirst * 256 + lane * 8, xfirst);
   load8_f32(gamma + lane * 8, g);
   load8_f32(beta + lane * 8, b);
-  const long stride = (long)gridDim.x * 8;
-  for (long mb = (long)blockIdx.x * 8 + warp; mb < M; mb += stride * TOK) {
+  const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
+  load_acat<R>(As, acat);
+  pdl_launch();
+  for (long mb = mfirst; mb < M; mb += stride * TOK) {
     float xv[TOK][8];
     uint32_t kb[TOK][3];
     float x[TOK][8];
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {      // all the row loads first
       const long m = mb + t * stride;
-      if (m < M) load8_f32(h + m * 256 + lane * 8, x[t]);
+      if (m == mfirst) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[t][e] = xfirst[e];
+      } else if (m < M) load8_f32(h + m * 256 + lane * 8, x[t]);
     }
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
@@ -199,14 +205,14 @@ __global__ void __launch_bounds__(256) ln_lora_drop_bwd_kernel(const uint16_t* _
                                                                float* __restrict__ dh, uint16_t* __restrict__ dh16, long M,
                                                                float sc, int bf) {
   constexpr int NV = 3 * R;
-  constexpr int TOK = 2;
+  constexpr int TOK = 1;     // measured: two tokens per pass is slower here (19.0 vs 14.8 us)
   __shared__ __align__(16) uint16_t As[NV * 256];
   pdl_wait();
-  load_acat<R>(As, acat);
-  pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[8];
   load8_f32(gamma + lane * 8, g);
+  load_acat<R>(As, acat);
+  pdl_launch();
   const long stride = (long)gridDim.x * 8;
   for (long mb = (long)blockIdx.x * 8 + warp; mb < M; mb += stride * TOK) {
     float v0[TOK], v1[TOK], d[TOK][8], x[TOK][8], r[TOK][8];
@@ -302,26 +308,36 @@ __global__ void __launch_bounds__(256) lora_wgrad_a_drop_kernel(const uint16_t* 
   const int c = blockIdx.x, p = blockIdx.y;
   const long m0 = (long)c * kWgaChunk;
   const int n = (int)(M - m0 < kWgaChunk ? M - m0 : kWgaChunk);
-  for (int i = threadIdx.x; i < kWgaChunk * R; i += 256) {
-    const int t = i / R, j = i - t * R;
-    vs[t][j] = t < n ? h16_to_f32(v[(m0 + t) * ld_v + p * R + j], bf) : 0.f;
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fq = warp & 3, th = warp >> 2;
   const int k0 = fq * 64 + lane * 2;
   float acc0[R], acc1[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-  const int t_begin = th * (kWgaChunk / 2), t_end = min(n, t_begin + kWgaChunk / 2);
-#pragma unroll 4
-  for (int t = t_begin; t < t_end; ++t) {
-    const long row = m0 + t;
-    const uint32_t xw = *reinterpret_cast<const uint32_t*>(x + row * 256 + k0);
-    const uint32_t w = bits[row * 24 + p * 8 + 2 * fq + (lane >> 4)];
-    const uint32_t kb = (w >> ((2 * lane) & 31)) & 3u;
+  const int t_begin = th * (kWgaChunk / 2);
+  constexpr int NT = kWgaChunk / 2;
+  uint32_t xws[NT], kws[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {      // all 2 x 32 loads of the warp in flight together (one L2 round trip)
+    const int t = t_begin + i;
+    xws[i] = 0u; kws[i] = 0u;
+    if (t < n) {
+      const long row = m0 + t;
+      xws[i] = *reinterpret_cast<const uint32_t*>(x + row * 256 + k0);
+      kws[i] = bits[row * 24 + p * 8 + 2 * fq + (lane >> 4)];
+    }
+  }
+  for (int i = threadIdx.x; i < kWgaChunk * R; i += 256) {
+    const int t = i / R, j = i - t * R;
+    vs[t][j] = t < n ? h16_to_f32(v[(m0 + t) * ld_v + p * R + j], bf) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int t = t_begin + i;
+    const uint32_t kb = (kws[i] >> ((2 * lane) & 31)) & 3u;
     float x0, x1;
-    unpack2_h16(xw, bf, x0, x1);
+    unpack2_h16(xws[i], bf, x0, x1);
     x0 = (kb & 1u) ? x0 : 0.f;
     x1 = (kb & 2u) ? x1 : 0.f;
 #pragma unroll
@@ -376,7 +392,8 @@ int launch_lora_seed_bump(unsigned long long* seed, cudaStream_t st) {
   LAUNCH_RET();
 }
 // warps take two tokens per pass (one for r = 16 in the forward): size the grid so that a pass covers M when it can
-static unsigned drop_grid(long M, int tok) { long g = (M + 8 * tok - 1) / (8 * tok); return (unsigned)(g < 148 * 4 ? g : 148 * 4); }
+static unsigned drop_grid(long M, int tok_unused) {
+  const int tok = 1; (void)tok_unused; long g = (M + 8 * tok - 1) / (8 * tok); return (unsigned)(g < 148 * 4 ? g : 148 * 4); }
 
 int launch_ln_lora_drop_fwd(const float* h, const float* gamma, const float* beta, const void* acat16, void* x16, void* ud16,
                             uint32_t* bits, long M, int r, int bf16, const LoraDropSpec& d, cudaStream_t st) {

@@ -98,6 +98,9 @@ class FlowLoRATrainer:
             self.xsumsq = torch.zeros(1, device=dev)
             self.xpartials = torch.zeros(296, device=dev)
 
+        self._chunks = []
+        if self.world > 1:
+            self._setup_grad_chunks()
         if self.world > 1:      # replicas must start identical (DDP broadcasts rank 0's parameters at construction)
             dist.broadcast(self.ne.param_bucket, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0,
                            group=self.pg)
@@ -106,6 +109,41 @@ class FlowLoRATrainer:
                                group=self.pg)
             self.ne.mark_dirty()
             self.ne.sync_lora()
+
+    def _setup_grad_chunks(self, n_chunks=3):
+        """Overlap the gradient exchange with the backward (what DDP's bucketed hooks do for the reference's modules): the
+        flat bucket is cut into chunks of whole attention blocks; the estimator backward finalises a chunk as soon as its
+        last-visited block is done and records an event, and optimizer_step allreduces each chunk on a side stream behind
+        that event. The chunk holding the first blocks (finished last) is kept small so that little is left exposed."""
+        ne = self.ne
+        r = ne.lora_r
+        if r <= 0 or ne.n_lora <= 0 or int(self.cfm.num_streams) > 1:
+            return
+        per_block = 3 * (r * 256 + 512 * r)
+        nb = ne.n_lora // per_block
+        if nb * per_block != ne.n_lora or nb < 4:
+            return
+        lo = sorted({0, max(1, nb // 8), max(2, nb // 2)})[:n_chunks]
+        self._comm_stream = torch.cuda.Stream(device=ne.device)
+        evs = [torch.cuda.Event() for _ in lo]
+        for e in evs:
+            e.record()           # materialises the cudaEvent_t handed to the library
+        lo_arr = (C.c_int32 * len(lo))(*lo)
+        ev_arr = (C.c_void_p * len(lo))(*[e.cuda_event for e in evs])
+        N.check(self.L.cvflow_set_grad_chunks(ne.handle, len(lo), lo_arr, ev_arr), "cvflow_set_grad_chunks")
+        hi = lo[1:] + [nb]
+        self._chunks = [(a * per_block, b * per_block, e) for a, b, e in zip(lo, hi, evs)]
+
+    def _allreduce_grads(self, g):
+        if not self._chunks:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            return
+        cur, side = torch.cuda.current_stream(), self._comm_stream
+        for a, b, ev in reversed(self._chunks):      # the chunk of the last blocks is complete first
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+        cur.wait_stream(side)
 
     def current_lr(self):
         """Learning rate the NEXT optimiser step will use (LambdaLR value after `step_count` scheduler steps)."""
@@ -189,7 +227,7 @@ class FlowLoRATrainer:
         if self.extra:
             self._gather_extra()
         if self.world > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            self._allreduce_grads(g)
             if self.extra:
                 dist.all_reduce(self.xgrad, op=dist.ReduceOp.SUM, group=self.pg)
         N.check(self.L.cvflow_sumsq(g.data_ptr(), ne.n_lora, self.partials.data_ptr(), self.sumsq.data_ptr(), st),
@@ -281,6 +319,10 @@ class FlowLoRATrainer:
             self.ne.sync_lora()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            # NB: a loss tensor of an earlier EAGER step that is still referenced keeps that step's autograd graph, and
+            # with it the parameters' AccumulateGrad nodes (bound to the stream they were created on), alive; the captured
+            # backward would then sync the capturing stream with that uncaptured stream and the capture fails with
+            # cudaErrorStreamCaptureIsolation. Drop such references (float(loss) / del loss) before the first graphed step.
             with torch.cuda.graph(g):
                 st["loss"] = body()
             self.step_count = snap["step"]         # capture executes nothing

@@ -167,6 +167,14 @@ CVFLOW_API int cvflow_estimator_backward_inputs(cvflow_estimator* h, const void*
  * [n_blocks][3][debug_rows][256] bytes (1 = keep) with debug_rows = B*T, for parity tests against the reference. */
 CVFLOW_API int cvflow_set_lora_dropout(cvflow_estimator* h, float p, uint64_t seed, const uint8_t* debug_mask,
                                        int64_t debug_rows);
+/* Data-parallel overlap: split the flat LoRA-gradient bucket into n chunks of whole attention blocks. Chunk k covers
+ * blocks [first_block[k], first_block[k+1]) in execution order, which is also their order in the bucket
+ * (first_block[0] = 0; a block holds 3 (r 256 + 512 r) floats). The backward visits blocks last to first; as soon as a
+ * chunk's lowest block is done it reduces the chunk's split partials into the bucket and records events[k] (a
+ * cudaEvent_t, timing disabled) on the backward's stream, so the caller can allreduce that slice on a side stream while
+ * the rest of the backward runs (replaces DDP's bucketed gradient hooks; the reference trainer is single-device,
+ * train_joint.py:349-352). n = 0 restores the single final reduction. */
+CVFLOW_API int cvflow_set_grad_chunks(cvflow_estimator* h, int32_t n, const int32_t* first_block, void** events);
 /* ---------------------------------------------------------------------------------------------
  * Euler-ODE solve with classifier-free guidance as ONE CUDA graph owned by the handle
  * (replaces ConditionalCFM.solve_euler's Python loop, flow_model.py:94-125; stands where the reference's TensorRT
