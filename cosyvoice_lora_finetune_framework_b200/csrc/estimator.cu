@@ -382,13 +382,13 @@ int Estimator::iso_at(int L, int T, int iso_len) const {
 int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L,
                           const float* mask, const float* tb, long tb_stride, float** h_out, ResnetRec* rec) {
   const long M = (long)B * L;
-  void* c1 = alloc(M * 256 * 2);
-  void* a1 = alloc(M * 256 * 2);
-  void* c2 = alloc(M * 256 * 2);
-  void* r = alloc(M * 256 * 2);
+  void* c1 = training_ ? alloc(M * 256 * 2) : scr_c1_;      // conv outputs are stashed for the GroupNorm backward
+  void* a1 = scr_a1_;
+  void* c2 = training_ ? alloc(M * 256 * 2) : scr_c2_;
+  void* r = scr_r_;
   float* st1 = (float*)alloc(B * 16 * 4);
   float* st2 = (float*)alloc(B * 16 * 4);
-  float* h = (float*)alloc(M * 256 * 4);
+  float* h = training_ ? (float*)alloc(M * 256 * 4) : scr_rh_;
   {
     GemmArgs g = conv3_args(xin, B, L, ld_in, col0, cin, get(P + ".block1.w", cfg.bf16, 256L * 3 * cin), 256, c1, 256, 0);
     g.bias = (const float*)get(P + ".block1.b", 2, 256);
@@ -439,17 +439,18 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   const bool drop = cfg.lora_r > 0 && training_ && drop_p_ > 0.f;
   const bool ext = cfg.lora_r > 0 && training_ && !drop;
   const long ldq = ext ? 1600 : 1536;
-  void* x1 = alloc(M * 256 * 2);
+  const TbSet& es = scr_tb_[lora_idx & 1];      // eval(): ping-pong sets, nothing is stashed
+  void* x1 = training_ ? alloc(M * 256 * 2) : es.x1;
   void* ud = drop ? alloc(M * 64 * 2) : nullptr;
   uint32_t* bits = drop ? (uint32_t*)alloc(M * 24 * 4) : nullptr;
-  void* qkv = alloc(M * ldq * 2);
-  void* o = alloc(M * 512 * 2);
-  float* lse = (float*)alloc((long)B * 8 * L * 4);
-  float* h1 = (float*)alloc(M * 256 * 4);
-  void* x3 = alloc(M * 256 * 2);
-  void* pre = alloc(M * 1024 * 2);
-  void* g16 = fused_mlp_ ? nullptr : alloc(M * 1024 * 2);
-  float* h2 = (float*)alloc(M * 256 * 4);
+  void* qkv = training_ ? alloc(M * ldq * 2) : es.qkv;
+  void* o = training_ ? alloc(M * 512 * 2) : es.o;
+  float* lse = training_ ? (float*)alloc((long)B * 8 * L * 4) : es.lse;
+  float* h1 = training_ ? (float*)alloc(M * 256 * 4) : es.h1;
+  void* x3 = scr_x3_;
+  void* pre = (training_ || fused_mlp_) ? alloc(M * 1024 * 2) : nullptr;      // GELU pre-activation: backward only
+  void* g16 = fused_mlp_ ? nullptr : scr_g16_;
+  float* h2 = training_ ? (float*)alloc(M * 256 * 4) : es.h2;
   if (!dry_) {
     prof_begin(3, (double)M * (drop ? 1536 + 128 + 96 : 1536));   // algorithmic bytes: fp32 row in, 16-bit row out (+ u_d, bits)
     if (drop)    // LayerNorm, mask draw and the masked down-projection u_d in one pass over the residual stream
@@ -506,7 +507,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       GemmArgs g = linear_args(x3, M, 256, get(Q + ".w1", cfg.bf16, 1024L * 256), 1024, g16, 0);
       g.bias = (const float*)get(Q + ".b1", 2, 1024);
       g.act = cfg.gelu_erf ? ACT_GELU_ERF : ACT_GELU_TANH;
-      g.aux_out = pre; g.ld_aux = 1024;
+      g.aux_out = pre; g.ld_aux = 1024;      // pre == nullptr in eval(): no stash is written
       CK(run_gemm(g));
     }
     {
@@ -662,6 +663,26 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   void* xd1 = alloc((long)B * T2 * 256 * 2);
   kmax1_ = (int*)alloc(attn_kinfo_ints(B, T) * 4);
   kmax2_ = (int*)alloc(attn_kinfo_ints(B, T2) * 4);
+  {   // per-forward scratch shared by all blocks (sized for the full-rate token count)
+    const long MTr = (long)B * T;
+    scr_g16_ = fused_mlp_ ? nullptr : alloc(MTr * 1024 * 2);
+    scr_x3_ = alloc(MTr * 256 * 2);
+    scr_a1_ = alloc(MTr * 256 * 2);
+    scr_r_ = alloc(MTr * 256 * 2);
+    if (!training_) {
+      scr_c1_ = alloc(MTr * 256 * 2);
+      scr_c2_ = alloc(MTr * 256 * 2);
+      scr_rh_ = (float*)alloc(MTr * 256 * 4);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        scr_tb_[s2].x1 = alloc(MTr * 256 * 2);
+        scr_tb_[s2].qkv = alloc(MTr * 1536 * 2);
+        scr_tb_[s2].o = alloc(MTr * 512 * 2);
+        scr_tb_[s2].lse = (float*)alloc((long)B * 8 * T * 4);
+        scr_tb_[s2].h1 = (float*)alloc(MTr * 256 * 4);
+        scr_tb_[s2].h2 = (float*)alloc(MTr * 256 * 4);
+      }
+    }
+  }
   mask1_ = mask1; mask2_ = mask2; cat1_ = cat1; cat0_ = cat0;
   drop_mcap_ = (long)B * T;
   if (!dry_ && training_ && cfg.lora_r > 0 && drop_p_ > 0.f) {

@@ -177,6 +177,14 @@ class Estimator {
 #else
   static constexpr unsigned kSkip(unsigned) { return 0u; }   // product build: every launch always runs
 #endif
+  // Buffers that do not outlive their block are allocated ONCE per forward and reused by every block, so that they stay
+  // dirty-in-L2 and are overwritten in place instead of streaming to HBM: in training the FF hidden activation g16, the
+  // LayerNorm-3 output and the resnets' a1 / r (nothing in the backward reads them); in eval() every block tensor
+  // (two ping-pong sets, block j+1 reads block j's h2 while writing its own).
+  struct TbSet { void *x1, *qkv, *o; float *lse, *h1, *h2; };
+  void *scr_g16_ = nullptr, *scr_x3_ = nullptr, *scr_a1_ = nullptr, *scr_r_ = nullptr, *scr_c1_ = nullptr, *scr_c2_ = nullptr;
+  float* scr_rh_ = nullptr;
+  TbSet scr_tb_[2] = {};
   float *tb_all_ = nullptr, *gn_partials_ = nullptr, *mask1_ = nullptr, *mask2_ = nullptr;
   int *kmax1_ = nullptr, *kmax2_ = nullptr;
   void *cat0_ = nullptr, *cat1_ = nullptr;

@@ -74,10 +74,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   constexpr int kSliceRows = BM / CL;
   long long* dbg = p.dbg ? p.dbg + (long)blockIdx.x * 16 : nullptr;
+  // profiling aid: slot 0 = globaltimer at CTA start (ns, aligns the CTAs of a launch), slots 1..13 = SM cycle counter
+  // (clock64: a few cycles per read; %globaltimer costs hundreds and perturbed the epilogue it was meant to time),
+  // slot 14 = clock64 at CTA start, slot 7 = tiles run by the CTA
   auto stamp = [&](int k) {
-    if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
+    if (dbg) dbg[k] = clock64();
   };
-  if (threadIdx.x == 0) stamp(0);
+  if (threadIdx.x == 0 && dbg) {
+    long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[0] = t; dbg[14] = clock64();
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -273,7 +278,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         if (it == 0 && threadIdx.x == 64) stamp(cc == 0 ? 8 : 11);
         float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * p.alpha;
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+        if (p.alpha != 1.f) {      // kernel-uniform; the estimator never scales (the epilogue is issue-bound: 32 FMULs matter)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] *= p.alpha;
+        }
         if (p.bias) {
           if (full_cols) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);

@@ -35,19 +35,23 @@ for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6
     torch.cuda.synchronize()
     t = dbg.view(-1, 16).cpu()
     t = t[t[:, 0] > 0].double()
+    MHZ = 1965.0                                  # SM clock under load on these boxes (bench.py's clocks line)
     t0 = t[:, 0].min()
-    span = (t[:, 6].max() - t0) / 1e3
+    start_us = (t[:, 0] - t0) / 1e3               # CTA start, us after the first CTA (globaltimer)
+    cyc = lambda k: (t[:, k] - t[:, 14]) / MHZ     # us since the CTA's own start (cycle counter)
+    end_us = start_us + cyc(6)
+    span = float(end_us.max())
     fl = 2.0 * M * Nn * K
     print("== M=%d N=%d K=%d %s: %d persistent CTAs, kernel span %.1f us (%.0f TFLOP/s), CTA start spread %.2f us, "
-          "CTA lifetime mean %.2f / max %.2f us" % (M, Nn, K, mode, t.shape[0], span, fl / span / 1e6,
-          float((t[:, 0].max() - t0) / 1e3), float((t[:, 6] - t[:, 0]).mean()) / 1e3, float((t[:, 6] - t[:, 0]).max()) / 1e3))
-    # mean / max over CTAs of every stamp, in us after the first CTA's start; CTAs grouped by the number of tiles they ran
+          "CTA lifetime mean %.2f / max %.2f us" % (M, Nn, K, mode, t.shape[0], span, fl / span / 1e6, float(start_us.max()),
+                                                   float(cyc(6).mean()), float(cyc(6).max())))
+    # mean / max over CTAs of every stamp, us after the CTA's own start; CTAs grouped by the number of tiles they ran
     for nt in sorted(set(t[:, 7].tolist())):
-        g = t[t[:, 7] == nt]
-        print("   %3d CTAs with %d tile(s): " % (g.shape[0], int(nt)) + " | ".join(
-            "%s %.2f/%.2f" % (names[k].split(" (")[0], float((g[:, k] - t0).mean()) / 1e3, float((g[:, k] - t0).max()) / 1e3)
-            for k in range(1, 7)))
+        sel = t[:, 7] == nt
+        print("   %3d CTAs with %d tile(s): " % (int(sel.sum()), int(nt)) + " | ".join(
+            "%s %.2f/%.2f" % (names[k].split(" (")[0], float(cyc(k)[sel].mean()), float(cyc(k)[sel].max())) for k in range(1, 7)))
         e = {8: "chunk0 tmem-ld done", 9: "chunk0 math done", 10: "chunk0 stored", 11: "chunk1 tmem-ld done", 12: "chunk1 stored",
              13: "tile0 acc released"}
         print("        first tile's epilogue (warp 2), us after its accumulator was ready: " + " | ".join(
-            "%s %.2f" % (e[k], float((g[:, k] - g[:, 4])[g[:, k] > 0].mean()) / 1e3) for k in sorted(e) if (g[:, k] > 0).any()))
+            "%s %.2f" % (e[k], float(((t[:, k] - t[:, 4]) / MHZ)[sel & (t[:, k] > 0)].mean())) for k in sorted(e)
+            if (sel & (t[:, k] > 0)).any()))
