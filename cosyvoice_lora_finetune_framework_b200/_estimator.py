@@ -48,6 +48,7 @@ def _lib():
         L.cvflow_workspace_bytes.restype = i64
         L.cvflow_set_workspace.argtypes = [vp, vp, i64]
         L.cvflow_lora_refresh.argtypes = [vp, vp]
+        L.cvflow_lora_refresh_factors.argtypes = [vp, vp]
         L.cvflow_estimator_forward.argtypes = [vp, C.POINTER(EstimatorIO), vp]
         L.cvflow_estimator_backward.argtypes = [vp, vp, f, vp, vp]
         L.cvflow_estimator_backward_inputs.argtypes = [vp, vp, f, vp, C.POINTER(InputGrads), vp]
@@ -270,8 +271,8 @@ class NativeEstimator:
                     self._bind(Q + ".b2", self._f(b2_))
             if r > 0 and self.lora_dropout_p > 0:
                 # lora_dropout > 0: the branch cannot be folded; per block [W0 | s B_cat] ([1536][320]) for the forward
-                # and [W0^T ; B_blk] ([320][1536]) for the dgrad, stacked so that the LoRA halves are refreshed by a few
-                # batched torch ops after every optimiser step (_refresh_dropout_images)
+                # and [W0^T ; B_blk] ([320][1536]) for the dgrad; the LoRA parts are rewritten by the refresh kernel after
+                # every optimiser step
                 tbs = [(("%s.1.%d" % (S, j)), tb) for S, st in stages for j, tb in enumerate(st[1])]
                 nb = len(tbs)
                 self.w0d = torch.zeros(nb, 1536, 320, device=self.device, dtype=self.dtype)
@@ -368,27 +369,18 @@ class NativeEstimator:
             for p, off, n in self.lora_views:
                 p.grad = self.grad_bucket[off:off + n].view_as(p)
 
-    def refresh_lora(self):
-        """Rebuild W_eff = W + (alpha/r) B A (call after every optimiser step)."""
-        N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
-        if self.lora_dropout_p > 0 and self.lora_r > 0:
-            self._refresh_dropout_images()
+    def refresh_lora(self, full=True):
+        """Rebuild the 16-bit LoRA operand images from the fp32 masters (after every optimiser step). full: the folded
+        W_eff = W + (alpha/r) B A in both layouts plus the factor images; not full: the factor images only -- all a
+        training step with lora_dropout > 0 reads (the folded images are then stale until the next full refresh)."""
+        if full:
+            N.check(self.L.cvflow_lora_refresh(self.handle, _stream()), "cvflow_lora_refresh")
+            self._folded_stale = False
+        else:
+            N.check(self.L.cvflow_lora_refresh_factors(self.handle, _stream()), "cvflow_lora_refresh_factors")
+            self._folded_stale = True
         self._merged_version = self._version()
         self._dirty = False
-
-    def _refresh_dropout_images(self):
-        """LoRA halves of the un-folded operands from the fp32 masters: w0d[:, n, 256 + p r + j] = s B_p[n][j] (block
-        structure), w0t_ext[:, 256 + p r + j, p 512 + n] = B_p[n][j]. The flat bucket holds, per attention block,
-        A_q, B_q, A_k, B_k, A_v, B_v in this order."""
-        r = self.lora_r
-        nb = self.w0d.shape[0]
-        with torch.no_grad():
-            per = self.param_bucket[: nb * 3 * (r * 256 + 512 * r)].view(nb, 3, r * 256 + 512 * r)
-            Bm = per[:, :, r * 256:].reshape(nb, 3, 512, r)
-            s = float(self.cfg.lora_scaling)
-            for p in range(3):
-                self.w0d[:, p * 512:(p + 1) * 512, 256 + p * r:256 + (p + 1) * r] = (Bm[:, p] * s).to(self.dtype)
-                self.w0t_ext[:, 256 + p * r:256 + (p + 1) * r, p * 512:(p + 1) * 512] = Bm[:, p].transpose(1, 2).to(self.dtype)
 
     def set_debug_dropout_mask(self, mask):
         """Explicit keep masks (uint8 [n_blocks][3][B*T][256], 1 = keep) instead of the hash RNG: parity tests only."""
@@ -434,11 +426,18 @@ class NativeEstimator:
     def mark_dirty(self):
         self._dirty = True
 
-    def sync_lora(self):
-        """Refresh W_eff when the LoRA parameters changed since the last merge (torch in-place
-        updates bump the bucket's version counter; raw-pointer updates call mark_dirty)."""
+    def sync_lora(self, need_folded=True):
+        """Refresh the operand images when the LoRA parameters changed since the last refresh (torch in-place updates
+        bump the bucket's version counter; raw-pointer updates call mark_dirty). need_folded: the coming forward reads
+        the folded W_eff (eval(), or training with lora_dropout = 0)."""
         if self._dirty or self._version() != self._merged_version:
-            self.refresh_lora()
+            self.refresh_lora(full=need_folded)
+        elif need_folded and getattr(self, "_folded_stale", False):
+            self.refresh_lora(full=True)
+
+    def trains_unfolded(self):
+        """True while training forwards run the un-folded LoRA branch (lora_dropout > 0 active on the handle)."""
+        return self._drop_active != 0.0
 
     def check_trainable(self, est):
         """LoRA dropout follows the module's train()/eval() state, like nn.Dropout in the reference."""
@@ -570,7 +569,6 @@ class _EstimatorFn(torch.autograd.Function):
 
 def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
     ne = native_of(module)
-    ne.sync_lora()
     dev = ne.device
     x_, mu_, t_ = _prep_g(x, dev), _prep_g(mu, dev), _prep(t, dev)
     mask_ = _prep(mask, dev).reshape(mask.shape[0], -1)
@@ -581,7 +579,9 @@ def estimator_forward(module, x, mask, mu, t, spks=None, cond=None):
                                               any(v is not None and v.requires_grad for v in (x_, mu_, spks_, cond_)))
     if needs_grad:
         ne.sync_dropout(bool(module.training) and not getattr(module, "cvflow_ignore_lora_dropout", False))
+        ne.sync_lora(need_folded=not ne.trains_unfolded())
         out = _EstimatorFn.apply(ne, x_, mask_, mu_, t_, spks_, cond_, iso, *[p for p, _, _ in ne.lora_views])
     else:
+        ne.sync_lora(need_folded=True)
         out = ne.forward(x_, mask_, mu_, t_, spks_, cond_, iso_len=iso, training=False)
     return out.to(x.dtype) if x.dtype != torch.float32 else out

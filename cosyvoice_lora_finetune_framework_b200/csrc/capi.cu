@@ -101,6 +101,10 @@ extern "C" CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream)
   if (!h) { set_error("cvflow_lora_refresh: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->lora_refresh((cudaStream_t)stream) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
 }
+extern "C" CVFLOW_API int cvflow_lora_refresh_factors(cvflow_estimator* h, void* stream) {
+  if (!h) { set_error("cvflow_lora_refresh_factors: null handle"); return CVFLOW_ERR_ARG; }
+  return h->e->lora_refresh((cudaStream_t)stream, false) ? CVFLOW_ERR_CUDA : CVFLOW_OK;
+}
 extern "C" CVFLOW_API int cvflow_lora_prepare(cvflow_estimator* h, void* stream) {
   if (!h) { set_error("cvflow_lora_prepare: null handle"); return CVFLOW_ERR_ARG; }
   return h->e->lora_refresh((cudaStream_t)stream, false) ? CVFLOW_ERR_CUDA : CVFLOW_OK;

@@ -74,6 +74,7 @@ class Estimator {
   int bind(const char* name, void* ptr, long numel, int dtype);
   void set_workspace(void* p, long bytes) { ws_ = p; ws_bytes_ = bytes; plans_.clear(); }
   long workspace_bytes(int B, int T, int training);
+  // merge = true: every 16-bit LoRA operand image (folded W_eff in both layouts + factor images); false: factor images only
   int lora_refresh(cudaStream_t st, bool merge = true);
   int forward(const EstimatorIO& io, cudaStream_t st);
   int backward(const void* dpred16, float grad_scale, const float* grad_scale_dev, cudaStream_t st,
@@ -159,7 +160,7 @@ class Estimator {
   cudaStream_t side_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_done_[2] = {nullptr, nullptr};
   bool ev_done_valid_[2] = {false, false};
-  bool wgrad_side_ = false;  // CVFLOW_WGRAD_SIDE=1 (measured: no gain over PDL-chained launches on one stream)
+  bool wgrad_side_ = true;   // CVFLOW_WGRAD_SIDE=0 disables (see the constructor for the measurement)
   struct SolveGraph { cudaGraph_t graph; cudaGraphExec_t exec; };
   std::map<std::pair<int, int>, SolveGraph> solves_;   // (T, n_steps) -> captured solve
   float* solve_keep_dev_ = nullptr;     // {1, 0}: CFG keep factors of the (cond, uncond) rows

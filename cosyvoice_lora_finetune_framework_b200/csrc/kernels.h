@@ -110,9 +110,13 @@ struct LoraBlockPtrs {       // one attention block: q, k, v + the merged 16-bit
   void* weff_t;              // [256][1536]
   void* acat16;              // [64][256]  rows p*r+j = A_p[j]      (nullable)
   void* bblk16;              // [64][1536] rows p*r+j, cols p*512+n = B_p[n][j]
+  void* w0d;                 // lora_dropout > 0: [1536][320] = [W0 | s B_cat] (columns 256 + p*r+j of row p*512+n = s B_p[n][j]), nullable
+  void* w0t_ext;             // lora_dropout > 0: [320][1536] = [W0^T ; B_blk] (rows 256 + p*r+j as bblk16), nullable
 };
-// W_eff = W + s * B A for every block in one launch; writes both layouts.
-int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, cudaStream_t st);
+// All 16-bit LoRA operand images of every block in one launch. factors_only = 0: W_eff = W + s B A in both layouts plus
+// the factor images (A_cat, B_blk, LoRA parts of w0d / w0t_ext); factors_only = 1: the factor images alone (what a
+// training step with lora_dropout > 0 consumes: it never reads the folded W_eff).
+int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, int factors_only, cudaStream_t st);
 // dA, dB of the three projections of one block: tcgen05 reductions over the token axis of
 // dY^T u and x^T v (u = x A_cat^T, v = dY B_blk^T are produced by two engine GEMMs, [M][64] each).
 int lora_wgrad_plan_bytes();

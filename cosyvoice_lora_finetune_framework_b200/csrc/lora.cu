@@ -20,7 +20,7 @@ namespace cvflow {
 // The K-major image is written row by row (512 B per warp store); the transposed image goes through a 16-bit shared-memory
 // tile so that every row of it receives 64 contiguous values (128 B) instead of 2-element fragments.
 static constexpr int kMergeRows = 64;
-__global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __restrict__ blocks, int r, int bf) {
+__global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __restrict__ blocks, int r, int bf, int factors_only) {
   __shared__ __align__(16) uint16_t tile[kMergeRows][256 + 8];
   const LoraBlockPtrs& blk = blocks[blockIdx.z];
   const int p = blockIdx.y;
@@ -39,11 +39,18 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __
     uint16_t* bblk = reinterpret_cast<uint16_t*>(blk.bblk16);
     if (blockIdx.x == 0)
       for (int j = 0; j < r; ++j) acat[(p * r + j) * 256 + k] = f32_to_h16(a[j], bf);
+    uint16_t* w0d = reinterpret_cast<uint16_t*>(blk.w0d);
+    uint16_t* w0t = reinterpret_cast<uint16_t*>(blk.w0t_ext);
     for (int t = k; t < kMergeRows * r; t += 256) {
       const int i = t / r, j = t - i * r;
-      bblk[(long)(p * r + j) * 1536 + p * 512 + n0 + i] = f32_to_h16(lp.Bm[(n0 + i) * r + j], bf);
+      const float bv = lp.Bm[(n0 + i) * r + j];
+      const uint16_t b16 = f32_to_h16(bv, bf);
+      bblk[(long)(p * r + j) * 1536 + p * 512 + n0 + i] = b16;
+      if (w0t) w0t[(long)(256 + p * r + j) * 1536 + p * 512 + n0 + i] = b16;
+      if (w0d) w0d[(long)(p * 512 + n0 + i) * 320 + 256 + p * r + j] = f32_to_h16(bv * lp.scaling, bf);
     }
   }
+  if (factors_only) return;
   for (int i = 0; i < kMergeRows; ++i) {
     const int n = n0 + i;
     float w = lp.W[n * 256 + k];
@@ -68,9 +75,9 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const LoraBlockPtrs* __
     *reinterpret_cast<uint4*>(weff_t + (long)kk * 1536 + p * 512 + n0 + 8 * u) = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
-int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, cudaStream_t st) {
+int launch_lora_merge(const LoraBlockPtrs* blocks_dev, int nblocks, int r, int bf16, int factors_only, cudaStream_t st) {
   if (r > 16) return -1;
-  lora_merge_kernel<<<dim3(512 / kMergeRows, 3, nblocks), 256, 0, st>>>(blocks_dev, r, bf16);
+  lora_merge_kernel<<<dim3(512 / kMergeRows, 3, nblocks), 256, 0, st>>>(blocks_dev, r, bf16, factors_only);
   LAUNCH_RET();
 }
 

@@ -311,7 +311,7 @@ class ConditionalCFM(nn.Module):
         spks_ = fg(spks) if spks is not None else None
         cond_ = fg(cond) if cond is not None else None
         keep_ = keep.to(dev).float().contiguous() if keep is not None else None
-        ne.sync_lora()
+        ne.sync_lora(need_folded=not ne.trains_unfolded())
         S = min(int(self.num_streams), b)
         if S > 1:
             if upstream:

@@ -256,7 +256,7 @@ class FlowLoRATrainer:
                                          C.c_void_p(self.hyper.data_ptr()), st), "cvflow_adamw_step")
         g.zero_()
         ne.mark_dirty()
-        ne.sync_lora()
+        ne.sync_lora(need_folded=not ne.trains_unfolded())      # lora_dropout > 0: factor images only (the folded W_eff is unused)
         self.micro = 0
 
     def train_step(self, x1, mask, mu, spks, cond, prompt_lens=None):

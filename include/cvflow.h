@@ -120,6 +120,10 @@ CVFLOW_API int cvflow_lora_refresh(cvflow_estimator* h, void* stream);
 /* Same pointer-table setup without the merge launch: for a second handle that shares the weight
  * images of another one (batch shards running concurrently on several streams). */
 CVFLOW_API int cvflow_lora_prepare(cvflow_estimator* h, void* stream);
+/* The light refresh a training step with lora_dropout > 0 needs after its optimiser update: only the 16-bit FACTOR images
+ * (A_cat, B_blk and the LoRA parts of "<block>.w0d" / "<block>.w0t_ext"), not the 100 MB of folded W_eff images that such
+ * a step never reads. Call cvflow_lora_refresh before the next eval() / lora_dropout = 0 forward. */
+CVFLOW_API int cvflow_lora_refresh_factors(cvflow_estimator* h, void* stream);
 
 typedef struct cvflow_estimator_io {
   const float* x;    int32_t x_nb;     /* [x_nb][80][T]; batch row b reads row b % x_nb */
