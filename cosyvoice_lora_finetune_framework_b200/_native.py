@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("n_valid", C.c_int32), ("alpha", C.c_float), ("act", C.c_int32), ("bias", C.c_void_p),
         ("aux_out", C.c_void_p), ("mul_src", C.c_void_p), ("ld_aux", C.c_int64),
         ("rowmask", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64), ("dbg", C.c_void_p),
-        ("gn_part", C.c_void_p),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("gn_part", C.c_void_p),
     ]
 
 

@@ -43,7 +43,7 @@ extern "C" CVFLOW_API int cvflow_gemm(const cvflow_gemm_desc* d, void* stream) {
   a.col_off = d->col_off; a.n_valid = d->n_valid; a.alpha = d->alpha; a.act = d->act;
   a.bias = d->bias; a.aux_out = d->aux_out; a.mul_src = d->mul_src; a.ld_aux = d->ld_aux;
   a.rowmask = d->rowmask; a.resid = d->resid; a.ldr = d->ldr; a.dbg = (long long*)d->dbg;
-  a.gn_part = d->gn_part;
+  a.gn_part = d->gn_part; a.ln_gamma = d->ln_gamma; a.ln_beta = d->ln_beta;
   GemmParams p;
   if (gemm_prepare(a, &p, error_buf(), error_buf_len())) return CVFLOW_ERR_ARG;
   int r = gemm_launch(p, (cudaStream_t)stream);

@@ -37,6 +37,13 @@ Estimator::Estimator(const EstimatorConfig& c) : cfg(c) {
   // of the backward: they run on a side stream next to the main chain (fork after the q/k/v dgrad GEMM, join before the
   // gradients are finalised). Measured on B200, 32 x 400: 17.15 -> 16.39 ms per step with lora_dropout 0.05, 15.20 -> 14.91
   // folded. CVFLOW_WGRAD_SIDE=0 keeps everything on one stream.
+  // LayerNorm fused into the epilogue of the GEMM that finishes the residual row (to_out -> norm3, FF2 -> the next block's
+  // norm1 when that LayerNorm is not the fused LoRA-dropout form). Parity-green, but MEASURED SLOWER on B200 at 32 x 400
+  // (step 16.25 -> 16.80 ms with lora_dropout 0.05, 14.92 -> 15.64 ms folded): the row-owning 128x256 tile leaves 50 CTAs
+  // with a 3-pass, 11 us epilogue (4 chunks per warp, each waiting on its own un-coalesced residual loads and TMA stores),
+  // against 200 CTAs of 128x64 + a 5 us LayerNorm launch. Opt-in: CVFLOW_LN_FUSE=1.
+  const char* e4 = getenv("CVFLOW_LN_FUSE");
+  ln_fuse_ = e4 && e4[0] == '1';
   const char* e2 = getenv("CVFLOW_WGRAD_SIDE");
   wgrad_side_ = !(e2 && e2[0] == '0');
 #ifdef CVFLOW_PROFILING_BUILD
@@ -434,7 +441,7 @@ int Estimator::resnet_fwd(const std::string& P, const void* xin, long ld_in, int
 }
 
 int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, const int* kmax,
-                      int iso_p, float** h_out, TBRec* rec) {
+                      int iso_p, float** h_out, TBRec* rec, const std::string& Qnext) {
   const long M = (long)B * L;
   // with LoRA in training the q/k/v GEMM also emits u = x1 A_cat^T as 64 extra output columns
   // (operand rows 1536..1599 of weff_ext), which the wgrad kernel consumes in the backward pass
@@ -444,7 +451,9 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   const bool ext = cfg.lora_r > 0 && training_ && !drop;
   const long ldq = ext ? 1600 : 1536;
   const TbSet& es = scr_tb_[lora_idx & 1];      // eval(): ping-pong sets, nothing is stashed
-  void* x1 = training_ ? alloc(M * 256 * 2) : es.x1;
+  const bool x1_ready = next_x1_ != nullptr;      // written by the previous block's FF2 epilogue (fused LayerNorm)
+  void* x1 = x1_ready ? next_x1_ : (training_ ? alloc(M * 256 * 2) : es.x1);
+  next_x1_ = nullptr;
   void* ud = drop ? alloc(M * 64 * 2) : nullptr;
   uint32_t* bits = drop ? (uint32_t*)alloc(M * 24 * 4) : nullptr;
   void* qkv = training_ ? alloc(M * ldq * 2) : es.qkv;
@@ -455,7 +464,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
   void* pre = (training_ || fused_mlp_) ? alloc(M * 1024 * 2) : nullptr;      // GELU pre-activation: backward only
   void* g16 = fused_mlp_ ? nullptr : scr_g16_;
   float* h2 = training_ ? (float*)alloc(M * 256 * 4) : es.h2;
-  if (!dry_) {
+  if (!dry_ && !x1_ready) {
     prof_begin(3, (double)M * (drop ? 1536 + 128 + 96 : 1536));   // algorithmic bytes: fp32 row in, 16-bit row out (+ u_d, bits)
     if (drop)    // LayerNorm, mask draw and the masked down-projection u_d in one pass over the residual stream
       CKL(launch_ln_lora_drop_fwd(h0, (const float*)get(Q + ".norm1.w", 2, 256), (const float*)get(Q + ".norm1.b", 2, 256),
@@ -494,9 +503,14 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     GemmArgs g = linear_args(o, M, 512, get(Q + ".wo", cfg.bf16, 256L * 512), 256, h1, 1);
     g.bias = (const float*)get(Q + ".bo", 2, 256);
     g.resid = h0; g.ldr = 256;
+    if (ln_fuse_) {   // x3 = LayerNorm3(h1) from the same epilogue: the 128x256 tile owns whole rows
+      g.ln_gamma = (const float*)get(Q + ".norm3.w", 2, 256);
+      g.ln_beta = (const float*)get(Q + ".norm3.b", 2, 256);
+      g.aux_out = x3; g.ld_aux = 256;
+    }
     CK(run_gemm(g));
   }
-  if (!dry_) {
+  if (!dry_ && !ln_fuse_) {
     prof_begin(3, (double)M * 1536);
     if (!(kSkip(skip_) & 2u)) CKL(launch_layernorm_fwd(h1, (const float*)get(Q + ".norm3.w", 2, 256), (const float*)get(Q + ".norm3.b", 2, 256), x3,
                             M, cfg.bf16, stream_));
@@ -518,6 +532,12 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
       GemmArgs g = linear_args(g16, M, 1024, get(Q + ".w2", cfg.bf16, 256L * 1024), 256, h2, 1);
       g.bias = (const float*)get(Q + ".b2", 2, 256);
       g.resid = h1; g.ldr = 256;
+      if (ln_fuse_ && !drop && !Qnext.empty()) {   // x1 of the NEXT block = LayerNorm1_next(h2), from this epilogue
+        next_x1_ = training_ ? alloc(M * 256 * 2) : scr_tb_[(lora_idx + 1) & 1].x1;
+        g.ln_gamma = (const float*)get(Qnext + ".norm1.w", 2, 256);
+        g.ln_beta = (const float*)get(Qnext + ".norm1.b", 2, 256);
+        g.aux_out = next_x1_; g.ld_aux = 256;
+      }
       CK(run_gemm(g));
     }
   }
@@ -538,7 +558,8 @@ int Estimator::stage_fwd(const std::string& S, int res_idx, const void* xin, lon
   for (int j = 0; j < cfg.n_blocks; ++j) {
     TBRec tr;
     const std::string Q = S + ".1." + std::to_string(j);
-    CK(tb_fwd(Q, tb_counter_++, h, B, L, mask, mask == mask1_ ? kmax1_ : kmax2_, iso_p, &h, &tr));
+    const std::string Qnext = j + 1 < cfg.n_blocks ? S + ".1." + std::to_string(j + 1) : std::string();
+    CK(tb_fwd(Q, tb_counter_++, h, B, L, mask, mask == mask1_ ? kmax1_ : kmax2_, iso_p, &h, &tr, Qnext));
     st.tbs.push_back(tr);
   }
   st.h_out = h;
@@ -651,6 +672,7 @@ int Estimator::forward_impl(const EstimatorIO& io) {
   const int B = io.B, T = io.T, T2 = (T + 1) / 2;
   training_ = io.training != 0;
   gemm_idx_ = 0; attn_idx_ = 0; tb_counter_ = 0; wg_idx_ = 0; mlp_idx_ = 0;
+  next_x1_ = nullptr;
   stages_.clear();
   const int nres = n_resnets();
   float* mask1 = (float*)alloc((long)B * T * 4);

@@ -122,7 +122,7 @@ class Estimator {
   int resnet_fwd(const std::string& P, const void* xin, long ld_in, int col0, int cin, int B, int L, const float* mask,
                  const float* tb, long tb_stride, float** h_out, ResnetRec* rec);
   int tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int L, const float* mask, const int* kmax, int iso_p,
-             float** h_out, TBRec* rec);
+             float** h_out, TBRec* rec, const std::string& Qnext);
   int stage_fwd(const std::string& S, int res_idx, const void* xin, long ld_in, int col0, int cin, int B, int L, int T,
                 const float* mask, int iso_len, float** h_out);
   int tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_grad, float grad_scale, BwdTemps& tmp);
@@ -138,6 +138,8 @@ class Estimator {
   bool training_ = false;
   bool dry_ = false, missing_ = false, oom_ = false, have_fwd_ = false, lora_table_ready_ = false;
   int gemm_idx_ = 0, attn_idx_ = 0, tb_counter_ = 0, wg_idx_ = 0, mlp_idx_ = 0;
+  bool ln_fuse_ = false;    // CVFLOW_LN_FUSE=1: LayerNorm in the row-owning GEMM epilogue (measured slower, see estimator.cu)
+  void* next_x1_ = nullptr; // x1 of the next transformer block when the previous FF2 epilogue already wrote it
   bool fused_mlp_ = false;  // CVFLOW_FUSED_MLP=1 runs the feed-forward as one fused launch (mlp.cu) instead of two engine GEMMs
   long launches_ = 0;
   cudaStream_t stream_ = nullptr;

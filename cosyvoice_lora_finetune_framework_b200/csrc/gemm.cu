@@ -29,7 +29,8 @@ struct GemmCfg {
   static constexpr int kStagingBytes = 8 * 2048;   // per epilogue warp: 32 rows x 64 B (32 x 16-bit, or 16 x fp32 per pass)
   // two CTAs per SM leave (228 KB - 2 x 1 KB reserved) / 2 = 115,712 B each: stages + staging + 128 B of
   // barriers + 896 B of alignment slack (the dynamic window is at least 128-byte aligned; checked at run time)
-  static constexpr int kPayloadBytes = kStages * kStageBytes + kStagingBytes + 128;
+  static constexpr int kExchBytes = (BN == 256) ? 2048 : 0;   // fused LayerNorm: row sums exchanged between the two column halves
+  static constexpr int kPayloadBytes = kStages * kStageBytes + kStagingBytes + 128 + kExchBytes;
   static constexpr int kSmemBytes = kPayloadBytes + 896;
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
@@ -261,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       };
 
       EpiPrefetch pf;
+      float ln_s1 = 0.f;
       prefetch(half, pf);
       mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -366,6 +368,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               x[4 * j + 2] += __uint_as_float(pf.v[j].z); x[4 * j + 3] += __uint_as_float(pf.v[j].w);
             }
           }
+          if constexpr (BN == 256) {
+            if (p.ln_gamma) {   // fused LayerNorm, pass 1: the finished fp32 row goes back into TMEM, its sum is taken
+              uint32_t w0[16], w1[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { w0[j] = __float_as_uint(x[j]); w1[j] = __float_as_uint(x[16 + j]); ln_s1 += x[j] + x[16 + j]; }
+              tmem_st_32x32b_x16(t_acc + (uint32_t)(c * 32), w0);
+              tmem_st_32x32b_x16(t_acc + (uint32_t)(c * 32 + 16), w1);
+            }
+          }
           if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
           if (it == 0 && threadIdx.x == 64 && cc == 0) stamp(9);
           if (p.epi_direct == 2) {
@@ -410,6 +421,63 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 4; ++j) dst[j] = pack8_h16(x + 8 * j, bf);
           }
           if (it == 0 && threadIdx.x == 64) stamp(cc == 0 ? 10 : 12);
+        }
+      }
+      if constexpr (BN == 256) {
+        if (p.ln_gamma) {
+          // fused LayerNorm, passes 2 and 3 over the row kept in TMEM (this warp: 32 rows x its 4 chunks = 128 columns;
+          // the other column half of the same rows belongs to warp +-4: sums cross through shared memory)
+          const uint32_t exch = bar_base + 128u;
+          const int row = q * 32 + lane;
+          tmem_st_wait();
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(exch + (uint32_t)(half * 128 + row) * 4u), "f"(ln_s1) : "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          float sa, sb;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sa) : "r"(exch + (uint32_t)row * 4u) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sb) : "r"(exch + (uint32_t)(128 + row) * 4u) : "memory");
+          const float mean = (sa + sb) * (1.f / 256.f);
+          float s2 = 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_acc + (uint32_t)((cc * 2 + half) * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) - mean; s2 = fmaf(d, d, s2); }
+          }
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(exch + (uint32_t)(256 + half * 128 + row) * 4u), "f"(s2) : "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sa) : "r"(exch + (uint32_t)(256 + row) * 4u) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sb) : "r"(exch + (uint32_t)(384 + row) * 4u) : "memory");
+          const float rstd = rsqrtf((sa + sb) * (1.f / 256.f) + 1e-5f);
+#pragma unroll 1
+          for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
+            const int nn = (cc * 2 + half) * 32;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_acc + (uint32_t)nn, r);
+            tmem_ld_wait();
+            float y[32];
+            const float4* gp = reinterpret_cast<const float4*>(p.ln_gamma + nn);
+            const float4* bp = reinterpret_cast<const float4*>(p.ln_beta + nn);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(gp + j), b4 = __ldg(bp + j);
+              y[4 * j + 0] = (__uint_as_float(r[4 * j + 0]) - mean) * rstd * g4.x + b4.x;
+              y[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
+              y[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
+              y[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+            }
+            if (p.epi_direct) {
+              stage_h16(y);
+              store_slice(p.aux_out, p.ld_aux * 2, (long)nn * 2, b, i0);
+            } else {
+              stage_release();
+              stage_h16(y);
+              stage_store(&p.tmAux, nn, i0 + q * 32, b);
+            }
+          }
+          // the exchange slots are reused by the next tile: every warp has read them before anyone writes again
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }
       // all of this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
@@ -550,6 +618,12 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->mul_src = a.mul_src; p->ld_aux = a.ld_aux; p->rowmask = a.rowmask; p->resid = a.resid;
   p->ldr = a.ldr;
   p->gn_part = a.gn_part;
+  p->ln_gamma = a.ln_gamma; p->ln_beta = a.ln_beta;
+  if (a.ln_gamma) {
+    if (!a.ln_beta || !a.aux_out || a.N != 256 || a.n_valid != 256 || a.transposed_out || !a.out_f32 || a.act != ACT_NONE ||
+        a.rmul != 1 || a.roff != 0 || a.col_off != 0)
+      GEMM_FAIL("gemm: fused LayerNorm needs N = n_valid = 256, fp32 row-major output, no activation, aux_out = 16-bit x~");
+  }
   if (a.gn_part && (a.transposed_out || a.n_valid % 32)) GEMM_FAIL("gemm: gn_part needs a row-major output with n_valid %% 32 == 0");
   // tile shape: 256-wide tiles only when N divides evenly and there is more than a wave of them
   const long mtiles = (long)p->tiles_per_batch * a.nbatch;
@@ -561,6 +635,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= bn256_min) bn = 256;
   else if (mtiles * ((a.n_valid + 127) / 128) >= 2 * 148 || a.n_valid > 512) bn = 128;
   if (a.transposed_out) bn = 128;
+  if (a.ln_gamma) bn = 256;      // the tile must own whole rows
   p->block_n = bn;
   p->grid_x = (int)mtiles;
   p->grid_y = (a.n_valid + bn - 1) / bn;
@@ -622,6 +697,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
       }
     }
   }
+  if (a.ln_gamma && !p->tma_out && !p->epi_direct) GEMM_FAIL("gemm: fused LayerNorm needs 16-byte aligned outputs");
   if (reinterpret_cast<uintptr_t>(a.W) & 15) GEMM_FAIL("gemm: W must be 16-byte aligned");
   int r = encode_2d(&p->tmW, a.W, a.bf16, (uint64_t)a.Ktot, (uint64_t)a.N, (uint64_t)a.Ktot * 2, BK,
                     bn);

@@ -60,6 +60,12 @@ struct GemmArgs {
   const float* rowmask = nullptr;  // [nbatch*out_rows]
   const float* resid = nullptr;    // fp32 [nbatch*out_rows][ldr] (may alias out)
   long ldr = 0;
+  // LayerNorm of the finished output rows fused into the epilogue (modules.py:349-375: h += to_out(...); x~ = LN3(h)):
+  // with N = n_valid = 256 one 128x256 tile owns whole rows, so the epilogue writes the fp32 row (out, with bias and
+  // residual) AND x~ = (row - mean) * rstd * ln_gamma + ln_beta as 16-bit to aux_out (ld_aux), statistics exact two-pass
+  // over the row kept in TMEM. Needs out_f32, act == ACT_NONE, rmul == 1, roff == 0.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
   // GroupNorm statistics of the output (groups of 32 channels) taken in the epilogue, before the 16-bit rounding:
   // gn_part[((b * gn_nsplit + tile_in_batch * 4 + lane_quadrant) * (n_valid / 32) + group) * 3] = {n, mean, M2} over the
   // valid rows of that 32-row slice (Chan-mergeable partials; the consumer merges them). gn_nsplit = 4 * ceil(R / 128).
@@ -82,6 +88,7 @@ struct alignas(64) GemmParams {
   float alpha; const float* bias; int act; void* aux_out; const void* mul_src; long ld_aux;
   const float* rowmask; const float* resid; long ldr;
   float* gn_part;
+  const float* ln_gamma; const float* ln_beta;
   long long* dbg;
   const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
   int block_n;   // 64, 128 or 256

@@ -82,6 +82,10 @@ typedef struct cvflow_gemm_desc {
   const float* resid;
   int64_t ldr;
   int64_t* dbg;         /* optional: 16 x int64 globaltimer stamps per CTA (profiling aid), else NULL */
+  const float* ln_gamma; /* optional: LayerNorm fused into the epilogue (modules.py:349-375: h += to_out(..); x~ = LN(h)): with */
+  const float* ln_beta;  /* N = n_valid = 256 and an fp32 output the tile owns whole rows; besides out (+ bias + resid) the
+                          * epilogue writes x~ = (row - mean) rstd ln_gamma + ln_beta (eps 1e-5, two-pass statistics) as
+                          * 16-bit to aux_out / ld_aux. Needs act = 0, rmul = 1, roff = 0, col_off = 0. Else NULL. */
   float* gn_part;       /* optional: GroupNorm partial statistics of the output taken in the epilogue (before the 16-bit
                          * rounding): {n, mean, M2} per (batch, 32-row slice, 32-channel group),
                          * [nbatch][4 * ceil(R / 128)][n_valid / 32][3] floats, Chan-mergeable (replaces the separate

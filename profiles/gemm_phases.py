@@ -13,13 +13,17 @@ dt = torch.bfloat16
 L = N.lib()
 names = ["start", "grid-dependency wait passed", "first stage landed (MMA warp)", "last tile's MMAs issued", "first accumulator ready (epilogue)",
          "last epilogue done", "exit"]
-for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6400, 1024, 256, "gelu"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (6400, 256, 1024, "h16"), (6400, 512, 256, "h16"), (6400, 256, 1536, "h16"), (6400, 64, 1536, "h16"), (12800, 1536, 256, "h16"), (12800, 256, 1024, "resid")]:
+for (M, Nn, K, mode) in [(6400, 1536, 256, "h16"), (6400, 256, 512, "resid"), (6400, 1024, 256, "gelu"), (6400, 256, 1024, "resid"), (6400, 1024, 256, "mulgrad"), (6400, 256, 1024, "h16"), (6400, 512, 256, "h16"), (6400, 256, 1536, "h16"), (6400, 64, 1536, "h16"), (12800, 1536, 256, "h16"), (12800, 256, 1024, "resid"),
+                        (6400, 256, 512, "resid+ln"), (6400, 256, 1024, "resid+ln")]:
     A = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
     W = (torch.randn(Nn, K, device="cuda") * 0.1).to(dt)
-    out = torch.randn(M, Nn, device="cuda") if mode == "resid" else torch.empty(M, Nn, device="cuda", dtype=dt)
+    out = torch.randn(M, Nn, device="cuda") if mode.startswith("resid") else torch.empty(M, Nn, device="cuda", dtype=dt)
     kw = {}
-    if mode == "resid":
+    if mode.startswith("resid"):
         kw = dict(resid=out, ldr=Nn, bias=torch.randn(Nn, device="cuda"))
+    if mode == "resid+ln":      # LayerNorm fused into the row-owning 128x256 epilogue
+        kw.update(ln_gamma=torch.ones(Nn, device="cuda"), ln_beta=torch.zeros(Nn, device="cuda"),
+                  aux_out=torch.empty(M, Nn, device="cuda", dtype=dt), ld_aux=Nn)
     if mode == "gelu":
         kw = dict(act=N.ACT_GELU_TANH, aux_out=torch.empty(M, Nn, device="cuda", dtype=dt), ld_aux=Nn, bias=torch.randn(Nn, device="cuda"))
     if mode == "mulgrad":

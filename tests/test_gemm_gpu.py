@@ -38,7 +38,7 @@ def _desc(A, W, out, *, segs, R, nbatch=1, a_rows=None, dtype=torch.float16, **k
     d.n_valid = kw.get("n_valid", W.shape[0])
     d.alpha = kw.get("alpha", 1.0)
     d.act = kw.get("act", 0)
-    for name in ("bias", "aux_out", "mul_src", "rowmask", "resid", "gn_part"):
+    for name in ("bias", "aux_out", "mul_src", "rowmask", "resid", "gn_part", "ln_gamma", "ln_beta"):
         t = kw.get(name)
         setattr(d, name, t.data_ptr() if t is not None else None)
     d.ld_aux = kw.get("ld_aux", 0)
@@ -185,3 +185,27 @@ def test_conv_k3_groupnorm_partials(B, L, dtype):
     g = ref.double().view(B, L, 8, 32)
     assert torch.allclose(mean, g.mean(dim=(1, 3)), atol=2e-3, rtol=1e-3)
     assert torch.allclose(var, g.var(dim=(1, 3), unbiased=False), rtol=3e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,K", [(6400, 512), (333, 1024), (12800, 512), (128, 64)])
+def test_linear_fused_layernorm(M, K, dtype):
+    """h = resid + A W^T + bias (fp32) and x~ = LayerNorm(h) (16-bit) from ONE launch: the 128x256 tile owns whole rows, the
+    statistics are taken two-pass over the row kept in TMEM (replaces `h = h + to_out(o); x = norm3(h)`, modules.py:349-375)."""
+    torch.manual_seed(2)
+    A = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    W = (torch.randn(256, K, device="cuda") * 0.1).to(dtype)
+    bias = torch.randn(256, device="cuda")
+    resid = torch.randn(M, 256, device="cuda") * 3.0 + 1.5        # a row mean away from zero
+    gamma, beta = torch.rand(256, device="cuda") + 0.5, torch.randn(256, device="cuda")
+    out = resid.clone()
+    xn = torch.full((M, 256), float("nan"), device="cuda").to(dtype)
+    d = _desc(A, W, out, segs=[(0, 0, 0, K // 64)], R=M, dtype=dtype, bias=bias, resid=out, ldr=256, ln_gamma=gamma,
+              ln_beta=beta, aux_out=xn, ld_aux=256)
+    _run(d)
+    ref_h = resid + A.float() @ W.float().t() + bias
+    ref_x = torch.nn.functional.layer_norm(ref_h, (256,), gamma, beta, eps=1e-5)
+    assert torch.allclose(out, ref_h, atol=2e-3, rtol=1e-3), float((out - ref_h).abs().max())
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    assert torch.isfinite(xn.float()).all()
+    assert torch.allclose(xn.float(), ref_x, atol=tol, rtol=tol), float((xn.float() - ref_x).abs().max())
