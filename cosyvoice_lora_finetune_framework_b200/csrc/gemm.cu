@@ -20,9 +20,12 @@ namespace cvflow {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 
-template <int BN>
+// DEEP (BN = 128 only): one CTA per SM with six stages (192 KB in flight instead of 96 KB). A CTA's main loop runs at
+// (bytes in flight) / (TMA round trip of ~1.1 us); the narrow-N GEMMs (N = 256: 200 tiles of 128x64, most SMs holding a
+// single CTA) spent 4-6 us of their 8-10 us there. 100 tiles of 128x128 with twice the bytes in flight halve that.
+template <int BN, int DEEP = 0>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kStages = DEEP ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -32,7 +35,7 @@ struct GemmCfg {
   static constexpr int kExchBytes = (BN == 256) ? 2048 : 0;   // fused LayerNorm: row sums exchanged between the two column halves
   static constexpr int kPayloadBytes = kStages * kStageBytes + kStagingBytes + 128 + kExchBytes;
   static constexpr int kSmemBytes = kPayloadBytes + 896;
-  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
+  static constexpr int kCtasPerSm = (BN == 256 || DEEP) ? 1 : 2;
   static constexpr int kTmemCols = BN;          // 64 / 128 / 256: powers of two >= 32
   static constexpr int kChunksPerWarp = BN / 64; // 8 epilogue warps: 2 per TMEM lane quadrant
 };
@@ -51,10 +54,10 @@ struct EpiPrefetch {
 // CL > 1: thread-block clusters of CL CTAs along N work on the same m-tile; every CTA fetches 1/CL of the A rows of
 // a k-block and TMA-multicasts it to the whole cluster, so the L2 -> SM traffic of the (bandwidth-bound, short-K)
 // GEMMs of this model drops from A + B to A/CL + B per k-block.
-template <int BN, int CL>
-__global__ void __launch_bounds__(kGemmThreads, (BN == 256) ? 1 : 2)
+template <int BN, int CL, int DEEP = 0>
+__global__ void __launch_bounds__(kGemmThreads, (BN == 256 || DEEP) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   if (smem_base - smem_u32(smem_raw) + Cfg::kPayloadBytes > Cfg::kSmemBytes) __trap();   // alignment slack exceeded
@@ -261,18 +264,24 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         }
       };
 
-      EpiPrefetch pf;
+      // DEEP: both chunks' residual / pre-activation operands are requested before the accumulator wait (registers allow
+      // it at one CTA per SM); otherwise the next chunk's are requested after the current chunk's math
+      constexpr int kNPf = DEEP ? 2 : 1;
+      constexpr int kUnroll = DEEP ? 2 : 1;
+      EpiPrefetch pfs[kNPf];
       float ln_s1 = 0.f;
-      prefetch(half, pf);
+      prefetch(half, pfs[0]);
+      if constexpr (DEEP) prefetch(half + 2, pfs[1]);
       mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (it == 0 && threadIdx.x == 64) stamp(4);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll kUnroll
       for (int cc = 0; cc < Cfg::kChunksPerWarp; ++cc) {
         const int c = cc * 2 + half;
         const int nn = n0 + c * 32;
         if (nn >= p.n_valid) break;  // warp-uniform
+        EpiPrefetch& pf = pfs[DEEP ? cc : 0];
         uint32_t r[32];
         __syncwarp();
         tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
@@ -377,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               tmem_st_32x32b_x16(t_acc + (uint32_t)(c * 32 + 16), w1);
             }
           }
-          if (cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
+          if (!DEEP && cc + 1 < Cfg::kChunksPerWarp) prefetch(c + 2, pf);   // next chunk's operands fly during the stores
           if (it == 0 && threadIdx.x == 64 && cc == 0) stamp(9);
           if (p.epi_direct == 2) {
             // diagnostic build of the launch (CVFLOW_GEMM_EPI=2): no stores at all
@@ -636,6 +645,14 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   else if (mtiles * ((a.n_valid + 127) / 128) >= 2 * 148 || a.n_valid > 512) bn = 128;
   if (a.transposed_out) bn = 128;
   if (a.ln_gamma) bn = 256;      // the tile must own whole rows
+  // deep pipeline for the narrow-N, long-K shapes (N <= 256): see GemmCfg
+  static int deep_env = -1;
+  if (deep_env < 0) { const char* e = getenv("CVFLOW_GEMM_DEEP"); deep_env = e ? atoi(e) : 0; }   // measured: faster stand-alone (FF2 10.1 -> 9.7, q/k/v dgrad 9.7 -> 8.7 us), slower inside the PDL-chained step (16.17 -> 16.75 ms: 100 single-CTA SMs with 208 KB of shared memory keep the next kernel's CTAs out)
+  p->deep = 0;
+  if (deep_env && bn == 64 && !a.transposed_out && !a.ln_gamma && a.n_valid % 128 == 0 && a.n_valid <= 256 && a.Ktot >= 512) {
+    bn = 128;
+    p->deep = 1;
+  }
   p->block_n = bn;
   p->grid_x = (int)mtiles;
   p->grid_y = (a.n_valid + bn - 1) / bn;
@@ -644,7 +661,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   static int cl_env = -1;
   if (cl_env < 0) { const char* e = getenv("CVFLOW_GEMM_CLUSTER"); cl_env = e ? atoi(e) : 1; }
   int cl = 1;
-  if (bn != 256 && !a.transposed_out) cl = p->grid_y >= 4 ? 4 : (p->grid_y >= 2 ? 2 : 1);
+  if (bn != 256 && !a.transposed_out && !p->deep) cl = p->grid_y >= 4 ? 4 : (p->grid_y >= 2 ? 2 : 1);
   if (bn == 128 && cl > 2) cl = 2;
   if (cl_env != 2 && cl_env != 4) cl = 1;
   else if (cl_env < cl) cl = cl_env;
@@ -714,6 +731,7 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
     cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
     cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes);
     cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes);
+    cudaFuncSetAttribute(gemm_tc_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 1>::kSmemBytes);
     attr_done = true;
   }
   static int num_sms = 0;
@@ -724,7 +742,7 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
   }
   const int cl = p.cluster;
   const long total = (long)p.grid_x * ((p.grid_y + cl - 1) / cl) * cl;   // CTAs if every (m-tile, n-group) had its own cluster
-  long slots = (long)num_sms * (p.block_n == 256 ? 1 : 2);
+  long slots = (long)num_sms * ((p.block_n == 256 || p.deep) ? 1 : 2);
   slots -= slots % cl;
   dim3 grid((unsigned)(total < slots ? total : slots));
   cudaLaunchConfig_t cfg{};
@@ -740,7 +758,10 @@ int gemm_launch(const GemmParams& p, cudaStream_t stream) {
     cfg.dynamicSmemBytes = GemmCfg<BN_>::kSmemBytes;               \
     cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN_, CL_>, p);         \
   } while (0)
-  if (p.block_n == 256) CVFLOW_GEMM_LAUNCH(256, 1);
+  if (p.deep) {
+    cfg.dynamicSmemBytes = GemmCfg<128, 1>::kSmemBytes;
+    cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, 1, 1>, p);
+  } else if (p.block_n == 256) CVFLOW_GEMM_LAUNCH(256, 1);
   else if (p.block_n == 128) { if (cl == 2) CVFLOW_GEMM_LAUNCH(128, 2); else CVFLOW_GEMM_LAUNCH(128, 1); }
   else { if (cl == 4) CVFLOW_GEMM_LAUNCH(64, 4); else if (cl == 2) CVFLOW_GEMM_LAUNCH(64, 2); else CVFLOW_GEMM_LAUNCH(64, 1); }
 #undef CVFLOW_GEMM_LAUNCH

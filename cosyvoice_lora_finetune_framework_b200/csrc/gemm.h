@@ -92,6 +92,7 @@ struct alignas(64) GemmParams {
   long long* dbg;
   const void* src_A[2]; const void* src_W;   // operand pointers the tensor maps were encoded for
   int block_n;   // 64, 128 or 256
+  int deep;      // 1: BN = 128 with one CTA per SM and six pipeline stages (narrow-N, long-K shapes)
   int cluster;   // CTAs per cluster along N sharing (multicasting) the A tile: 1, 2 or 4
   int grid_x, grid_y;
 };
