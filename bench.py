@@ -248,6 +248,63 @@ def oracle_euler_fn(T, P_, n_steps, device):
     return run
 
 
+def flow_model_batch(B, T, seed, min_len=0.6):
+    """A batch in the reference's collate schema (train_joint.py dataset: tokens at 50 Hz, mel at 22050/256 Hz)."""
+    g = torch.Generator().manual_seed(seed)
+    feat_len = torch.randint(int(min_len * T) + 1, T + 1, (B,), generator=g)
+    feat_len[0] = T
+    tok_len = (feat_len.float() * 256 * 50 / 22050).long().clamp(min=1)
+    N = int(tok_len.max())
+    feat = torch.full((B, T, 80), -11.5)
+    tok = torch.zeros(B, N, dtype=torch.long)
+    for i in range(B):
+        feat[i, : feat_len[i]] = torch.randn(int(feat_len[i]), 80, generator=g) * 2 - 6
+        tok[i, : tok_len[i]] = torch.randint(0, 4096, (int(tok_len[i]),), generator=g)
+    return {'speech_token': tok, 'speech_token_len': tok_len, 'speech_feat': feat, 'speech_feat_len': feat_len,
+            'embedding': torch.randn(B, 192, generator=g)}
+
+
+def flow_model_leg(a, device, dtype, timed):
+    """One optimiser step of the WHOLE flow model the reference trains in flow_only mode (flow_model.py:248-400:
+    MaskedDiffWithXvec.forward(batch) -> loss.backward() -> clip + AdamW) with the reference's flow_lora target list
+    (estimator attn1 q/k/v AND the Conformer encoder's linear_q/k/v, w_1, w_2; config.py:207-216). The estimator, the
+    CFM and the optimiser run on the CUDA path; what sits in front of the estimator is reported separately so the
+    cost of the path's callers is visible."""
+    import random
+    from cosyvoice_lora_finetune_framework_b200 import flow_model as FM, lora as LR, utils as U
+    from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer
+    B, T = a.batch, a.frames
+    U.set_all_random_seed(4321)
+    m = FM.build_flow_model(None, 'cpu')
+    LR.apply_lora_to_model(m, r=8, lora_alpha=16, lora_dropout=a.lora_dropout,
+                           target_modules=['to_q', 'to_k', 'to_v', 'linear_q', 'linear_k', 'linear_v', 'w_1', 'w_2'])
+    m = m.to(device).train()
+    m.decoder.estimator.cvflow_dtype = dtype
+    m.encoder_autocast = dtype            # the reference trains under Lightning '16-mixed' (config.py:76)
+    upstream = [p for n, p in m.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]
+    tr = FlowLoRATrainer(m.decoder, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, extra_params=upstream)
+    batch = flow_model_batch(B, T, 4321, a.min_len)
+    random.seed(7)
+
+    def step():
+        out = m(batch, device)
+        out['loss'].backward()
+        tr.optimizer_step()
+        return out['loss']
+
+    for _ in range(3):
+        step()
+    n = 5
+    ms = timed(step, n) / n
+    loss = float(step())
+    res = {"config": "MaskedDiffWithXvec.forward(batch) + backward + clip/AdamW, %d x %d frames, LoRA on estimator q/k/v and on "
+                     "the 6-block Conformer encoder (%d upstream tensors), eager launches" % (B, T, len(upstream)),
+           "ms_per_step": ms, "value": B * T / (ms / 1e3), "unit": UNIT, "loss": loss,
+           "path_inputs": getattr(m, "path_inputs_backend", "host PyTorch"),
+           "encoder": "host PyTorch (eager, torch.autocast %s); SURVEY 8 f3 is not a kernel of this library" % str(dtype)}
+    return res
+
+
 def run_reference(a):
     """The reference's own algorithm for the path (oracle port) on all host cores, on the GPU arm's config. Each step
     is the FULL workload (32 x 400 frames, fp32, fwd + bwd + clip + AdamW, lora_dropout like the GPU arm) when that
@@ -504,6 +561,15 @@ def run_cvflow(a):
         except Exception as e:
             extra["eager_pytorch_gpu_leg"] = {"error": repr(e)[:200]}
         _trace("eager GPU leg done")
+
+    # ---- the whole flow model: token embedding -> Conformer encoder -> length regulator -> CFM ----
+    if solo and not a.no_extra_legs:
+        try:
+            extra["flow_model_leg"] = flow_model_leg(a, device, dtype, timed)
+        except Exception as e:
+            extra["flow_model_leg"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        _trace("flow model leg done")
 
     # ---- Euler-ODE inference (BASELINE configs[1]) -------------------------------------------------
     inference = None

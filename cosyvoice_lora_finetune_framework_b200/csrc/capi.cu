@@ -291,3 +291,66 @@ extern "C" CVFLOW_API int cvflow_mlp_backward(const void* dy16, const void* w2_t
     return CVFLOW_ERR_ARG;
   RET_LAUNCH(mlp_launch(plan.data(), (cudaStream_t)stream), "cvflow_mlp_backward");
 }
+
+// ---- the inputs of the path (regulator.cu) ---------------------------------------------------------------------
+static int regulator_args(const cvflow_regulator_weights* w, const cvflow_regulator_io* io, RegulatorWeights* W, RegulatorIO* I,
+                          const char* who) {
+  if (!w || !io || !io->src || !io->saved) { set_error("%s: null argument", who); return CVFLOW_ERR_ARG; }
+  if (io->B < 1 || io->T < 1 || io->n_src < 1 || io->n_seg < 1 || io->n_seg > 4) {
+    set_error("%s: B %d, T %d, n_src %d, n_seg %d out of range", who, io->B, io->T, io->n_src, io->n_seg);
+    return CVFLOW_ERR_ARG;
+  }
+  for (int l = 0; l < 5; ++l) {
+    if (!w->wf[l] || !w->wb[l] || !w->bias[l] || (l < 4 && (!w->gamma[l] || !w->beta[l]))) {
+      set_error("%s: weight image %d missing", who, l);
+      return CVFLOW_ERR_ARG;
+    }
+    W->wf[l] = w->wf[l]; W->wb[l] = w->wb[l]; W->bias[l] = w->bias[l];
+    if (l < 4) { W->gamma[l] = w->gamma[l]; W->beta[l] = w->beta[l]; }
+  }
+  int covered = 0;
+  for (int s = 0; s < io->n_seg; ++s) {
+    const int32_t* g = io->seg[s];
+    if (g[0] < 0 || g[1] < 1 || g[0] + g[1] > io->n_src || g[2] != covered || g[3] < 1) {
+      set_error("%s: segment %d {%d,%d,%d,%d} invalid (segments must tile the frames in order)", who, s, g[0], g[1], g[2], g[3]);
+      return CVFLOW_ERR_ARG;
+    }
+    I->seg[s] = RegSeg{g[0], g[1], g[2], g[3]};
+    covered += g[3];
+  }
+  if (covered != io->T) { set_error("%s: segments cover %d frames, T = %d", who, covered, io->T); return CVFLOW_ERR_ARG; }
+  for (int s = io->n_seg; s < 4; ++s) I->seg[s] = RegSeg{0, 0, 0, 0};
+  I->src = io->src; I->B = io->B; I->n_src = io->n_src; I->T = io->T; I->n_seg = io->n_seg;
+  I->lens = io->lens; I->blind = io->blind; I->out = io->out; I->channel_major = io->channel_major; I->saved = io->saved;
+  return CVFLOW_OK;
+}
+extern "C" CVFLOW_API int64_t cvflow_regulator_saved_floats(int32_t B, int32_t T) { return regulator_saved_floats(B, T); }
+extern "C" CVFLOW_API int64_t cvflow_regulator_scratch_floats(int32_t B, int32_t T) { return regulator_scratch_floats(B, T); }
+extern "C" CVFLOW_API int cvflow_regulator_forward(const cvflow_regulator_weights* w, const cvflow_regulator_io* io, void* stream) {
+  RegulatorWeights W; RegulatorIO I;
+  if (int r = regulator_args(w, io, &W, &I, "cvflow_regulator_forward")) return r;
+  if (!io->out) { set_error("cvflow_regulator_forward: null output"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_regulator_forward(W, I, (cudaStream_t)stream), "cvflow_regulator_forward");
+}
+extern "C" CVFLOW_API int cvflow_regulator_backward(const cvflow_regulator_weights* w, const cvflow_regulator_io* io,
+                                                    const float* dout, float* dsrc, float* scratch, void* stream) {
+  RegulatorWeights W; RegulatorIO I;
+  if (int r = regulator_args(w, io, &W, &I, "cvflow_regulator_backward")) return r;
+  if (!dout || !dsrc || !scratch) { set_error("cvflow_regulator_backward: null argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_regulator_backward(W, I, dout, dsrc, scratch, (cudaStream_t)stream), "cvflow_regulator_backward");
+}
+extern "C" CVFLOW_API int cvflow_path_inputs_pack(const float* feat, const float* cross, int32_t cross_T, const int32_t* desc,
+                                                  float mel_mean, float mel_std, float silence, float* x1, float* cond, float* mask,
+                                                  int32_t B, int32_t T, void* stream) {
+  if (!feat || !desc || !x1 || !cond || !mask || B < 1 || T < 1 || (cross && cross_T < 1) || mel_std == 0.f) {
+    set_error("cvflow_path_inputs_pack: null/invalid argument");
+    return CVFLOW_ERR_ARG;
+  }
+  RET_LAUNCH(launch_path_inputs_pack(feat, cross, cross_T, desc, mel_mean, mel_std, silence, x1, cond, mask, B, T,
+                                     (cudaStream_t)stream), "cvflow_path_inputs_pack");
+}
+extern "C" CVFLOW_API int cvflow_spk_affine(const float* e, const float* W, const float* bias, float* out, int32_t B, int32_t K,
+                                            int32_t N, void* stream) {
+  if (!e || !W || !out || B < 1 || K < 1 || K > 8192 || N < 1) { set_error("cvflow_spk_affine: null/invalid argument"); return CVFLOW_ERR_ARG; }
+  RET_LAUNCH(launch_spk_affine(e, W, bias, out, B, K, N, (cudaStream_t)stream), "cvflow_spk_affine");
+}

@@ -169,4 +169,34 @@ int launch_adamw(float* p, const float* g, float* m, float* v, long n, const flo
 int launch_optim_advance(int* state, float* hyper, const float* sumsq, const float* sumsq2, float grad_unscale, float base_lr,
                          int warmup_steps, int total_steps, float min_lr, float beta1, float beta2, cudaStream_t st);
 
+// ---- regulator.cu: the inputs of the path (length regulator, speaker affine, conditioning pack) -----------------
+struct RegSeg { int src0, srcn, dst0, dstn; };   // F.interpolate(src[:, src0:src0+srcn], size=dstn, mode='linear') -> frames [dst0, dst0+dstn)
+struct RegulatorWeights {          // fp32 device pointers; conv images [ci][tap][8][12] (see regulator.cu), wb = dgrad images
+  const float* wf[5];
+  const float* wb[5];
+  const float* bias[5];
+  const float* gamma[4];
+  const float* beta[4];
+};
+struct RegulatorIO {
+  const float* src;                // [B][n_src][80]
+  int B, n_src, T, n_seg;
+  RegSeg seg[4];
+  const int* lens;                 // nullable: frames >= lens[b] are zero
+  const int* blind;                // nullable: frames < blind[b] are zero
+  float* out;                      // [B][T][80] or, channel_major, [B][80][T]
+  int channel_major;
+  float* saved;                    // regulator_saved_floats(B, T): raw layer outputs + GroupNorm partials (kept for the backward)
+};
+long regulator_saved_floats(int B, int T);
+long regulator_scratch_floats(int B, int T);
+int launch_regulator_forward(const RegulatorWeights& w, const RegulatorIO& io, cudaStream_t st);
+// dout in the layout of io.out (masked / blinded here); dsrc [B][n_src][80]; scratch: regulator_scratch_floats(B, T)
+int launch_regulator_backward(const RegulatorWeights& w, const RegulatorIO& io, const float* dout, float* dsrc, float* scratch,
+                              cudaStream_t st);
+// desc[b] = {len, prompt frames, silence-gap frames, flags (bit 0: prompt from cross)}; feat / cross raw log-mel [B][T][80]
+int launch_path_inputs_pack(const float* feat, const float* cross, int cross_T, const int* desc, float mel_mean, float mel_std,
+                            float silence, float* x1, float* cond, float* mask, int B, int T, cudaStream_t st);
+int launch_spk_affine(const float* e, const float* W, const float* bias, float* out, int B, int K, int N, cudaStream_t st);
+
 }  // namespace cvflow

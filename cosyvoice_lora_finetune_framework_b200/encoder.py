@@ -208,11 +208,19 @@ class InterpolateRegulator(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, x, ylens=None):
+        if x.is_cuda:      # csrc/regulator.cu through the C ABI (five fused conv launches); CPU tensors: host logic / tests
+            from . import _path_inputs as PI
+            return PI.regulate(self, x, int(ylens.max()), lens=ylens), ylens
         keep = (~make_pad_mask(ylens)).to(x).unsqueeze(-1)
         x = F.interpolate(x.transpose(1, 2).contiguous(), size=ylens.max(), mode='linear')
         return self.model(x).transpose(1, 2).contiguous() * keep, ylens
 
     def inference(self, x1, x2, mel_len1, mel_len2, input_frame_rate=50):
+        if x2.is_cuda:
+            from . import _path_inputs as PI
+            segs = PI.inference_segments(x1.shape[1], x2.shape[1], mel_len1, mel_len2, input_frame_rate)
+            x = torch.concat([x1, x2], dim=1) if x1.shape[1] != 0 else x2
+            return PI.regulate(self, x, mel_len1 + mel_len2, segs=segs), mel_len1 + mel_len2
         up = lambda t, n: F.interpolate(t.transpose(1, 2).contiguous(), size=n, mode='linear')
         edge = int(20 / input_frame_rate * 22050 / 256)
         if x2.shape[1] > 40:

@@ -391,9 +391,18 @@ class MaskedDiffWithXvec(nn.Module):
     def _speaker(self, embedding):
         return self.spk_embed_affine_layer(F.normalize(embedding, dim=1))
 
+    # Mixed precision of the host-side encoder on a CUDA device: None = fp32 (exact, the parity tests), or torch.bfloat16 /
+    # torch.float16 = torch.autocast around the Conformer encoder, which is what the reference's trainer does to the whole
+    # model (Lightning precision '16-mixed', config.py:76; train_joint.py sets this to the estimator's operand dtype).
+    encoder_autocast = None
+
     def _encode(self, token, token_len, like):
         keep = (~make_pad_mask(token_len)).unsqueeze(-1).to(like)
         emb = self.input_embedding(torch.clamp(token, min=0)) * keep
+        if self.encoder_autocast is not None and token.is_cuda:
+            with torch.autocast('cuda', dtype=self.encoder_autocast):
+                h, _ = self.encoder(emb, token_len)
+                return self.encoder_proj(h).float()
         h, _ = self.encoder(emb, token_len)
         return self.encoder_proj(h)
 
@@ -405,29 +414,11 @@ class MaskedDiffWithXvec(nn.Module):
         return {'loss': loss}
 
     # -- training ----------------------------------------------------------------------------------
-    def forward(self, batch: dict, device: torch.device) -> Dict[str, Any]:
-        """Training forward with the reference's anti-leakage prompt strategies
-        (flow_model.py:248-400). Python's `random` is consumed in the same order as the reference."""
+    def _prompt_plan(self, lens, cross_lens, have_cross):
+        """The anti-leakage decisions of the reference's per-utterance loop (flow_model.py:319-387) from HOST lengths:
+        one (prompt frames, silence-gap frames, prompt from the cross sample, recorded prompt_len, blind the text side)
+        tuple per utterance. Python's `random` is consumed in the reference's order."""
         from .config import ANTI_LEAKAGE_CONFIG as AL
-        dtype = self.input_embedding.weight.dtype
-        token = batch['speech_token'].to(device)
-        token_len = batch['speech_token_len'].to(device)
-        feat = self.normalize_mel(batch['speech_feat'].to(device).to(dtype))
-        feat_len = batch['speech_feat_len'].to(device)
-        embedding = batch['embedding'].to(device).to(dtype)
-        if NO_PROMPT_TRAINING_CONFIG.get('enabled', False):
-            return self._forward_no_prompt(token, token_len, feat, feat_len, embedding, device, dtype)
-
-        cross_mel = cross_len = None
-        if 'cross_sample_mel' in batch:
-            cross_mel = self.normalize_mel(batch['cross_sample_mel'].to(device).to(dtype))
-            cross_len = batch.get('cross_sample_mel_len', None)
-            if cross_len is not None:
-                cross_len = cross_len.to(device)
-        embedding = self._speaker(embedding)
-        h = self._encode(token, token_len, torch.zeros((), dtype=dtype, device=device))
-        h, _ = self.length_regulator(h, feat_len)
-
         silence_on = AL.get('silence_padding_enabled', False)
         dynamic_on = AL.get('dynamic_prompt_enabled', True)
         dropout_on = AL.get('prompt_dropout_enabled', True)
@@ -436,61 +427,104 @@ class MaskedDiffWithXvec(nn.Module):
         lo_ratio, hi_ratio = AL.get('prompt_min_ratio', 0.10), AL.get('prompt_max_ratio', 0.30)
         p_drop, p_blind = AL.get('prompt_dropout_prob', 0.10), AL.get('text_blinding_prob', 0.7)
         sil_lo, sil_hi = AL.get('silence_min_tokens', 5), AL.get('silence_max_tokens', 10)
-        silence_value = (AL.get('silence_mel_value', -11.5) - self.mel_mean) / self.mel_std
-
-        conds = torch.zeros(feat.shape, device=device, dtype=dtype)
-        prompt_lens = []
-        for i, n in enumerate(feat_len):
-            n = int(n.item())
+        plan = []
+        for i, n in enumerate(lens):
             if dropout_on and random.random() < p_drop:                 # strategy 3: prompt dropout
-                prompt_lens.append(0)
+                plan.append((0, 0, False, 0, False))
                 continue
             if dynamic_on:                                              # strategy 2: dynamic prompt length
                 lo = max(1, int(lo_ratio * n))
                 p = random.randint(lo, max(lo + 1, int(hi_ratio * n)))
             else:
                 p = max(1, int(0.3 * n))
-            source = feat                                               # strategy 5: cross-sample prompt
-            if cross_on and cross_mel is not None and cross_len is not None and cross_len[i].item() > 0:
-                source = cross_mel
-                p = min(p, int(cross_len[i].item()))
-            recorded = p
+            use_cross = bool(cross_on and have_cross and cross_lens is not None and cross_lens[i] > 0)
+            if use_cross:                                               # strategy 5: cross-sample prompt
+                p = min(p, int(cross_lens[i]))
+            gap = 0
             if silence_on:                                              # strategy 1: silence gap
-                gap = int(random.randint(sil_lo, sil_hi) * 22050 / 256 / self.input_frame_rate)
-                gap = max(3, min(gap, 20))
-                conds[i, :p] = source[i, :p]
-                if p + gap < n:
-                    conds[i, p:p + gap] = silence_value
-                    recorded = p + gap
-            else:
-                conds[i, :p] = source[i, :p]
-            prompt_lens.append(recorded)
-            if blind_on and random.random() < p_blind:                  # strategy 6: text-side blinding
-                h[i, :p, :] = 0.0
-        return self._loss(feat, feat_len, h, embedding, conds, prompt_lens)
+                g = int(random.randint(sil_lo, sil_hi) * 22050 / 256 / self.input_frame_rate)
+                g = max(3, min(g, 20))
+                if p + g < n:
+                    gap = g
+            blind = bool(blind_on and random.random() < p_blind)        # strategy 6: text-side blinding
+            plan.append((p, gap, use_cross, p + gap, blind))
+        return plan
 
-    def _forward_no_prompt(self, token, token_len, feat, feat_len, embedding, device, dtype) -> Dict[str, Any]:
-        """No-prompt training (flow_model.py:402-473): zero conditioning ('full') or a small prompt with
-        probability 1 - no_prompt_ratio ('mixed')."""
+    def _no_prompt_plan(self, lens):
         mode = NO_PROMPT_TRAINING_CONFIG.get('mode', 'full')
         ratio = NO_PROMPT_TRAINING_CONFIG.get('no_prompt_ratio', 0.8)
+        plan = []
+        for n in lens:
+            if mode == 'full' or random.random() < ratio:
+                plan.append((0, 0, False, 0, False))
+            else:
+                p = random.randint(1, max(2, int(0.1 * n)))
+                plan.append((p, 0, False, p, False))
+        return plan
+
+    @staticmethod
+    def _host_ints(t):
+        """Lengths as Python ints. The collate function leaves them on the host (no device synchronisation); a device
+        tensor costs one."""
+        return [int(v) for v in (t.tolist() if torch.is_tensor(t) else t)]
+
+    def forward(self, batch: dict, device: torch.device) -> Dict[str, Any]:
+        """Training forward with the reference's anti-leakage prompt strategies
+        (flow_model.py:248-400). Python's `random` is consumed in the same order as the reference. On a CUDA device
+        everything in front of compute_loss except the Conformer encoder runs in csrc/regulator.cu (speaker affine,
+        length regulator with its autograd, mel normalisation + conditioning + mask in one launch) and the loop makes no
+        device synchronisation; on the CPU (host-logic tests) the same plan is applied with torch ops."""
+        from .config import ANTI_LEAKAGE_CONFIG as AL
+        device = torch.device(device)
+        dtype = self.input_embedding.weight.dtype
+        lens = self._host_ints(batch['speech_feat_len'])
+        no_prompt = NO_PROMPT_TRAINING_CONFIG.get('enabled', False)
+        cross_raw, cross_lens = None, None
+        if not no_prompt and 'cross_sample_mel' in batch:
+            cross_raw = batch['cross_sample_mel'].to(device).to(dtype)
+            if batch.get('cross_sample_mel_len', None) is not None:
+                cross_lens = self._host_ints(batch['cross_sample_mel_len'])
+        token = batch['speech_token'].to(device)
+        token_len = batch['speech_token_len'].to(device)
+        feat_raw = batch['speech_feat'].to(device).to(dtype)
+        feat_len = batch['speech_feat_len'].to(device)
+        embedding = batch['embedding'].to(device).to(dtype)
+        silence_value = (AL.get('silence_mel_value', -11.5) - self.mel_mean) / self.mel_std
+
+        if device.type == 'cuda':
+            from . import _path_inputs as PI
+            if feat_raw.shape[1] != max(lens):
+                raise ValueError("speech_feat must be padded to max(speech_feat_len) (the length regulator produces "
+                                 "max(speech_feat_len) frames, modules.py:822)")
+            spks = PI.spk_affine(self.spk_embed_affine_layer, embedding)
+            h = self._encode(token, token_len, torch.zeros((), dtype=dtype, device=device))
+            plan = self._no_prompt_plan(lens) if no_prompt else self._prompt_plan(lens, cross_lens, cross_raw is not None)
+            desc = torch.tensor([[n, p, gap, 1 if xs else 0] for n, (p, gap, xs, _, _) in zip(lens, plan)], dtype=torch.int32)
+            blind = torch.tensor([p if b else 0 for (p, _, _, _, b) in plan], dtype=torch.int32)
+            both = torch.cat([desc.reshape(-1), blind]).pin_memory().to(device, non_blocking=True)
+            B = len(lens)
+            mu = PI.regulate(self.length_regulator, h, feat_raw.shape[1], lens=both[:4 * B:4], blind=both[4 * B:],
+                             channel_major=True)
+            x1, cond, mask = PI.pack_inputs(feat_raw, cross_raw, both[:4 * B], self.mel_mean, self.mel_std, silence_value)
+            self.path_inputs_backend = "libcvflow (regulator.cu)"
+            loss, _ = self.decoder.compute_loss(x1, mask, mu, spks, cond=cond, prompt_lens=[r for (_, _, _, r, _) in plan])
+            return {'loss': loss}
+
+        feat = self.normalize_mel(feat_raw)
+        cross_mel = self.normalize_mel(cross_raw) if cross_raw is not None else None
         embedding = self._speaker(embedding)
         h = self._encode(token, token_len, torch.zeros((), dtype=dtype, device=device))
         h, _ = self.length_regulator(h, feat_len)
+        plan = self._no_prompt_plan(lens) if no_prompt else self._prompt_plan(lens, cross_lens, cross_mel is not None)
         conds = torch.zeros(feat.shape, device=device, dtype=dtype)
-        if mode == 'full':
-            prompt_lens = [0] * feat.shape[0]
-        else:
-            prompt_lens = []
-            for i, n in enumerate(feat_len):
-                n = int(n.item())
-                if random.random() < ratio:
-                    prompt_lens.append(0)
-                else:
-                    p = random.randint(1, max(2, int(0.1 * n)))
-                    conds[i, :p] = feat[i, :p]
-                    prompt_lens.append(p)
-        return self._loss(feat, feat_len, h, embedding, conds, prompt_lens)
+        for i, (p, gap, use_cross, _, blind) in enumerate(plan):
+            if p > 0:
+                conds[i, :p] = (cross_mel if use_cross else feat)[i, :p]
+            if gap > 0:
+                conds[i, p:p + gap] = silence_value
+            if blind:
+                h[i, :p, :] = 0.0
+        return self._loss(feat, feat_len, h, embedding, conds, [r for (_, _, _, r, _) in plan])
 
     # -- inference ---------------------------------------------------------------------------------
     @torch.inference_mode()

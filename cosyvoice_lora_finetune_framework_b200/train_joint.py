@@ -97,6 +97,7 @@ def main(argv=None):
     flow_lora = dict(cfg.get('flow_lora', {}))
     model = build_joint_model(PRETRAINED_MODEL_DIR, str(device), 'flow_only', None, flow_lora)
     model.flow.decoder.estimator.cvflow_dtype = torch.float16 if args.dtype == 'fp16' else torch.bfloat16
+    model.flow.encoder_autocast = model.flow.decoder.estimator.cvflow_dtype      # '16-mixed' (config.py:76) for the host-side encoder
     upstream = [p for n, p in model.flow.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]
     resume, start_epoch = None, 0
     if args.resume:      # Lightning's ckpt_path semantics: parameters, optimiser moments, schedule position, epoch

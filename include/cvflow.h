@@ -294,6 +294,53 @@ CVFLOW_API int cvflow_optim_advance(int32_t* state, float* hyper, const float* s
                                     float grad_unscale, float base_lr, int32_t warmup_steps, int32_t total_steps,
                                     float min_lr, float beta1, float beta2, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The inputs of the path: what MaskedDiffWithXvec.forward prepares for compute_loss.
+ * Stateless entry points (no estimator handle); fp32; all pointers device pointers unless stated.
+ *
+ * Length regulator = InterpolateRegulator.forward / .inference (modules.py:800-837):
+ *   F.interpolate(mode='linear') of the projected encoder output, 4 x [Conv1d(80,80,3,pad 1) -> GroupNorm(1,80) -> Mish],
+ *   Conv1d(80,80,1), * pad mask; the interpolation indices are bit-identical to at::upsample_linear1d's.
+ * The weights are the module's frozen parameters in a kernel-friendly image:
+ *   wf[l] forward image  [ci][tap][8][12]: wf[((ci*taps + k)*8 + co/10)*12 + co%10] = weight[co][ci][k]   (taps 3,3,3,3,1)
+ *   wb[l] dgrad image, same layout with the roles of ci / co swapped and the taps reversed: weight[ci][co][taps-1-k]
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cvflow_regulator_weights {
+  const float* wf[5];
+  const float* wb[5];
+  const float* bias[5];
+  const float* gamma[4];
+  const float* beta[4];
+} cvflow_regulator_weights;
+typedef struct cvflow_regulator_io {
+  const float* src;      /* encoder_proj output [B][n_src][80] */
+  int32_t B, n_src, T, n_seg;
+  int32_t seg[4][4];     /* {src0, src_n, dst0, dst_n}: F.interpolate(src[:, src0:src0+src_n], size=dst_n) -> frames [dst0, dst0+dst_n);
+                          * training: one segment {0, n_src, 0, T} (modules.py:822); inference: prompt | head | mid | tail (:827-836) */
+  const int32_t* lens;   /* optional [B]: frames >= lens[b] are zero (modules.py:821,824) */
+  const int32_t* blind;  /* optional [B]: frames < blind[b] are zero (text-side blinding, flow_model.py:372-373) */
+  float* out;            /* [B][T][80] like the module, or with channel_major = 1 [B][80][T] as compute_loss takes mu */
+  int32_t channel_major;
+  float* saved;          /* cvflow_regulator_saved_floats(B, T) floats; the backward reads them */
+} cvflow_regulator_io;
+CVFLOW_API int64_t cvflow_regulator_saved_floats(int32_t B, int32_t T);
+CVFLOW_API int64_t cvflow_regulator_scratch_floats(int32_t B, int32_t T);
+CVFLOW_API int cvflow_regulator_forward(const cvflow_regulator_weights* w, const cvflow_regulator_io* io, void* stream);
+/* autograd of the above with respect to src (the weights are frozen under LoRA fine-tuning): dout in the layout of io->out,
+ * dsrc [B][n_src][80]; io as passed to the forward (io->out unused); scratch: cvflow_regulator_scratch_floats(B, T) */
+CVFLOW_API int cvflow_regulator_backward(const cvflow_regulator_weights* w, const cvflow_regulator_io* io, const float* dout,
+                                         float* dsrc, float* scratch, void* stream);
+/* x1 = ((feat - mel_mean) / mel_std)^T, cond (prompt frames from feat or cross, silence gap, zeros), mask, each [B][80|1][T],
+ * from per-utterance descriptors desc[b] = {len, prompt frames, silence-gap frames, flags (bit 0: prompt from cross)}
+ * (flow_model.py:266-269, 319-387: mel normalisation, the conds loop, make_pad_mask, the transposes). feat / cross are
+ * the raw log-mel [B][T][80] / [B][cross_T][80] (cross nullable). */
+CVFLOW_API int cvflow_path_inputs_pack(const float* feat, const float* cross, int32_t cross_T, const int32_t* desc,
+                                       float mel_mean, float mel_std, float silence_normalised, float* x1, float* cond,
+                                       float* mask, int32_t B, int32_t T, void* stream);
+/* spks = Linear(F.normalize(embedding, dim=1))   (flow_model.py:297-298): e [B][K], W [N][K], out [B][N] */
+CVFLOW_API int cvflow_spk_affine(const float* e, const float* W, const float* bias, float* out, int32_t B, int32_t K,
+                                 int32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

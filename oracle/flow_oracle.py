@@ -275,6 +275,89 @@ def cfm_forward(P, mu: Tensor, mask: Tensor, n_timesteps: int, z: Tensor, spks: 
 
 
 # ----------------------------------------------------------------------------------------------
+# the inputs of the path: length regulator, speaker affine, conditioning    modules.py:800-837, flow_model.py:266-387
+# ----------------------------------------------------------------------------------------------
+def interp_linear_taps(n_in: int, n_out: int):
+    """Index arithmetic of F.interpolate(mode='linear', align_corners=False) (ATen upsample_linear1d:
+    area_pixel_compute_source_index, fp32 throughout): for each of the n_out frames the two source indices and their
+    weights, as numpy arrays (i0, i1, w0, w1). Pinned bit-for-bit against torch itself in tests/test_oracle.py."""
+    import numpy as np
+    f32 = np.float32
+    scale = f32(n_in) / f32(n_out)
+    j = np.arange(n_out, dtype=np.float32)
+    # ATen evaluates scale * (j + 0.5) - 0.5 as ONE fused multiply-add (CPU and CUDA builds alike); float64 holds the
+    # product of two float32 and the subtraction exactly, so rounding it once to float32 is that FMA
+    s = (float(scale) * (j + f32(0.5)).astype(np.float64) - 0.5).astype(np.float32)
+    s = np.where(s < 0, f32(0), s).astype(np.float32)
+    i0 = np.minimum(s.astype(np.int64), n_in - 1)
+    i1 = i0 + (i0 < n_in - 1)
+    w1 = np.clip(s - i0.astype(np.float32), f32(0), f32(1)).astype(np.float32)
+    w0 = (f32(1) - w1).astype(np.float32)
+    return i0, i1, w0, w1
+
+
+def interp_linear(x: Tensor, n_out: int) -> Tensor:
+    """x [B][n_in][C] -> [B][n_out][C] with the taps above (== F.interpolate on the transposed tensor)."""
+    i0, i1, w0, w1 = interp_linear_taps(x.shape[1], n_out)
+    i0, i1 = torch.from_numpy(i0), torch.from_numpy(i1)
+    w0, w1 = torch.from_numpy(w0).to(x)[None, :, None], torch.from_numpy(w1).to(x)[None, :, None]
+    return w0 * x[:, i0] + w1 * x[:, i1]
+
+
+def regulator_stack(P, prefix: str, x: Tensor) -> Tensor:
+    """InterpolateRegulator.model (modules.py:806-818): x [B][T][80] -> [B][T][80]."""
+    h = x.transpose(1, 2)
+    n = 0
+    while f"{prefix}model.{3 * n}.weight" in P and P[f"{prefix}model.{3 * n}.weight"].shape[-1] == 3:
+        h = F.conv1d(h, P[f"{prefix}model.{3 * n}.weight"], P[f"{prefix}model.{3 * n}.bias"], padding=1)
+        h = F.group_norm(h, 1, P[f"{prefix}model.{3 * n + 1}.weight"], P[f"{prefix}model.{3 * n + 1}.bias"], eps=1e-5)
+        h = F.mish(h)
+        n += 1
+    h = F.conv1d(h, P[f"{prefix}model.{3 * n}.weight"], P[f"{prefix}model.{3 * n}.bias"])
+    return h.transpose(1, 2)
+
+
+def regulator_forward(P, prefix: str, x: Tensor, ylens: Tensor) -> Tensor:
+    """InterpolateRegulator.forward (modules.py:820-824)."""
+    keep = (~make_pad_mask(ylens)).to(x).unsqueeze(-1)
+    return regulator_stack(P, prefix, interp_linear(x, int(ylens.max()))) * keep
+
+
+def regulator_inference(P, prefix: str, x1: Tensor, x2: Tensor, mel_len1: int, mel_len2: int, input_frame_rate: int = 50) -> Tensor:
+    """InterpolateRegulator.inference (modules.py:826-837): the target is stretched in three pieces."""
+    if x2.shape[1] > 40:
+        edge = int(20 / input_frame_rate * 22050 / 256)
+        x2 = torch.cat([interp_linear(x2[:, :20], edge), interp_linear(x2[:, 20:-20], mel_len2 - edge * 2),
+                        interp_linear(x2[:, -20:], edge)], dim=1)
+    else:
+        x2 = interp_linear(x2, mel_len2)
+    x = torch.cat([interp_linear(x1, mel_len1), x2], dim=1) if x1.shape[1] != 0 else x2
+    return regulator_stack(P, prefix, x)
+
+
+def speaker_affine(W: Tensor, b: Tensor, embedding: Tensor) -> Tensor:
+    """flow_model.py:297-298."""
+    return F.linear(F.normalize(embedding, dim=1), W, b)
+
+
+def path_inputs_pack(feat: Tensor, cross: Optional[Tensor], desc, mel_mean: float, mel_std: float, silence: float):
+    """Mel normalisation, conditioning and mask of flow_model.py:266-269, 319-387 from per-utterance descriptors
+    desc[b] = (len, prompt frames, silence-gap frames, prompt from cross): x1, cond [B][80][T], mask [B][1][T]."""
+    B, T, _ = feat.shape
+    f = (feat - mel_mean) / mel_std
+    c = (cross - mel_mean) / mel_std if cross is not None else None
+    cond = torch.zeros_like(f)
+    mask = torch.zeros(B, 1, T)
+    for i, (n, p, gap, use_cross) in enumerate(desc):
+        if p > 0:
+            cond[i, :p] = (c if use_cross else f)[i, :p]
+        if gap > 0:
+            cond[i, p:p + gap] = silence
+        mask[i, 0, :n] = 1.0
+    return f.transpose(1, 2).contiguous(), cond.transpose(1, 2).contiguous(), mask
+
+
+# ----------------------------------------------------------------------------------------------
 # seeded synthetic weights shared by the golden generator, the tests and the bench
 # ----------------------------------------------------------------------------------------------
 def synth_tensor(name: str, shape, seed: int) -> Tensor:
@@ -304,3 +387,12 @@ def synth_tensor(name: str, shape, seed: int) -> Tensor:
 
 def synth_state_dict(spec: Dict[str, tuple], seed: int = 1234) -> Dict[str, Tensor]:
     return {k: synth_tensor(k, shp, seed) for k, shp in spec.items()}
+
+
+def synth_regulator_state_dict(spec: Dict[str, tuple], seed: int = 1234) -> Dict[str, Tensor]:
+    """synth_state_dict for an InterpolateRegulator: the GroupNorm scales are moved to 1 + 0.1 w so the stack stays alive."""
+    sd = synth_state_dict(spec, seed)
+    for k in sd:
+        if k.endswith("weight") and sd[k].dim() == 1:
+            sd[k] = 1.0 + 0.1 * sd[k]
+    return sd

@@ -67,6 +67,12 @@ def run(B, L, ragged, ldq=1600):
                                              o[j].data_ptr(), lse[j].data_ptr(), dout[j].data_ptr(), delta.data_ptr(),
                                              dqkv.data_ptr(), st))
 
+    if os.environ.get("ATTN_NCU"):      # profiling mode: one forward + one backward launch set per shape, in the order printed
+        fwd(0); bwd(0)
+        torch.cuda.synchronize()
+        print("ncu shape: B=%d L=%d %s (8 heads x 64, bf16): attn_kinfo, attn_fwd, attn_kinfo, attn_bwd_dq, attn_bwd_dkv" %
+              (B, L, "ragged" if ragged else "full"))
+        return
     for j in range(ncopy):
         fwd(j)
     tf, tb = timeit(fwd), timeit(bwd)
@@ -74,6 +80,11 @@ def run(B, L, ragged, ldq=1600):
     print("B=%3d L=%5d %-6s fwd %7.1f us (%5.0f TF/s valid)  bwd %7.1f us (%5.0f TF/s valid)  [includes the kmax launch]" %
           (B, L, "ragged" if ragged else "full", tf, 4 * valid / tf / 1e6, tb, 10 * valid / tb / 1e6))
 
+
+if __name__ == "__main__" and os.environ.get("ATTN_NCU"):
+    for B, L in ((32, 200), (32, 400), (16, 1500)):
+        run(B, L, True)
+    sys.exit(0)
 
 if __name__ == "__main__":
     for ragged in (False, True):

@@ -10,6 +10,9 @@
                                                      # P=200, 10 steps), train_tiny_padprompt (boundary window running into the
                                                      # padding), dropout_c1 (300M, lora_dropout = 0.05 with preset masks)
 
+    python tests/golden/make_golden.py regulator     # regulator_tiny / regulator_c3: InterpolateRegulator forward, inference and
+                                                     # input gradient, real reference modules.py:800-837
+
 The GPU box has no /root/reference; tests read the committed .pt files. Weights are not stored:
 they are a pure function of (parameter name, shape, seed) - oracle.flow_oracle.synth_tensor - and
 each fixture records a checksum so a drift in that generator is detected.
@@ -394,6 +397,39 @@ def euler_case(name, n_blocks, n_mid, T, prompt, n_steps, seed):
     print(name, "mel sum", float(mel.sum()), "absmax", float(mel.abs().max()), tuple(cache.shape))
 
 
+def regulator_case(name, B, n_src, ylens, seed, full):
+    """The real InterpolateRegulator (modules.py:800-837) on seeded weights: forward, d(sum(out * R))/dx, and the two
+    inference layouts. `full` keeps whole tensors, otherwise checksums + a few rows (the 32 x 400 benchmarked shape)."""
+    reg = ref_modules.InterpolateRegulator(channels=80, sampling_ratios=(1, 1, 1, 1), out_channels=80, groups=1)
+    spec = {k: tuple(v.shape) for k, v in reg.state_dict().items()}
+    sd = O.synth_regulator_state_dict(spec, WSEED)
+    reg.load_state_dict(sd, strict=True)
+    reg.eval()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, n_src, 80, generator=g).requires_grad_(True)
+    yl = torch.tensor(ylens)
+    R = torch.randn(B, int(yl.max()), 80, generator=g)
+    out, _ = reg(x, yl)
+    (out * R).sum().backward()
+    fx = dict(spec=spec, wseed=WSEED, seed=seed, B=B, n_src=n_src, ylens=list(ylens), wsum=wsum(sd),
+              out_sum=csum(out.detach()), dx_sum=csum(x.grad))
+    if full:
+        fx.update(x=x.detach().clone(), R=R, out=out.detach().clone(), dx=x.grad.clone())
+        x1 = torch.randn(1, 30, 80, generator=g)
+        x2 = torch.randn(1, 75, 80, generator=g)
+        m2 = int(75 / 50 * 22050 / 256)
+        with torch.no_grad():
+            o1, n1 = reg.inference(x1, x2, 52, m2, 50)
+            x3 = torch.randn(1, 33, 80, generator=g)
+            o2, n2 = reg.inference(x3[:, :0], x3, 0, 56, 50)
+        fx.update(inf_x1=x1, inf_x2=x2, inf_len=(52, m2), inf_out=o1, inf_total=int(n1), inf_short_x=x3, inf_short_len=56,
+                  inf_short_out=o2)
+    else:
+        fx.update(out_rows=out.detach()[:, ::97].clone(), dx_rows=x.grad[:, ::53].clone())
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "out", tuple(out.shape), "|out|", float(out.abs().mean()), "|dx|", float(x.grad.abs().mean()))
+
+
 def structure_checks():
     """Our module tree == the reference's (names, shapes, and same-seed random init)."""
     for nb, nm in [(1, 1), (4, 12)]:
@@ -431,6 +467,11 @@ if __name__ == "__main__":
             euler_bench_case("euler_c2", 700, 200, 10, 5)
         if not only or only == "train":
             train_bench_case("train_c3", 32, 400, 99, 7, fml)
+        sys.exit(0)
+    if sys.argv[1:] == ["regulator"]:
+        regulator_case("regulator_tiny", 3, 47, [81, 60, 33], 17, True)
+        lens = bench_batch(32, 400, 99)[-1]
+        regulator_case("regulator_c3", 32, int(int(lens.max()) * 256 * 50 / 22050), [int(v) for v in lens], 18, False)
         sys.exit(0)
     if sys.argv[1:] == ["flowmodel"]:
         flow_model_case("flowmodel_tiny", 21, 3, 5)

@@ -112,3 +112,31 @@ def grad_errors(grads, ref):
     den = sum(ref[k].double().pow(2).sum() for k in ref)
     per = sorted(float((grads[k].cpu() - ref[k]).double().norm() / (ref[k].double().norm() + 1e-30)) for k in ref)
     return dict(bucket_rel_l2=float((num / den).sqrt()), tensor_rel_l2_median=per[len(per) // 2], tensor_rel_l2_max=per[-1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# length regulator fixtures (regulator_tiny / regulator_c3): inputs regenerated from the seed, weights from the name hash
+# ------------------------------------------------------------------------------------------------------
+def regulator_inputs(fx):
+    """(state dict, x, ylens, R) of a `regulator` fixture, regenerated exactly as tests/golden/make_golden.py drew them."""
+    sd = O.synth_regulator_state_dict(fx["spec"], fx["wseed"])
+    assert abs(wsum(sd) - fx["wsum"]) <= 1e-6 * abs(fx["wsum"])
+    g = torch.Generator().manual_seed(fx["seed"])
+    x = torch.randn(fx["B"], fx["n_src"], 80, generator=g)
+    yl = torch.tensor(fx["ylens"])
+    R = torch.randn(fx["B"], int(yl.max()), 80, generator=g)
+    return sd, x, yl, R
+
+
+def build_regulator(sd):
+    from cosyvoice_lora_finetune_framework_b200.encoder import InterpolateRegulator
+    reg = InterpolateRegulator(channels=80, sampling_ratios=(1, 1, 1, 1), out_channels=80, groups=1)
+    reg.load_state_dict(sd, strict=True)
+    for p in reg.parameters():
+        p.requires_grad_(False)
+    return reg
+
+
+def close_sums(t, ref, tol):
+    s = csum(t)
+    return abs(s[0] - ref[0]) <= tol * (1.0 + abs(ref[1])) and abs(s[1] - ref[1]) <= tol * (1.0 + abs(ref[1]))

@@ -161,3 +161,66 @@ def test_lora_dropout_300m_matches_reference():
         assert torch.allclose(P[k].grad, g, atol=1e-6 + 1e-3 * float(g.abs().max()), rtol=1e-3), k
     worst = max(abs(float(P[k].grad.norm()) - n) / (n + 1e-12) for k, n in dg["grad_norms"].items())
     assert worst <= 2e-3, worst
+
+
+# ------------------------------------------------------------------------------------------------------
+# the inputs of the path: length regulator, speaker affine, conditioning pack
+# ------------------------------------------------------------------------------------------------------
+def test_interp_taps_bit_identical_to_torch():
+    """north_star: bit-exact length-regulation indices. The oracle's taps reproduce F.interpolate(mode='linear')'s
+    index arithmetic (what the reference calls, modules.py:822-836): the full weight matrix is read off torch with an
+    identity probe and must be equal bit for bit, for up- and down-sampling, edge lengths and the benchmarked ratios."""
+    import numpy as np
+    import torch.nn.functional as F
+    pairs = [(n_in, n_out) for n_in in (1, 2, 3, 5, 20, 33, 35, 47, 75, 100, 232, 233, 406, 870)
+             for n_out in (1, 2, 7, 34, 56, 61, 81, 129, 137, 200, 399, 400, 401, 700, 1500)]
+    for n_in, n_out in pairs:
+        i0, i1, w0, w1 = O.interp_linear_taps(n_in, n_out)
+        want = F.interpolate(torch.eye(n_in)[None], size=n_out, mode='linear')[0].numpy()
+        got = np.zeros((n_in, n_out), dtype=np.float32)
+        for j in range(n_out):
+            got[i0[j], j] += w0[j]
+            got[i1[j], j] += w1[j]
+        assert np.array_equal(got, want), (n_in, n_out)
+
+
+def test_regulator_oracle_matches_reference():
+    from tests.helpers import close_sums, regulator_inputs
+    fx = load_golden("regulator_tiny")
+    sd, x, yl, R = regulator_inputs(fx)
+    x.requires_grad_(True)
+    out = O.regulator_forward(sd, "", x, yl)
+    (out * R).sum().backward()
+    assert torch.allclose(out, fx["out"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(x.grad, fx["dx"], atol=1e-5, rtol=1e-4)
+    assert float(out[1, 60:].abs().max()) == 0.0 and float(out[2, 33:].abs().max()) == 0.0      # padded frames are exact zeros
+    with torch.no_grad():
+        o1 = O.regulator_inference(sd, "", fx["inf_x1"], fx["inf_x2"], *fx["inf_len"])
+        o2 = O.regulator_inference(sd, "", fx["inf_short_x"][:, :0], fx["inf_short_x"], 0, fx["inf_short_len"])
+    assert o1.shape[1] == fx["inf_total"] and torch.allclose(o1, fx["inf_out"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(o2, fx["inf_short_out"], atol=1e-5, rtol=1e-5)
+    # the benchmarked shape (32 utterances, 232 tokens -> 400 ragged frames): checksums and sampled rows of the reference
+    fc = load_golden("regulator_c3")
+    sd, x, yl, R = regulator_inputs(fc)
+    x.requires_grad_(True)
+    out = O.regulator_forward(sd, "", x, yl)
+    (out * R).sum().backward()
+    assert close_sums(out.detach(), fc["out_sum"], 1e-5) and close_sums(x.grad, fc["dx_sum"], 1e-5)
+    assert torch.allclose(out.detach()[:, ::97], fc["out_rows"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(x.grad[:, ::53], fc["dx_rows"], atol=1e-5, rtol=1e-4)
+
+
+def test_path_inputs_oracle_vs_reference_flow_model():
+    """Speaker affine and the conditioning pack against what the REAL MaskedDiffWithXvec.forward handed to compute_loss
+    (fixture flowmodel_tiny: x1, cond, spks seen by the reference)."""
+    from cosyvoice_lora_finetune_framework_b200 import flow_model, utils
+    fx = load_golden("flowmodel_tiny")
+    utils.set_all_random_seed(fx["init_seed"])
+    m = flow_model.build_flow_model(None, 'cpu', **fx["arch"])
+    b = fx["batch"]
+    spks = O.speaker_affine(m.spk_embed_affine_layer.weight, m.spk_embed_affine_layer.bias, b["embedding"])
+    assert torch.allclose(spks, fx["spks"], atol=1e-6, rtol=1e-5)
+    desc = [(int(n), int(p), 0, int(c) > 0) for n, p, c in zip(b["speech_feat_len"], fx["prompt_lens"], b["cross_sample_mel_len"])]
+    assert any(d[3] for d in desc)                      # the fixture exercises the cross-sample prompt (strategy 5)
+    x1, cond, mask = O.path_inputs_pack(b["speech_feat"], b["cross_sample_mel"], desc, m.mel_mean, m.mel_std, 0.0)
+    assert torch.allclose(x1, fx["x1"], atol=1e-6, rtol=1e-6) and torch.allclose(cond, fx["cond"], atol=1e-6, rtol=1e-6)
