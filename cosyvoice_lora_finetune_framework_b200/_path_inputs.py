@@ -75,7 +75,7 @@ class RegulatorImages:
 
     def refresh(self):
         ps = self._params()
-        if any(p.requires_grad for p in ps):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in ps):      # inference (no_grad / inference_mode) is fine
             raise RuntimeError("the CUDA length regulator computes input gradients only: its parameters must be frozen "
                                "(requires_grad=False), as they are under the reference's LoRA fine-tuning")
         key = tuple((p.data_ptr(), p._version) for p in ps)
@@ -187,7 +187,7 @@ def inference_segments(n_prompt, n_target, mel_len1, mel_len2, input_frame_rate=
 
 def spk_affine(layer, embedding):
     """Linear(F.normalize(embedding, dim=1)) with the layer's frozen parameters (flow_model.py:297-298)."""
-    if layer.weight.requires_grad or embedding.requires_grad:
+    if torch.is_grad_enabled() and (layer.weight.requires_grad or embedding.requires_grad):
         raise RuntimeError("the CUDA speaker affine kernel is forward-only: its parameters / input must not require grad")
     e = embedding.contiguous().float()
     w = layer.weight.detach().float().contiguous()

@@ -319,6 +319,7 @@ int Estimator::run_gemm(GemmArgs& a) {
   if (dry_) { ++gemm_idx_; return 0; }
   if (missing_ || oom_) return -1;
   Plan& pl = *plan_;
+  a.w_static = true;      // every W of the estimator is a weight image: written by lora_merge, several launches before the first GEMM
   if ((size_t)gemm_idx_ >= pl.gemms.size()) {
     a.bf16 = cfg.bf16;
     GemmParams p;

@@ -112,6 +112,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // Weights do not depend on the predecessor: the W half of the first tile's stages is requested before the
+  // grid-dependency wait, so only the A loads (half the bytes of the first ring fill) start after it.
+  int w_pre = 0;
+  if (CL == 1 && p.w_prefetch && warp == 0 && lane == 0 && cluster_id < total_super) {
+    const int nt0 = cluster_id % ntn_g;
+    w_pre = p.nkb_total < Cfg::kStages ? p.nkb_total : Cfg::kStages;
+    for (int kb = 0; kb < w_pre; ++kb) {
+      mbar_expect_tx(full_bar(kb), Cfg::kStageBytes);
+      tma_load_2d(smem_base + kb * Cfg::kStageBytes + Cfg::kABytes, &p.tmW, full_bar(kb), kb * BK, nt0 * BN);
+    }
+  }
   pdl_wait();     // everything above overlapped the previous kernel's tail; global memory from here on
   if (threadIdx.x == 0) stamp(1);
 
@@ -129,15 +140,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* tm = &p.tmA[sg.a_map];
           for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            const bool w_done = CL == 1 && st == cluster_id && kb_global < w_pre;   // requested before the wait
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            if (!w_done) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            }
             if (CL > 1)
               tma_load_3d_mc(sa + rank * kSliceRows * 128, tm, full_bar(stage), sg.a_col0 + kb * BK,
                              i0 + sg.row_shift + rank * kSliceRows, b, kMask);
             else
               tma_load_3d(sa, tm, full_bar(stage), sg.a_col0 + kb * BK, i0 + sg.row_shift, b);
-            tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
+            if (!w_done) tma_load_2d(sa + Cfg::kABytes, &p.tmW, full_bar(stage), kb_global * BK, n0);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -627,6 +641,9 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->mul_src = a.mul_src; p->ld_aux = a.ld_aux; p->rowmask = a.rowmask; p->resid = a.resid;
   p->ldr = a.ldr;
   p->gn_part = a.gn_part;
+  static int wpre_env = -1;
+  if (wpre_env < 0) { const char* e = getenv("CVFLOW_GEMM_WPRE"); wpre_env = e ? atoi(e) : 1; }
+  p->w_prefetch = (a.w_static && wpre_env) ? 1 : 0;
   p->ln_gamma = a.ln_gamma; p->ln_beta = a.ln_beta;
   if (a.ln_gamma) {
     if (!a.ln_beta || !a.aux_out || a.N != 256 || a.n_valid != 256 || a.transposed_out || !a.out_f32 || a.act != ACT_NONE ||

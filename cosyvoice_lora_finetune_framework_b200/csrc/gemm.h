@@ -34,6 +34,7 @@ struct GemmArgs {
   int nbatch = 1;
   // B operand: weights [N][Ktot] row-major, 16-bit, K contiguous (nn.Linear layout).
   const void* W = nullptr;
+  bool w_static = false;   // W is not written by the kernel launched just before this one: its first tiles may be fetched before the grid-dependency wait
   int N = 0;       // rows of W (padded to a multiple of the N tile by the caller or zero-filled by TMA)
   int Ktot = 0;
   GemmSeg seg[8];
@@ -79,6 +80,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tmOut;    // row-major output, box {32 cols, 32 rows, 1} (TMA store from the epilogue)
   CUtensorMap tmAux;    // pre-activation stash, same box
   int tma_out;          // 1: epilogue stores through TMA (CVFLOW_GEMM_EPI=0: the round-1 path, kept for A/B timing)
+  int w_prefetch;       // producer issues the first tile's W loads before griddepcontrol.wait (GemmArgs::w_static)
   int epi_direct;       // 1: epilogue stores as coalesced st.global.v4 after a transposition through the staging tile
   GemmSeg seg[8];
   int nseg, nkb_total;

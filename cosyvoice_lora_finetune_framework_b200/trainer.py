@@ -270,9 +270,11 @@ class FlowLoRATrainer:
         """One full optimiser step (CFM prep, estimator fwd, loss, bwd, allreduce, clip+AdamW, W_eff
         refresh: ~1,340 kernel launches) replayed as ONE CUDA graph. Shapes must stay fixed; the
         inputs are copied into static buffers, the RNG advances per replay (graph-safe Philox), and
-        the per-step optimiser scalars come from device memory. Returns the (static) loss tensor."""
-        if self.accumulate != 1:
-            raise ValueError("train_step_graphed captures a whole optimiser step: accumulate must be 1")
+        the per-step optimiser scalars come from device memory. Returns the (static) loss tensor.
+
+        With accumulate > 1 (the reference's accumulate_grad_batches, config.py) two graphs are captured: the
+        micro-step (forward + backward accumulating into the flat bucket, loss / accumulate) replayed per call, and the
+        optimiser tail (allreduce, clip + AdamW, refresh) replayed after every `accumulate`-th call."""
         if self.extra:
             raise ValueError("train_step_graphed captures the estimator-only step (prepared mu / spks); with "
                              "extra_params use micro_step / optimizer_step around the model's own forward")
@@ -284,11 +286,20 @@ class FlowLoRATrainer:
             for k in ("x1", "mask", "mu", "spks", "cond"):
                 st[k].copy_(locals()[k])
 
-            def body():
+            acc = self.accumulate
+
+            def micro_body():
                 loss, _ = self.cfm.compute_loss(st["x1"], st["mask"], st["mu"], st["spks"], cond=st["cond"])
-                loss.backward()
-                self.optimizer_step()
+                (loss / acc if acc > 1 else loss).backward()
                 return loss.detach()
+
+            def body():
+                loss = micro_body()
+                if acc > 1:                      # warm-up of the two-graph form: a full accumulation window
+                    for _ in range(acc - 1):
+                        micro_body()
+                self.optimizer_step()
+                return loss
 
             self.ne.attach_grads()
             # The two warm-up executions (plans, workspace, NCCL channels) must not count as training: parameters, Adam
@@ -323,9 +334,22 @@ class FlowLoRATrainer:
             # with it the parameters' AccumulateGrad nodes (bound to the stream they were created on), alive; the captured
             # backward would then sync the capturing stream with that uncaptured stream and the capture fails with
             # cudaErrorStreamCaptureIsolation. Drop such references (float(loss) / del loss) before the first graphed step.
-            with torch.cuda.graph(g):
-                st["loss"] = body()
+            if acc == 1:
+                with torch.cuda.graph(g):
+                    st["loss"] = body()
+            else:
+                with torch.cuda.graph(g):
+                    st["loss"] = micro_body()
+                g2 = torch.cuda.CUDAGraph()
+                chunks, self._chunks = self._chunks, []      # the chunk events belong to another capture: one plain allreduce
+                try:
+                    with torch.cuda.graph(g2):
+                        self.optimizer_step()
+                finally:
+                    self._chunks = chunks
+                st["opt_graph"] = g2
             self.step_count = snap["step"]         # capture executes nothing
+            self.micro = 0
             st["graph"] = g
             self._graph = st
         st = self._graph
@@ -335,6 +359,12 @@ class FlowLoRATrainer:
         st["spks"].copy_(spks, non_blocking=True)
         st["cond"].copy_(cond, non_blocking=True)
         st["graph"].replay()
+        if "opt_graph" in st:
+            self.micro += 1
+            if self.micro < self.accumulate:
+                return st["loss"]
+            st["opt_graph"].replay()
+            self.micro = 0
         self.step_count += 1
         return st["loss"]
 

@@ -133,6 +133,37 @@ def test_graphed_step_matches_eager_step():
     assert torch.allclose(p1, p0, rtol=1e-3, atol=2e-5), float((p1 - p0).abs().max())
 
 
+def test_graphed_accumulation_matches_eager_accumulation():
+    """accumulate_grad_batches > 1 (the reference trains with batch 1 x accumulate 16, config.py): the micro-step graph
+    replayed per micro-batch plus the optimiser-tail graph after every window == eager micro_step / optimizer_step."""
+    from cosyvoice_lora_finetune_framework_b200.trainer import FlowLoRATrainer
+    results = []
+    g = torch.Generator().manual_seed(2)
+    B, T = 2, 72
+    batches = [(torch.randn(B, 80, T, generator=g).cuda(), torch.randn(B, 80, T, generator=g).cuda(),
+                torch.randn(B, 80, generator=g).cuda()) for _ in range(3)]
+    cond, mask = torch.zeros(B, 80, T).cuda(), torch.ones(B, 1, T).cuda()
+    mask[1, :, 40:] = 0
+    for graphed in (False, True):
+        model = _model(seed=9)
+        model.eval()
+        cfm = model.flow.decoder
+        cfm.estimator.train()
+        tr = FlowLoRATrainer(cfm, lr=1e-3, accumulate=3)
+        torch.manual_seed(321)
+        torch.cuda.manual_seed_all(321)
+        losses = []
+        for w in range(2):                       # two optimiser steps of three micro-batches each
+            for x1, mu, spks in batches:
+                fn = tr.train_step_graphed if graphed else tr.train_step
+                losses.append(float(fn(x1, mask, mu, spks, cond)))
+        results.append((losses, tr.ne.param_bucket.clone(), tr.step_count, int(tr.opt_state[0].item())))
+    (l0, p0, s0, d0), (l1, p1, s1, d1) = results
+    assert s0 == s1 == 2 and d0 == d1 == 2
+    assert torch.allclose(torch.tensor(l1), torch.tensor(l0), rtol=2e-3, atol=1e-5), (l0, l1)
+    assert torch.allclose(p1, p0, rtol=1e-3, atol=2e-5), float((p1 - p0).abs().max())
+
+
 def test_optimizer_schedule_state_and_resume():
     """Device-side step counter / LR schedule (LambdaLR semantics: the first warm-up step runs with lr = 0), skipped
     steps on a non-finite gradient norm, and trainer.state_dict() / load_state_dict() round trip."""
