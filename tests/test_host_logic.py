@@ -138,3 +138,40 @@ def test_cabi_reports_argument_errors_without_a_gpu():
         assert rc < 0, tag
         assert tag in L.cvflow_last_error(), (tag, L.cvflow_last_error())
     assert L.cvflow_workspace_bytes(null, 2, 16, 1) < 0
+
+
+def test_cabi_path_input_entry_points_validate_arguments():
+    """The stateless path-input entry points (length regulator, pack, speaker affine) reject null / inconsistent
+    arguments through the status code; the segment table must tile the output frames in order."""
+    from cosyvoice_lora_finetune_framework_b200 import _path_inputs as PI
+    L = PI._lib()
+    null = ctypes.c_void_p(None)
+    assert L.cvflow_regulator_saved_floats(2, 130) == 4 * 2 * 130 * 80 + 4 * 2 * 2 * 3
+    assert L.cvflow_regulator_scratch_floats(2, 130) == 2 * 2 * 130 * 80 + 2 * 2 * 2 * 2
+    assert L.cvflow_regulator_forward(None, None, null) < 0 and b"cvflow_regulator_forward" in L.cvflow_last_error()
+    w, io = PI.RegulatorWeights(), PI.RegulatorIO()
+    fake = 0x1000                                  # never dereferenced: validation fails first
+    for i in range(5):
+        w.wf[i] = w.wb[i] = w.bias[i] = fake
+    for i in range(4):
+        w.gamma[i] = w.beta[i] = fake
+    io.src, io.saved, io.out = fake, fake, fake
+    io.B, io.n_src, io.T, io.n_seg = 1, 10, 20, 2
+    io.seg[0][:] = [0, 4, 0, 8]
+    io.seg[1][:] = [4, 6, 9, 11]                   # gap: frame 8 is covered by no segment
+    assert L.cvflow_regulator_forward(ctypes.byref(w), ctypes.byref(io), null) < 0
+    assert b"segment 1" in L.cvflow_last_error()
+    io.seg[1][:] = [4, 7, 8, 12]                   # reads source frame 10 of 10
+    assert L.cvflow_regulator_forward(ctypes.byref(w), ctypes.byref(io), null) < 0
+    io.seg[1][:] = [4, 6, 8, 11]                   # covers 19 of 20 frames
+    assert L.cvflow_regulator_forward(ctypes.byref(w), ctypes.byref(io), null) < 0
+    assert b"cover 19 frames" in L.cvflow_last_error()
+    w.gamma[2] = None
+    io.seg[1][:] = [4, 6, 8, 12]
+    assert L.cvflow_regulator_backward(ctypes.byref(w), ctypes.byref(io), null, null, null, null) < 0
+    assert b"weight image 2" in L.cvflow_last_error()
+    assert L.cvflow_path_inputs_pack(null, null, 0, null, -6.0, 2.0, 0.0, null, null, null, 1, 8, null) < 0
+    assert L.cvflow_spk_affine(null, null, null, null, 1, 192, 80, null) < 0 and b"cvflow_spk_affine" in L.cvflow_last_error()
+    # the segment table of InterpolateRegulator.inference (modules.py:826-836)
+    assert PI.inference_segments(30, 75, 52, 129) == [(0, 30, 0, 52), (30, 20, 52, 34), (50, 35, 86, 61), (85, 20, 147, 34)]
+    assert PI.inference_segments(0, 33, 0, 56) == [(0, 33, 0, 56)]
