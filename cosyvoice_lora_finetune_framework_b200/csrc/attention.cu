@@ -209,7 +209,12 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   if (threadIdx.x == 0) stamp(1);
+// the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
+  // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
+  AttnItem first;
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
   pdl_wait();
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
   if (threadIdx.x == 0) stamp(2);
 
   if (warp == 8) {
@@ -217,7 +222,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     if (lane == 0) {
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);   // extent of the next item: load issued early
@@ -254,7 +259,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
       const uint32_t idesc_o = umma_idesc_f16(bf, 128, 64, 0, 1);
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);
@@ -306,7 +311,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     uint32_t n = 0;
     const int nwords = 8 * ((L + 255) / 256);
     const int* bits_base = kmax_arr + ((plan.B + 3) & ~3);
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
+    AttnItem nxt = first;
     uint4 nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
     uint4 nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -426,6 +431,8 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
+
+void attn_plan_set_early_kinfo(void* plan, int on) { reinterpret_cast<AttnPlan*>(plan)->early_kinfo = on; }
 
 int attn_fwd_prepare(void* plan_, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen) {
   AttnPlan* p = reinterpret_cast<AttnPlan*>(plan_);

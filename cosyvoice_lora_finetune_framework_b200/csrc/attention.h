@@ -30,6 +30,7 @@ struct AttnPlan {
   int B, L, bf16;
   int tpi;              // 128-row tiles per item: 2 (one per warpgroup) or, when that leaves SMs idle, 1 (warpgroup 0 only)
   long long* dbg;       // optional per-CTA globaltimer stamps (profiling aid)
+  int early_kinfo;      // kinfo is NOT written by the kernel launched just before: its first read may precede the grid-dependency wait
 };
 
 static constexpr float kAttnScale = 0.125f;                               // d^-1/2, d = 64

@@ -79,14 +79,19 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+// the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
+  // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
+  AttnItem first;
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
   pdl_wait();
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
@@ -125,7 +130,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
       const uint32_t idesc_q = umma_idesc_f16(bf, 128, 64, 0, 1);
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0, m = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
@@ -179,7 +184,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
     const int nwords = 8 * ((L + 255) / 256);
     const int* bits_base = kinfo + ((plan.B + 3) & ~3);
     uint32_t n = 0, m = 0;
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+    AttnItem nxt = first;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const AttnItem a = nxt;
       nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
@@ -366,14 +371,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+// the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
+  // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
+  AttnItem first;
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
   pdl_wait();
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int ks = 0, ring = 0;
       uint32_t kph = 0, rph = 0;
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
@@ -408,7 +418,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
       int ks = 0, ring = 0;         // ring = slot of the item's first query block
       uint32_t kph = 0, rph = 0, m = 0;
       uint32_t pcnt[2] = {0u, 0u};  // completed uses of the two P^T/dS^T buffers (parity of p_full)
-      AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+      AttnItem nxt = first;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const AttnItem a = nxt;
         nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
@@ -497,7 +507,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
     float* stat = reinterpret_cast<float*>(gbase + DkvSmem::kStat) + w * 256;   // [2 buffers][-lse 64 | -delta d^-1/2 64]
     uint32_t m = 0, sgrp = 0;
     uint32_t scnt[2] = {0u, 0u};   // completed uses of the two score buffers (parity of s_full)
-    AttnItem nxt = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+    AttnItem nxt = first;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const AttnItem a = nxt;
       nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);

@@ -493,6 +493,7 @@ int Estimator::tb_fwd(const std::string& Q, int lora_idx, float* h0, int B, int 
     if ((size_t)attn_idx_ >= pl.attn.size()) {
       pl.attn.emplace_back(attn_plan_bytes());
       if (attn_fwd_prepare(pl.attn.back().data(), qkv, ldq, B, L, cfg.bf16, error_buf(), error_buf_len())) return -1;
+      attn_plan_set_early_kinfo(pl.attn.back().data(), 1);   // kinfo comes from the start of the forward, not from the previous launch
     }
     prof_begin(1, 4.0 * B * 8.0 * (double)L * L * 64);
     if (!(kSkip(skip_) & 1u)) CKL(attn_fwd_launch(pl.attn[attn_idx_].data(), kmax, iso_p, o, lse, stream_));
@@ -894,6 +895,7 @@ int Estimator::tb_bwd(const TBRec& t, float* dh32, void* dh16, bool need_input_g
       pl.attn.emplace_back(attn_plan_bytes());
       if (attn_bwd_prepare(pl.attn.back().data(), t.qkv, t.ldq, tmp.dO, t.B, t.L, cfg.bf16, error_buf(), error_buf_len()))
         return -1;
+      attn_plan_set_early_kinfo(pl.attn.back().data(), 1);
     }
     prof_begin(2, 10.0 * t.B * 8.0 * (double)t.L * t.L * 64);
     if (wgrad_side_ && ev_done_valid_[par]) {   // the side-stream wgrad that last read this dqkv / v buffer pair has finished

@@ -72,6 +72,7 @@ int launch_gn_bwd(const void* dy, int dy_f32, const void* c16, const float* stat
 // keymask fp32 [B][L]; iso_p: prompt-isolation boundary at this resolution (0 = off).
 struct AttnPlan;  // holds the encoded tensor maps
 int attn_plan_bytes();
+void attn_plan_set_early_kinfo(void* plan, int on);   // kinfo is not produced by the launch right before the attention kernels
 void attn_set_debug_buffer(void* p);   // profiling aid: 16 x int64 globaltimer stamps per CTA of the next forward plans
 int attn_fwd_prepare(void* plan, const void* qkv, long ldq, int B, int L, int bf16, char* err, int errlen);
 // kinfo (attn_kinfo_ints(B, L) ints): [b] = kmax[b] = 1 + last index with keymask[b][.] != 0 -- rows and keys beyond

@@ -84,17 +84,19 @@ __global__ void __launch_bounds__(256) ln_lora_drop_fwd_kernel(const float* __re
   constexpr int NV = 3 * R;
   constexpr int TOK = 1;     // measured: two tokens per pass (shared A-row fetches) is no faster, registers cost occupancy
   __shared__ __align__(16) uint16_t As[NV * 256];
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long stride = (long)gridDim.x * 8;
-  // the first pass's row, gamma / beta and the seed are requested before the A_cat staging: one L2 round trip, not three
+  // constants of the step (LayerNorm affine, the seed bumped at the start of the forward, the LoRA factor image written
+  // by lora_merge: none is produced by the kernel launched just before this one) are fetched and staged while the
+  // predecessor drains; only the token rows wait for it
   float g[8], b[8], xfirst[8];
-  const long mfirst = (long)blockIdx.x * 8 + warp;
-  if (mfirst < M) load8_f32(h + mfirst * 256 + lane * 8, xfirst);
   load8_f32(gamma + lane * 8, g);
   load8_f32(beta + lane * 8, b);
   const unsigned long long seed = d.dbg ? 0ull : d.seed[0];
   load_acat<R>(As, acat);
+  pdl_wait();
+  const long mfirst = (long)blockIdx.x * 8 + warp;
+  if (mfirst < M) load8_f32(h + mfirst * 256 + lane * 8, xfirst);
   pdl_launch();
   for (long mb = mfirst; mb < M; mb += stride * TOK) {
     float xv[TOK][8];
@@ -207,11 +209,11 @@ __global__ void __launch_bounds__(256) ln_lora_drop_bwd_kernel(const uint16_t* _
   constexpr int NV = 3 * R;
   constexpr int TOK = 1;     // measured: two tokens per pass is slower here (19.0 vs 14.8 us)
   __shared__ __align__(16) uint16_t As[NV * 256];
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[8];
-  load8_f32(gamma + lane * 8, g);
+  load8_f32(gamma + lane * 8, g);      // step constants: staged before the grid-dependency wait (see the forward kernel)
   load_acat<R>(As, acat);
+  pdl_wait();
   pdl_launch();
   const long stride = (long)gridDim.x * 8;
   for (long mb = (long)blockIdx.x * 8 + warp; mb < M; mb += stride * TOK) {
