@@ -47,10 +47,10 @@ def _stream():
 
 
 def _conv_image(w):
-    """Conv1d weight [co][ci][taps] -> kernel image [ci][tap][8][12] (10 output channels per group, padded to 12)."""
+    """Conv1d weight [co][ci][taps] -> kernel image [ci][tap][16][6] (5 output channels per group, padded to 6)."""
     co, ci, taps = w.shape
-    img = torch.zeros(ci, taps, 8, 12, device=w.device, dtype=torch.float32)
-    img[:, :, :, :10] = w.detach().float().permute(1, 2, 0).reshape(ci, taps, 8, 10)
+    img = torch.zeros(ci, taps, 16, 6, device=w.device, dtype=torch.float32)
+    img[:, :, :, :5] = w.detach().float().permute(1, 2, 0).reshape(ci, taps, 16, 5)
     return img.contiguous()
 
 

@@ -172,7 +172,7 @@ int launch_optim_advance(int* state, float* hyper, const float* sumsq, const flo
 
 // ---- regulator.cu: the inputs of the path (length regulator, speaker affine, conditioning pack) -----------------
 struct RegSeg { int src0, srcn, dst0, dstn; };   // F.interpolate(src[:, src0:src0+srcn], size=dstn, mode='linear') -> frames [dst0, dst0+dstn)
-struct RegulatorWeights {          // fp32 device pointers; conv images [ci][tap][8][12] (see regulator.cu), wb = dgrad images
+struct RegulatorWeights {          // fp32 device pointers; conv images [ci][tap][16][6] (see regulator.cu), wb = dgrad images
   const float* wf[5];
   const float* wb[5];
   const float* bias[5];

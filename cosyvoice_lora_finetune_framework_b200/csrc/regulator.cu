@@ -29,9 +29,10 @@ constexpr int kC = 80;        // channels (flow_model.py:715-720: InterpolateReg
 constexpr int kTT = 128;      // frames per CTA tile
 constexpr int kXP = 132;      // pitch of the transposed operand tile xs[ci][kXP]: frames t0-1 .. t0+128, 16-byte aligned rows
 constexpr int kOP = 81;       // pitch of the output tile os[frame][kOP]
-constexpr int kCG = 8;        // channel groups (one warp each) of 10 output channels ...
-constexpr int kCW = 12;       // ... padded to 12 floats so a group's weights are three aligned vector loads
-constexpr int kThreads = 256;
+constexpr int kCG = 16;       // channel groups (one warp each) of kCPW output channels ...
+constexpr int kCPW = 5;
+constexpr int kCW = 6;        // ... padded to 6 floats so a group's weights are three aligned 8-byte loads
+constexpr int kThreads = 512; // 16 warps: four per scheduler hide the shared-memory / FMA latency of the 20-accumulator inner loop
 constexpr float kGnEps = 1e-5f;
 
 enum { PRO_INTERP = 0, PRO_GN_MISH = 1, PRO_MASK = 2, PRO_GN_BWD = 3 };
@@ -79,7 +80,7 @@ struct RegConv {
   const float* spart_in;    // GN_BWD: [B][NT][2] partial sums of G and G x^
   const float* gamma_in;    // GN_MISH
   const float* beta_in;
-  const float* w;           // weight image [ci][tap][8][12]
+  const float* w;           // weight image [ci][tap][16][6]
   const float* bias;        // nullable
   // result
   float* out;
@@ -133,15 +134,24 @@ __global__ void __launch_bounds__(kThreads, 1) reg_conv_kernel(const RegConv p) 
   float* ws = smem + kC * kXP;               // [80][TAPS][8][12]
   __shared__ float sc[8];                    // 0 mean_in, 1 rstd_in, 2 m1, 3 m2, 4 mean_prev, 5 rstd_prev
   __shared__ float red[2][kThreads / 32];
+  __shared__ __align__(8) unsigned long long wbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kTT;
   const int T = p.T, nt = (T + kTT - 1) / kTT;
 
-  // the weight image is a constant of the model: fetch it while the previous kernel drains
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.w);
-    float4* dst = reinterpret_cast<float4*>(ws);
-    for (int i = tid; i < kC * TAPS * kCG * kCW / 4; i += kThreads) dst[i] = __ldg(src + i);
+  // the weight image is a constant of the model: one thread requests it as bulk copies (all 92 KB in flight at once)
+  // while the previous kernel drains; it lands under the prologue and is waited for right before the inner loop
+  constexpr uint32_t kWBytes = (uint32_t)(kC * TAPS * kCG * kCW * sizeof(float));
+  if (tid == 0) {
+    mbar_init(smem_u32(&wbar), 1);
+    fence_barrier_init();
+    mbar_expect_tx(smem_u32(&wbar), kWBytes);
+    constexpr uint32_t kChunk = kWBytes / TAPS / 2;     // 15,360-byte pieces
+#pragma unroll
+    for (uint32_t o = 0; o < kWBytes; o += kChunk)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ws) + o),
+                   "l"(reinterpret_cast<const uint8_t*>(p.w) + o), "r"(kChunk), "r"(smem_u32(&wbar))
+                   : "memory");
   }
   pdl_wait();
 
@@ -165,50 +175,64 @@ __global__ void __launch_bounds__(kThreads, 1) reg_conv_kernel(const RegConv p) 
   const int len_b = p.lens ? p.lens[b] : T;
   const int blind_b = p.blind ? p.blind[b] : 0;
   constexpr int kFr = kTT + 2;
-  if (PRO == PRO_MASK && p.in_channel_major) {
-    for (int idx = tid; idx < kC * kFr; idx += kThreads) {
-      const int c = idx / kFr, tt = idx - c * kFr, t = t0 - 1 + tt;
-      float v = 0.f;
-      if (t >= blind_b && t < len_b && t < T) v = p.in[((long)b * kC + c) * T + t];
-      xs[c * kXP + tt] = v;
-    }
-  } else {
-    const float mean = sc[0], rstd = sc[1], m1 = sc[2], m2 = sc[3];
-    for (int idx = tid; idx < kC * kFr; idx += kThreads) {
-      const int tt = idx / kC, c = idx - tt * kC, t = t0 - 1 + tt;
-      float v = 0.f;
+  // every global load of the tile is issued before the first value is used (one L2 round trip, not 21 dependent ones)
+  constexpr int kPer = (kC * kFr + kThreads - 1) / kThreads;
+  const bool cm_in = PRO == PRO_MASK && p.in_channel_major;
+  float ra[kPer], rb[kPer], rw[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int idx = tid + u * kThreads;
+    ra[u] = 0.f; rb[u] = 0.f; rw[u] = 0.f;
+    if (idx < kC * kFr) {
+      const int tt = cm_in ? idx % kFr : idx / kC, c = cm_in ? idx / kFr : idx % kC, t = t0 - 1 + tt;
       if (t >= 0 && t < T) {
         if (PRO == PRO_INTERP) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            if (s < p.n_seg && t >= p.seg[s].dst0 && t < p.seg[s].dst0 + p.seg[s].dstn) {
-              const LerpTap k = lerp_tap(t - p.seg[s].dst0, p.seg[s].srcn, p.seg[s].dstn);
-              const float* row = p.in + ((long)b * p.n_src + p.seg[s].src0) * kC + c;
-              v = k.w0 * row[(long)k.i0 * kC] + k.w1 * row[(long)k.i1 * kC];
+          for (int sg = 0; sg < 4; ++sg) {
+            if (sg < p.n_seg && t >= p.seg[sg].dst0 && t < p.seg[sg].dst0 + p.seg[sg].dstn) {
+              const LerpTap k = lerp_tap(t - p.seg[sg].dst0, p.seg[sg].srcn, p.seg[sg].dstn);
+              const float* row = p.in + ((long)b * p.n_src + p.seg[sg].src0) * kC + c;
+              ra[u] = row[(long)k.i0 * kC];
+              rb[u] = row[(long)k.i1 * kC];
+              rw[u] = k.w1;
             }
           }
-        } else if (PRO == PRO_GN_MISH) {
-          const float y = p.in[((long)b * T + t) * kC + c];
-          v = mish_acc((y - mean) * rstd * p.gamma_in[c] + p.beta_in[c]);
         } else if (PRO == PRO_MASK) {
-          if (t >= blind_b && t < len_b) v = p.in[((long)b * T + t) * kC + c];
-        } else {   // GroupNorm backward of the layer whose raw output is in_y: dy = rstd (G - mean(G) - x^ mean(G x^))
-          const float g = p.in[((long)b * T + t) * kC + c];
-          const float xh = (p.in_y[((long)b * T + t) * kC + c] - mean) * rstd;
-          v = rstd * (g - m1 - xh * m2);
+          if (t >= blind_b && t < len_b) ra[u] = cm_in ? p.in[((long)b * kC + c) * T + t] : p.in[((long)b * T + t) * kC + c];
+        } else {
+          ra[u] = p.in[((long)b * T + t) * kC + c];
+          if (PRO == PRO_GN_BWD) rb[u] = p.in_y[((long)b * T + t) * kC + c];
         }
       }
-      xs[c * kXP + tt] = v;
     }
   }
-  __syncthreads();
+  {
+    const float mean = sc[0], rstd = sc[1], m1 = sc[2], m2 = sc[3];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int idx = tid + u * kThreads;
+      if (idx < kC * kFr) {
+        const int tt = cm_in ? idx % kFr : idx / kC, c = cm_in ? idx / kFr : idx % kC, t = t0 - 1 + tt;
+        float v = 0.f;
+        if (t >= 0 && t < T) {
+          if (PRO == PRO_INTERP) v = __fsub_rn(1.f, rw[u]) * ra[u] + rw[u] * rb[u];
+          else if (PRO == PRO_GN_MISH) v = mish_acc((ra[u] - mean) * rstd * p.gamma_in[c] + p.beta_in[c]);
+          else if (PRO == PRO_MASK) v = ra[u];
+          else v = rstd * (ra[u] - m1 - (rb[u] - mean) * rstd * m2);   // GroupNorm backward: rstd (G - mean(G) - x^ mean(G x^))
+        }
+        xs[c * kXP + tt] = v;
+      }
+    }
+  }
+  __syncthreads();             // operand tile complete (and the barrier initialisation visible to every thread)
+  mbar_wait(smem_u32(&wbar), 0u);
 
-  // ---- 4 frames x 10 output channels per thread: warp = channel group (weights broadcast), lane = frame quad ----
-  float acc[4][10];
+  // ---- 4 frames x 5 output channels per thread: warp = channel group (weights broadcast), lane = frame quad ----
+  float acc[4][kCPW];
 #pragma unroll
   for (int f = 0; f < 4; ++f)
 #pragma unroll
-    for (int j = 0; j < 10; ++j) acc[f][j] = 0.f;
+    for (int j = 0; j < kCPW; ++j) acc[f][j] = 0.f;
   {
     const float* xr = xs + 4 * lane + (TAPS == 1 ? 1 : 0);
     const float* wr = ws + warp * kCW;
@@ -224,14 +248,15 @@ __global__ void __launch_bounds__(kThreads, 1) reg_conv_kernel(const RegConv p) 
       }
 #pragma unroll
       for (int k = 0; k < TAPS; ++k) {
-        const float4 wa = *reinterpret_cast<const float4*>(wr + k * kCG * kCW);
-        const float4 wb = *reinterpret_cast<const float4*>(wr + k * kCG * kCW + 4);
-        const float2 wc = *reinterpret_cast<const float2*>(wr + k * kCG * kCW + 8);
-        const float w[10] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y};
+        const float2 wa = *reinterpret_cast<const float2*>(wr + k * kCG * kCW);
+        const float2 wb = *reinterpret_cast<const float2*>(wr + k * kCG * kCW + 2);
+        const float2 wc = *reinterpret_cast<const float2*>(wr + k * kCG * kCW + 4);
+        float w[kCPW];
+        w[0] = wa.x; w[1] = wa.y; w[2] = wb.x; w[3] = wb.y; w[4] = wc.x;
 #pragma unroll
         for (int f = 0; f < 4; ++f)
 #pragma unroll
-          for (int j = 0; j < 10; ++j) acc[f][j] = fmaf(w[j], x[f + k], acc[f][j]);
+          for (int j = 0; j < kCPW; ++j) acc[f][j] = fmaf(w[j], x[f + k], acc[f][j]);
       }
       xr += kXP;
       wr += TAPS * kCG * kCW;
@@ -242,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) reg_conv_kernel(const RegConv p) 
 #pragma unroll
   for (int f = 0; f < 4; ++f)
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      const int c = warp * 10 + j;
+    for (int j = 0; j < kCPW; ++j) {
+      const int c = warp * kCPW + j;
       os[(4 * lane + f) * kOP + c] = acc[f][j] + (p.bias ? p.bias[c] : 0.f);
     }
   __syncthreads();
@@ -298,15 +323,25 @@ __global__ void __launch_bounds__(kThreads, 1) reg_conv_kernel(const RegConv p) 
   } else {   // EPI_MISH_BWD: acc = dL/d(activation of the layer below); G = acc mish'(u) gamma, sums of G and G x^
     const float mean = sc[4], rstd = sc[5];
     float s1 = 0.f, s2 = 0.f;
-    for (int idx = tid; idx < nv * kC; idx += kThreads) {
-      const int tt = idx / kC, c = idx - tt * kC;
-      const long gi = ((long)b * T + t0 + tt) * kC + c;
-      const float xh = (p.y_prev[gi] - mean) * rstd;
-      const float ga = p.gamma_prev[c];
-      const float g = os[tt * kOP + c] * mish_grad_acc(ga * xh + p.beta_prev[c]) * ga;
-      p.out[gi] = g;
-      s1 += g;
-      s2 += g * xh;
+    constexpr int kPerE = kTT * kC / kThreads;
+    float yp[kPerE];
+#pragma unroll
+    for (int u = 0; u < kPerE; ++u) {      // the tile's rows are contiguous in y_prev / out: element idx of the tile
+      const int idx = tid + u * kThreads;
+      yp[u] = idx < nv * kC ? p.y_prev[((long)b * T + t0) * kC + idx] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPerE; ++u) {
+      const int idx = tid + u * kThreads;
+      if (idx < nv * kC) {
+        const int tt = idx / kC, c = idx - tt * kC;
+        const float xh = (yp[u] - mean) * rstd;
+        const float ga = p.gamma_prev[c];
+        const float g = os[tt * kOP + c] * mish_grad_acc(ga * xh + p.beta_prev[c]) * ga;
+        p.out[((long)b * T + t0) * kC + idx] = g;
+        s1 += g;
+        s2 += g * xh;
+      }
     }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }

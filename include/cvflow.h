@@ -302,7 +302,7 @@ CVFLOW_API int cvflow_optim_advance(int32_t* state, float* hyper, const float* s
  *   F.interpolate(mode='linear') of the projected encoder output, 4 x [Conv1d(80,80,3,pad 1) -> GroupNorm(1,80) -> Mish],
  *   Conv1d(80,80,1), * pad mask; the interpolation indices are bit-identical to at::upsample_linear1d's.
  * The weights are the module's frozen parameters in a kernel-friendly image:
- *   wf[l] forward image  [ci][tap][8][12]: wf[((ci*taps + k)*8 + co/10)*12 + co%10] = weight[co][ci][k]   (taps 3,3,3,3,1)
+ *   wf[l] forward image  [ci][tap][16][6]: wf[((ci*taps + k)*16 + co/5)*6 + co%5] = weight[co][ci][k], pad entries 0 (taps 3,3,3,3,1)
  *   wb[l] dgrad image, same layout with the roles of ci / co swapped and the taps reversed: weight[ci][co][taps-1-k]
  * ------------------------------------------------------------------------------------------- */
 typedef struct cvflow_regulator_weights {
