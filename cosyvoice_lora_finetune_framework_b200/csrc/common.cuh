@@ -215,16 +215,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a wrong descriptor / byte count must fault loudly rather than hang the box
-// (a hung GPU box is a strike). Each try may park the thread for up to ~10 ms, so 2^9 tries is
-// seconds, far beyond any legitimate wait in these kernels.
+// Bounded wait: a wrong descriptor / byte count must fault loudly rather than hang the box (a hung GPU box is a
+// strike). The bound is WALL TIME on %globaltimer (5 s), not a try count: how long one try_wait parks is up to the
+// hardware (the hint is only an upper limit), and under a profiler's instrumented replay passes a kernel runs two orders
+// of magnitude slower -- a count-based bound fired there (ncu --set full on the dK/dV kernel at L = 400).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0ull;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 9)) {
-      printf("cvflow: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 255u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > 5000000000ull) {
+        printf("cvflow: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, bar,
+               parity);
+        __trap();
+      }
     }
   }
 }
