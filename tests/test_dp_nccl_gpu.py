@@ -1,7 +1,8 @@
 """Two NCCL ranks on two GPUs through the CUDA path (skipped with fewer than 2 devices; run with `gpurun --gpus 2`):
 the data-parallel optimiser step (chunked allreduce of the flat LoRA bucket on a side stream behind the backward's
 per-chunk events, fused clip + AdamW) must equal AdamW applied to the MEAN of the two single-rank CUDA gradients, and
-leave identical parameters on both ranks -- eager and as a captured whole-step graph."""
+leave identical parameters on both ranks -- eager, as a captured whole-step graph, and with gradient accumulation as the
+micro-step graph + optimiser-tail graph pair."""
 import os
 
 import pytest
@@ -10,7 +11,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, graphed, out):
+def _worker(rank, world, port, graphed, acc, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -30,7 +31,7 @@ def _worker(rank, world, port, graphed, out):
                         p.add_(0.01)
         est = est.to(dev).train()
         cfm = ConditionalCFM(in_channels=80, n_spks=1, spk_emb_dim=80, estimator=est)
-        tr = FlowLoRATrainer(cfm, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+        tr = FlowLoRATrainer(cfm, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, accumulate=acc)
         assert len(tr._chunks) >= 2, "gradient chunks not set up"
         p0 = tr.ne.param_bucket.clone()
         both = [torch.empty_like(p0) for _ in range(world)]
@@ -44,8 +45,9 @@ def _worker(rank, world, port, graphed, out):
         mask[1, :, 60 - 7 * rank:] = 0
         # single-rank gradient of this shard (same draws as the step below)
         torch.manual_seed(7 + rank)
-        loss, _ = cfm.compute_loss(x1, mask, mu, spks, cond=cond)
-        loss.backward()
+        for _ in range(acc):                                  # `acc` micro-batches (fresh draws each) accumulate loss / acc
+            loss, _ = cfm.compute_loss(x1, mask, mu, spks, cond=cond)
+            (loss / acc).backward()
         # drop the eager autograd graph: it keeps the parameters' AccumulateGrad nodes (created on the default stream)
         # alive, and a later CAPTURED backward that reuses them would make the capturing stream wait on the uncaptured
         # default stream (cudaErrorStreamCaptureIsolation)
@@ -64,10 +66,12 @@ def _worker(rank, world, port, graphed, out):
         opt.step()
         # the data-parallel step through the trainer
         torch.manual_seed(7 + rank)
-        if graphed:
-            tr.train_step_graphed(x1, mask, mu, spks, cond)
-        else:
-            tr.train_step(x1, mask, mu, spks, cond)
+        for _ in range(acc):       # accumulate > 1, graphed: the micro-step graph per call, the optimiser-tail graph after the last
+            if graphed:
+                tr.train_step_graphed(x1, mask, mu, spks, cond)
+            else:
+                tr.train_step(x1, mask, mu, spks, cond)
+        assert tr.step_count == 1
         torch.cuda.synchronize()
         got = tr.ne.param_bucket.clone()
         dist.all_gather(both, got)
@@ -83,13 +87,13 @@ def _worker(rank, world, port, graphed, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graphed", [False, True])
-def test_two_rank_nccl_step_equals_mean_gradient_adamw(graphed):
+@pytest.mark.parametrize("graphed,acc", [(False, 1), (True, 1), (True, 2)])
+def test_two_rank_nccl_step_equals_mean_gradient_adamw(graphed, acc):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29500 + (os.getpid() % 400) + (50 if graphed else 0)
-    mp.spawn(_worker, args=(2, port, graphed, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 400) + (50 if graphed else 0) + 25 * (acc - 1)
+    mp.spawn(_worker, args=(2, port, graphed, acc, out), nprocs=2, join=True)
     assert len(out) == 2
