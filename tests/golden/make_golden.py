@@ -10,6 +10,7 @@
                                                      # P=200, 10 steps), train_tiny_padprompt (boundary window running into the
                                                      # padding), dropout_c1 (300M, lora_dropout = 0.05 with preset masks)
 
+    python tests/golden/make_golden.py flowinfer     # flowmodel_infer_tiny: MaskedDiffWithXvec.inference / inference_like_training
     python tests/golden/make_golden.py regulator     # regulator_tiny / regulator_c3: InterpolateRegulator forward, inference and
                                                      # input gradient, real reference modules.py:800-837
 
@@ -356,6 +357,31 @@ def flow_model_case(name, init_seed, py_seed, step_seed):
           "|est|", float(est), stats["replaced_layers"])
 
 
+def flow_model_infer_case(name, init_seed, seed):
+    """MaskedDiffWithXvec.inference of the REAL reference (flow_model.py:475-551): prompt + target tokens -> encoder ->
+    InterpolateRegulator.inference (prompt | head | middle | tail stretched separately) -> prompt conditioning -> CFM Euler
+    solve (step count by length) -> mel without the prompt frames; plus inference_like_training (:553-638). The noise is the
+    first draw after torch.manual_seed(seed), so the test can regenerate it."""
+    ref_utils.set_all_random_seed(init_seed)
+    m = ref_flow.build_flow_model(None, 'cpu', **FLOW_TINY).eval()
+    g = torch.Generator().manual_seed(seed)
+    n_prompt, n_target = 30, 75
+    tok = torch.randint(0, 4096, (1, n_target), generator=g)
+    ptok = torch.randint(0, 4096, (1, n_prompt), generator=g)
+    pfeat = torch.randn(1, 52, 80, generator=g)
+    emb = torch.randn(1, 192, generator=g)
+    with torch.no_grad():
+        torch.manual_seed(seed)
+        mel, cache = m.inference(tok, torch.tensor([n_target]), ptok, torch.tensor([n_prompt]), pfeat, torch.tensor([52]), emb)
+        torch.manual_seed(seed + 1)
+        mel2 = m.inference_like_training(tok[:, :40], torch.tensor([40]), torch.tensor([68]), emb, prompt_feat=pfeat,
+                                         prompt_len=12, n_timesteps=10)
+    fx = dict(kind="flow_model_infer", arch=FLOW_TINY, init_seed=init_seed, seed=seed, token=tok, prompt_token=ptok,
+              prompt_feat=pfeat, embedding=emb, mel=mel, cache=cache, mel_like_training=mel2, wsum=wsum(m.state_dict()))
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "mel", tuple(mel.shape), "cache", tuple(cache.shape), "like-training", tuple(mel2.shape), float(mel.abs().mean()))
+
+
 def estimator_case(name, n_blocks, n_mid, Ts, seed):
     """export_onnx.py:34-41,95-116 protocol: batch 2, torch.rand inputs, random T."""
     cfm, sd, _ = build_ref(n_blocks, n_mid, r=0)
@@ -475,6 +501,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if sys.argv[1:] == ["flowmodel"]:
         flow_model_case("flowmodel_tiny", 21, 3, 5)
+        sys.exit(0)
+    if sys.argv[1:] == ["flowinfer"]:
+        flow_model_infer_case("flowmodel_infer_tiny", 21, 9)
         sys.exit(0)
     structure_checks()
     first_mid_last = lambda k: any(s in k for s in ("down_blocks.0.1.0.", "mid_blocks.5.1.2.", "up_blocks.1.1.3."))
