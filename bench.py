@@ -297,9 +297,14 @@ def flow_model_leg(a, device, dtype, timed):
     n = 5
     ms = timed(step, n) / n
     loss = float(step())
+    m.encoder_cuda_graphs = True          # encoder forward / backward replayed from CUDA graphs captured for this shape
+    for _ in range(3):
+        step()
+    ms_g = timed(step, n) / n
     res = {"config": "MaskedDiffWithXvec.forward(batch) + backward + clip/AdamW, %d x %d frames, LoRA on estimator q/k/v and on "
                      "the 6-block Conformer encoder (%d upstream tensors), eager launches" % (B, T, len(upstream)),
            "ms_per_step": ms, "value": B * T / (ms / 1e3), "unit": UNIT, "loss": loss,
+           "ms_per_step_encoder_cuda_graphs": ms_g,
            "path_inputs": getattr(m, "path_inputs_backend", "host PyTorch"),
            "encoder": "host PyTorch (eager, torch.autocast %s); SURVEY 8 f3 is not a kernel of this library" % str(dtype)}
     return res

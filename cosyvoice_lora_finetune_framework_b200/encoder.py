@@ -182,10 +182,8 @@ class ConformerEncoder(nn.Module):
     def forward(self, xs, xs_lens, decoding_chunk_size=0, num_decoding_left_chunks=-1):
         masks = ~make_pad_mask(xs_lens, xs.size(1)).unsqueeze(1)           # (b, 1, t)
         xs, pos_emb, masks = self.embed(xs, masks)
-        attn_masks = masks.clone()
-        empty = attn_masks.sum(dim=-1) == 0                                # fully padded rows attend everywhere
-        if bool(empty.any()):
-            attn_masks[empty] = True
+        empty = masks.sum(dim=-1, keepdim=True) == 0                       # fully padded rows attend everywhere
+        attn_masks = masks | empty                                         # (no host synchronisation: graph-capturable)
         for layer in self.encoders:
             xs, attn_masks, _, _ = layer(xs, attn_masks, pos_emb, masks)
         if self.normalize_before:

@@ -396,15 +396,54 @@ class MaskedDiffWithXvec(nn.Module):
     # model (Lightning precision '16-mixed', config.py:76; train_joint.py sets this to the estimator's operand dtype).
     encoder_autocast = None
 
+    # The host-side encoder is ~1,500 small ATen launches per step (forward + backward), i.e. launch-bound. With
+    # encoder_cuda_graphs = True its forward and backward are captured once per input shape
+    # (torch.cuda.make_graphed_callables) and replayed; meant for pipelines that pad batches to a few fixed shapes.
+    encoder_cuda_graphs = False
+    _enc_graph_cache_limit = 8
+
     def _encode(self, token, token_len, like):
         keep = (~make_pad_mask(token_len)).unsqueeze(-1).to(like)
         emb = self.input_embedding(torch.clamp(token, min=0)) * keep
+        if self.encoder_cuda_graphs and token.is_cuda and torch.is_grad_enabled() and self.training:
+            return self._encode_graphed(emb, token_len)
         if self.encoder_autocast is not None and token.is_cuda:
             with torch.autocast('cuda', dtype=self.encoder_autocast):
                 h, _ = self.encoder(emb, token_len)
                 return self.encoder_proj(h).float()
         h, _ = self.encoder(emb, token_len)
         return self.encoder_proj(h)
+
+    def _encode_graphed(self, emb, token_len):
+        cache = self.__dict__.setdefault("_enc_graphs", {})
+        key = (tuple(emb.shape), self.encoder_autocast, self.encoder.training)
+        fn = cache.get(key)
+        ac = self.encoder_autocast
+
+        class _Enc(nn.Module):
+            def __init__(s, enc, proj):
+                super().__init__()
+                s.enc, s.proj = enc, proj
+
+            def forward(s, x, n):
+                h, _ = s.enc(x, n)
+                return s.proj(h).float()
+
+        if fn is None:
+            if len(cache) >= self._enc_graph_cache_limit:
+                cache.pop(next(iter(cache)))
+            mod = _Enc(self.encoder, self.encoder_proj)
+            sample = (emb.detach().clone(), token_len.clone())
+            if ac is not None:
+                with torch.autocast('cuda', dtype=ac, cache_enabled=False):
+                    fn = torch.cuda.make_graphed_callables(mod, sample)
+            else:
+                fn = torch.cuda.make_graphed_callables(mod, sample)
+            cache[key] = fn
+        if ac is not None:
+            with torch.autocast('cuda', dtype=ac, cache_enabled=False):
+                return fn(emb, token_len)
+        return fn(emb, token_len)
 
     def _loss(self, feat, feat_len, h, embedding, conds, prompt_lens):
         mask = (~make_pad_mask(feat_len)).to(h)

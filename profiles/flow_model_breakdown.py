@@ -27,6 +27,7 @@ def main():
     m = m.to(dev).train()
     m.decoder.estimator.cvflow_dtype = torch.bfloat16
     m.encoder_autocast = torch.bfloat16 if os.environ.get('FMB_AUTOCAST', '1') == '1' else None
+    m.encoder_cuda_graphs = os.environ.get('FMB_ENC_GRAPHS', '0') == '1'
     upstream = [p for n, p in m.named_parameters() if p.requires_grad and not n.startswith('decoder.estimator.')]
     tr = FlowLoRATrainer(m.decoder, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, extra_params=upstream)
     batch = bench.flow_model_batch(B, T, 4321)
@@ -81,7 +82,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print("un-instrumented step (CUDA events): %.2f ms" % (e0.elapsed_time(e1) / n))
-    print("path inputs backend:", getattr(m, "path_inputs_backend", "host PyTorch"), "| encoder autocast:", m.encoder_autocast)
+    print("path inputs backend:", getattr(m, "path_inputs_backend", "host PyTorch"), "| encoder autocast:", m.encoder_autocast, "| encoder CUDA graphs:", m.encoder_cuda_graphs)
     # host-only cost of the estimator part: the same step with prepared inputs through the trainer (eager, then graph)
     b, _ = bench.make_batch(B, T, 99, dev)
     tr2 = FlowLoRATrainer(cfm, lr=1e-4)
