@@ -334,6 +334,14 @@ int Estimator::run_gemm(GemmArgs& a) {
   }
   // per-call pointers at the API edge may move between calls
   p.out = a.out; p.rowmask = a.rowmask; p.gn_part = a.gn_part;
+  // L2 prefetch of the next GEMM's weight image (the launch sequence of a plan is fixed once it has run)
+  static int pf_env = -1;
+  if (pf_env < 0) { const char* e = getenv("CVFLOW_GEMM_PFNEXT"); pf_env = e ? atoi(e) : 1; }
+  p.pf_ptr = nullptr; p.pf_bytes = 0;
+  if (pf_env && training_ && (size_t)gemm_idx_ < pl.gemms.size()) {   // measured: -0.065 ms per training step, +0.17 ms per Euler solve (B = 2): training only
+    const GemmParams& nx = pl.gemms[gemm_idx_];
+    if (nx.src_W != p.src_W) { p.pf_ptr = nx.src_W; p.pf_bytes = (unsigned)((long)nx.w_rows * nx.nkb_total * 64 * 2); }
+  }
   prof_begin(0, 2.0 * (double)a.nbatch * a.R * (double)a.n_valid * a.Ktot);
   int r = (kSkip(skip_) & 16u) ? 0 : gemm_launch(p, stream_);
   prof_end();

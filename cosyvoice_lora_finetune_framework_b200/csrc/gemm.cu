@@ -123,6 +123,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       tma_load_2d(smem_base + kb * Cfg::kStageBytes + Cfg::kABytes, &p.tmW, full_bar(kb), kb * BK, nt0 * BN);
     }
   }
+  if (p.pf_ptr && warp == 0 && lane == 1) {     // weights are static: no need to wait for the predecessor
+    const unsigned per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
+    const unsigned off = blockIdx.x * per;
+    if (off < p.pf_bytes) {
+      const unsigned n = min(per, p.pf_bytes - off) & ~15u;
+      if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(p.pf_ptr) + off), "r"(n) : "memory");
+    }
+  }
   pdl_wait();     // everything above overlapped the previous kernel's tail; global memory from here on
   if (threadIdx.x == 0) stamp(1);
 
@@ -641,6 +649,7 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   p->mul_src = a.mul_src; p->ld_aux = a.ld_aux; p->rowmask = a.rowmask; p->resid = a.resid;
   p->ldr = a.ldr;
   p->gn_part = a.gn_part;
+  p->w_rows = a.N;
   static int wpre_env = -1;
   if (wpre_env < 0) { const char* e = getenv("CVFLOW_GEMM_WPRE"); wpre_env = e ? atoi(e) : 1; }
   p->w_prefetch = (a.w_static && wpre_env) ? 1 : 0;

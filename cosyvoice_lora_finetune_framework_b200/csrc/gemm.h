@@ -80,6 +80,9 @@ struct alignas(64) GemmParams {
   CUtensorMap tmOut;    // row-major output, box {32 cols, 32 rows, 1} (TMA store from the epilogue)
   CUtensorMap tmAux;    // pre-activation stash, same box
   int tma_out;          // 1: epilogue stores through TMA (CVFLOW_GEMM_EPI=0: the round-1 path, kept for A/B timing)
+  int w_rows;           // rows of the W image (GemmArgs::N)
+  const void* pf_ptr;   // weights of the NEXT GEMM of the plan (nullable): every CTA asks L2 for one slice of them
+  unsigned pf_bytes;    // (cp.async.bulk.prefetch.L2), so the next launch streams its W operand from L2, not from HBM
   int w_prefetch;       // producer issues the first tile's W loads before griddepcontrol.wait (GemmArgs::w_static)
   int epi_direct;       // 1: epilogue stores as coalesced st.global.v4 after a transposition through the staging tile
   GemmSeg seg[8];
