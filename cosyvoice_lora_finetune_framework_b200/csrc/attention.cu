@@ -41,7 +41,7 @@ int attn_num_sms() {
 // ------------------------------------------------------------------------------------------
 int attn_kinfo_words(int L) { return 8 * ((L + 255) / 256); }
 static int kinfo_bits_off(int B) { return (B + 3) & ~3; }   // bit words start 16-byte aligned
-long attn_kinfo_ints(int B, int L) { return kinfo_bits_off(B) + (long)B * attn_kinfo_words(L); }
+long attn_kinfo_ints(int B, int L) { return kinfo_bits_off(B) + (long)B * attn_kinfo_words(L) + 2L * B; }   // + order table
 
 __global__ void __launch_bounds__(256) attn_kinfo_kernel(const float* __restrict__ mask, int Bp, int L, int nw,
                                                          int* __restrict__ kinfo) {
@@ -65,8 +65,22 @@ __global__ void __launch_bounds__(256) attn_kinfo_kernel(const float* __restrict
     kinfo[b] = m;
   }
 }
+// samples by decreasing valid length: ord[rank] = b, ord[B + rank] = kmax[b] (ties by index: a fixed, deterministic order)
+__global__ void __launch_bounds__(256) attn_order_kernel(const int* __restrict__ kmax, int B, int* __restrict__ ord) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int mine = kmax[b];
+    int rank = 0;
+    for (int o = 0; o < B; ++o) {
+      const int v = kmax[o];
+      rank += (v > mine || (v == mine && o < b)) ? 1 : 0;
+    }
+    ord[rank] = b;
+    ord[B + rank] = mine;
+  }
+}
 int launch_attn_kinfo(const float* mask, int B, int L, int* kinfo, cudaStream_t st) {
   attn_kinfo_kernel<<<B, 256, 0, st>>>(mask, kinfo_bits_off(B), L, attn_kinfo_words(L), kinfo);
+  attn_order_kernel<<<1, 256, 0, st>>>(kinfo, B, kinfo + kinfo_bits_off(B) + B * attn_kinfo_words(L));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -185,6 +199,7 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
   const int tpi = plan.tpi;
   const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
+  const int* ord = attn_order_ptr(kmax_arr, plan.B, L);
   long long* dbg = plan.dbg ? plan.dbg + (long)blockIdx.x * 32 : nullptr;
   auto stamp = [&](int k) {
     if (dbg) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
@@ -212,9 +227,9 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
 // the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
   // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
   AttnItem first;
-  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
   pdl_wait();
-  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kmax_arr);
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
   if (threadIdx.x == 0) stamp(2);
 
   if (warp == 8) {
@@ -223,9 +238,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);   // extent of the next item: load issued early
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);   // extent of the next item: load issued early
         if (!a.act[0]) continue;
         mbar_wait(q_empty(qs), qph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
@@ -260,9 +276,10 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0;
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
         if (!a.act[0]) continue;
         mbar_wait(q_full(qs), qph);
         if (w == 0 && n == 0) stamp(17);
@@ -314,10 +331,11 @@ attn_fwd_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict__ k
     AttnItem nxt = first;
     uint4 nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
     uint4 nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
       const AttnItem a = nxt;
       const uint4 fb0 = nb0, fb1 = nb1;   // validity words of the item's first key block
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kmax_arr);
+      nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
       nb0 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords));
       nb1 = __ldg(reinterpret_cast<const uint4*>(bits_base + (long)nxt.b * nwords) + 1);
       const int qi = (a.tile0 + w) * 128 + r;

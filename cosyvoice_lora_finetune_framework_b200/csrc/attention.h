@@ -45,17 +45,33 @@ struct AttnItem {
   int ext;              // kmax rounded up to 16 (MMA granularity), <= round16(L)
   bool act[2];          // does tile (2*pair + w) contain a valid row?
 };
-__device__ __forceinline__ AttnItem attn_item(int it, int npairs, int tpi, const int* __restrict__ kmax_arr) {
+// Items are enumerated in DESCENDING COST: `ord` (written by attn_order_kernel after attn_kinfo_kernel) lists the samples
+// by decreasing valid length (ord[rank] = b, ord[B + rank] = kmax[b]); item index = (tile pair, rank, head) with the pair
+// slowest, so later pairs (partly or wholly padding) come last. Together with the zig-zag assignment of attn_sched() a CTA
+// that took a long item in one round gets a short one in the next (longest-processing-time pairing): with ragged
+// batches the kernel time is the MEAN of a long and a short item, not the sum of two long ones.
+__device__ __forceinline__ AttnItem attn_item(int it, int npairs, int tpi, int B, const int* __restrict__ ord) {
   AttnItem a;
-  a.tile0 = (it % npairs) * tpi;
-  const int bh = it / npairs;
-  a.h = bh & 7;
-  a.b = bh >> 3;
-  a.kmax = kmax_arr[a.b];
+  const int per_pair = B * 8;
+  const int pair = it / per_pair, rem = it - pair * per_pair;
+  a.tile0 = pair * tpi;
+  a.h = rem & 7;
+  const int rank = rem >> 3;
+  a.b = ord[rank];
+  a.kmax = ord[B + rank];
   a.ext = (a.kmax + 15) & ~15;
   a.act[0] = a.tile0 * 128 < a.kmax;
   a.act[1] = tpi == 2 && (a.tile0 + 1) * 128 < a.kmax;
   return a;
+}
+// k-th item of this CTA (-1: none): rounds alternate direction over the CTAs
+__device__ __forceinline__ int attn_sched(int k, int n_items) {
+  const int G = (int)gridDim.x, base = k * G;
+  const int idx = base + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+  return (base < n_items && idx < n_items) ? idx : -1;
+}
+__device__ __forceinline__ const int* attn_order_ptr(const int* kinfo, int B, int L) {
+  return kinfo + ((B + 3) & ~3) + B * (8 * ((L + 255) / 256));
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit, two K elements per 32-bit column, lane = row)

@@ -59,6 +59,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
   const int tpi = plan.tpi;
   const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
+  const int* ord = attn_order_ptr(kinfo, plan.B, L);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -82,9 +83,9 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
 // the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
   // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
   AttnItem first;
-  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
   pdl_wait();
-  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -92,9 +93,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0;
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
         if (!a.act[0]) continue;
         mbar_wait(q_empty(qs), qph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
@@ -131,9 +133,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
       int qs = 0, ring = 0;
       uint32_t qph = 0, rph = 0, n = 0, m = 0;
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
         if (!a.act[0]) continue;
         mbar_wait(q_full(qs), qph);
         const int nkb = (a.ext + kDqKB - 1) / kDqKB;
@@ -185,9 +188,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict_
     const int* bits_base = kinfo + ((plan.B + 3) & ~3);
     uint32_t n = 0, m = 0;
     AttnItem nxt = first;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
       const AttnItem a = nxt;
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+      nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
       const int q0 = (a.tile0 + w) * 128;
       const int qi = q0 + r;
       const long stat_idx = ((long)a.b * 8 + a.h) * L + qi;
@@ -352,6 +356,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
   const int tpi = plan.tpi;
   const int npairs = ((L + 127) / 128 + tpi - 1) / tpi;   // items per (batch, head)
   const int n_items = plan.B * 8 * npairs;
+  const int* ord = attn_order_ptr(kinfo, plan.B, L);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -374,9 +379,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
 // the per-sample extents were written at the start of the step (estimator) -- not by the previous kernel --
   // so the first item's extent is fetched before the grid-dependency wait and the producer's first TMA is not behind it
   AttnItem first;
-  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+  if (plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
   pdl_wait();
-  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, kinfo);
+  if (!plan.early_kinfo) first = attn_item(min((int)blockIdx.x, n_items - 1), npairs, tpi, plan.B, ord);
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -384,9 +389,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
       int ks = 0, ring = 0;
       uint32_t kph = 0, rph = 0;
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
         if (!a.act[0]) continue;
         mbar_wait(kv_empty(ks), kph ^ 1u);
         const int ntile = a.act[1] ? 2 : 1;
@@ -419,9 +425,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
       uint32_t kph = 0, rph = 0, m = 0;
       uint32_t pcnt[2] = {0u, 0u};  // completed uses of the two P^T/dS^T buffers (parity of p_full)
       AttnItem nxt = first;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
         const AttnItem a = nxt;
-        nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+        nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
         if (!a.act[0]) continue;
         mbar_wait(kv_full(ks), kph);
         const int nqb = (a.ext + kDkvQB - 1) / kDkvQB;
@@ -508,9 +515,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnPlan plan, const int* __restrict
     uint32_t m = 0, sgrp = 0;
     uint32_t scnt[2] = {0u, 0u};   // completed uses of the two score buffers (parity of s_full)
     AttnItem nxt = first;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (int k_it = 0, it = attn_sched(0, n_items), itn; it >= 0; ++k_it, it = itn) {
+        itn = attn_sched(k_it + 1, n_items);
       const AttnItem a = nxt;
-      nxt = attn_item(min(it + (int)gridDim.x, n_items - 1), npairs, tpi, kinfo);
+      nxt = attn_item(itn >= 0 ? itn : it, npairs, tpi, plan.B, ord);
       const int k0 = (a.tile0 + w) * 128;
       const int kj = k0 + r;
       if (!a.act[w]) {   // tile of padding keys only
