@@ -41,7 +41,7 @@ int attn_num_sms() {
 // ------------------------------------------------------------------------------------------
 int attn_kinfo_words(int L) { return 8 * ((L + 255) / 256); }
 static int kinfo_bits_off(int B) { return (B + 3) & ~3; }   // bit words start 16-byte aligned
-long attn_kinfo_ints(int B, int L) { return kinfo_bits_off(B) + (long)B * attn_kinfo_words(L) + 2L * B; }   // + order table
+long attn_kinfo_ints(int B, int L) { return kinfo_bits_off(B) + (long)B * attn_kinfo_words(L) + 2L * B * ((L + 127) / 128); }   // + order table (<= one entry per tile and sample)
 
 __global__ void __launch_bounds__(256) attn_kinfo_kernel(const float* __restrict__ mask, int Bp, int L, int nw,
                                                          int* __restrict__ kinfo) {
@@ -65,22 +65,32 @@ __global__ void __launch_bounds__(256) attn_kinfo_kernel(const float* __restrict
     kinfo[b] = m;
   }
 }
-// samples by decreasing valid length: ord[rank] = b, ord[B + rank] = kmax[b] (ties by index: a fixed, deterministic order)
-__global__ void __launch_bounds__(256) attn_order_kernel(const int* __restrict__ kmax, int B, int* __restrict__ ord) {
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const int mine = kmax[b];
+// (tile pair, sample) entries by decreasing cost (ties by index: a fixed, deterministic order); see attn_item()
+__global__ void __launch_bounds__(256) attn_order_kernel(const int* __restrict__ kmax, int B, int L, int tpi, int* __restrict__ ord) {
+  const int tiles = (L + 127) / 128;
+  const int npairs = (tiles + tpi - 1) / tpi;
+  const int n = npairs * B;
+  auto cost = [&](int e) {
+    const int pair = e / B, b = e - pair * B, km = kmax[b];
+    int act = 0;
+    for (int t = 0; t < tpi; ++t) act += ((pair * tpi + t) * 128 < km) ? 1 : 0;
+    return act * ((km + 15) & ~15);
+  };
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int mine = cost(e);
     int rank = 0;
-    for (int o = 0; o < B; ++o) {
-      const int v = kmax[o];
-      rank += (v > mine || (v == mine && o < b)) ? 1 : 0;
+    for (int o = 0; o < n; ++o) {
+      const int v = cost(o);
+      rank += (v > mine || (v == mine && o < e)) ? 1 : 0;
     }
-    ord[rank] = b;
-    ord[B + rank] = mine;
+    const int pair = e / B, b = e - pair * B;
+    ord[2 * rank] = (pair << 16) | b;
+    ord[2 * rank + 1] = kmax[b];
   }
 }
 int launch_attn_kinfo(const float* mask, int B, int L, int* kinfo, cudaStream_t st) {
   attn_kinfo_kernel<<<B, 256, 0, st>>>(mask, kinfo_bits_off(B), L, attn_kinfo_words(L), kinfo);
-  attn_order_kernel<<<1, 256, 0, st>>>(kinfo, B, kinfo + kinfo_bits_off(B) + B * attn_kinfo_words(L));
+  attn_order_kernel<<<1, 256, 0, st>>>(kinfo, B, L, attn_tiles_per_item(B, L), kinfo + kinfo_bits_off(B) + B * attn_kinfo_words(L));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -45,20 +45,20 @@ struct AttnItem {
   int ext;              // kmax rounded up to 16 (MMA granularity), <= round16(L)
   bool act[2];          // does tile (2*pair + w) contain a valid row?
 };
-// Items are enumerated in DESCENDING COST: `ord` (written by attn_order_kernel after attn_kinfo_kernel) lists the samples
-// by decreasing valid length (ord[rank] = b, ord[B + rank] = kmax[b]); item index = (tile pair, rank, head) with the pair
-// slowest, so later pairs (partly or wholly padding) come last. Together with the zig-zag assignment of attn_sched() a CTA
-// that took a long item in one round gets a short one in the next (longest-processing-time pairing): with ragged
-// batches the kernel time is the MEAN of a long and a short item, not the sum of two long ones.
+// Items are enumerated in DESCENDING COST: `ord` (written by attn_order_kernel after attn_kinfo_kernel) lists the
+// (tile pair, sample) entries by decreasing cost = active 128-row tiles of the pair x valid keys of the sample
+// (ord[2 r] = pair << 16 | b, ord[2 r + 1] = kmax[b]); item index = (entry rank, head). Together with the zig-zag
+// assignment of attn_sched() a CTA that took a long item in one round gets a short one in the next
+// (longest-processing-time pairing): with ragged batches the kernel time is the MEAN of a long and a short item, not the
+// sum of two long ones. Entries whose tiles are all padding sort last and are skipped by every role.
 __device__ __forceinline__ AttnItem attn_item(int it, int npairs, int tpi, int B, const int* __restrict__ ord) {
   AttnItem a;
-  const int per_pair = B * 8;
-  const int pair = it / per_pair, rem = it - pair * per_pair;
-  a.tile0 = pair * tpi;
-  a.h = rem & 7;
-  const int rank = rem >> 3;
-  a.b = ord[rank];
-  a.kmax = ord[B + rank];
+  const int rank = it >> 3;
+  const int2 e = *reinterpret_cast<const int2*>(ord + 2 * rank);
+  a.h = it & 7;
+  a.b = e.x & 0xffff;
+  a.tile0 = (e.x >> 16) * tpi;
+  a.kmax = e.y;
   a.ext = (a.kmax + 15) & ~15;
   a.act[0] = a.tile0 * 128 < a.kmax;
   a.act[1] = tpi == 2 && (a.tile0 + 1) * 128 < a.kmax;
