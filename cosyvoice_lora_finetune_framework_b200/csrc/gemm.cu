@@ -668,7 +668,9 @@ int gemm_prepare(const GemmArgs& a, GemmParams* p, char* err, int errlen) {
   if (bn256_min < 0) { const char* e = getenv("CVFLOW_GEMM_BN256_MIN"); bn256_min = e ? atoi(e) : 4 * 148; }
   int bn = 64;
   if (a.n_valid % 256 == 0 && mtiles * (a.n_valid / 256) >= bn256_min) bn = 256;
-  else if (mtiles * ((a.n_valid + 127) / 128) >= 2 * 148 || a.n_valid > 512) bn = 128;
+  static int bn128_min = -1;   // tuning knob (CVFLOW_GEMM_BN128_MIN)
+  if (bn128_min < 0) { const char* e = getenv("CVFLOW_GEMM_BN128_MIN"); bn128_min = e ? atoi(e) : 2 * 148; }
+  if (bn == 64 && (mtiles * ((a.n_valid + 127) / 128) >= bn128_min || a.n_valid > 512)) bn = 128;
   if (a.transposed_out) bn = 128;
   if (a.ln_gamma) bn = 256;      // the tile must own whole rows
   // deep pipeline for the narrow-N, long-K shapes (N <= 256): see GemmCfg
