@@ -228,7 +228,8 @@ CVFLOW_API int cvflow_profile_read(cvflow_estimator* h, double* ms, int64_t* cou
  *   qkv   16-bit [B][L][ldq], columns [0,512) q | [512,1024) k | [1024,1536) v, 8 heads x 64
  *   keymask fp32 [B][L] (0 = padded key, utils.py:103-109); iso_p = prompt-isolation boundary (0 = off)
  *   kmax_scratch int32 [cvflow_attention_scratch_ints(B, L)] (written: per sample 1 + last valid index, then key
- *   validity bit words)
+ *   validity bit words, then the (tile pair, sample) work items ranked by cost: the persistent CTAs take them longest
+ *   first, in zig-zag rounds, so ragged batches are load-balanced)
  *   o 16-bit [B][L][512]; lse fp32 [B][8][L] (base-2 log-sum-exp of the scaled scores, +inf on empty rows)
  * backward: dout 16-bit [B][L][512] (rows at or beyond a sample's last valid index are taken as zero, as they are
  * in the estimator where every consumer of padded rows is masked); delta_scratch fp32 [B][8][L];
