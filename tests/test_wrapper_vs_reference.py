@@ -45,6 +45,28 @@ def test_wrapper_matches_reference():
             assert ra['prompt_lens']==rb['prompt_lens'], (ra['prompt_lens'],rb['prompt_lens'])
             for k in ('x1','mask','mu','spks','cond'): assert torch.equal(ra[k],rb[k]), k
         print("training wrapper: prepared tensors identical over 4 seeds", ra['prompt_lens'])
+        # every anti-leakage strategy switch of the per-utterance plan (flow_model.py:301-387): silence gap on, dynamic
+        # prompt length off, cross-sample off, text blinding off / always, prompt dropout always
+        from cosyvoice_lora_finetune_framework_b200 import config as OC
+        variants = [dict(silence_padding_enabled=True), dict(dynamic_prompt_enabled=False),
+                    dict(cross_sample_enabled=False, text_blinding_enabled=False),
+                    dict(silence_padding_enabled=True, text_blinding_prob=1.0, prompt_max_ratio=0.6),
+                    dict(prompt_dropout_prob=1.0)]
+        keep_r, keep_o = dict(R.ANTI_LEAKAGE_CONFIG), dict(OC.ANTI_LEAKAGE_CONFIG)
+        try:
+            for vi, var in enumerate(variants):
+                for cfgd, keep in ((R.ANTI_LEAKAGE_CONFIG, keep_r), (OC.ANTI_LEAKAGE_CONFIG, keep_o)):
+                    cfgd.clear(); cfgd.update(keep); cfgd.update(var)
+                for trial in range(3):
+                    ra,rb={},{}
+                    a.decoder.compute_loss=cap(ra); b.decoder.compute_loss=cap(rb)
+                    random.seed(100+trial); a(batch,torch.device('cpu')); random.seed(100+trial); b(batch,torch.device('cpu'))
+                    assert ra['prompt_lens']==rb['prompt_lens'], (var, ra['prompt_lens'],rb['prompt_lens'])
+                    for k in ('x1','mask','mu','spks','cond'): assert torch.equal(ra[k],rb[k]), (var, k)
+        finally:
+            R.ANTI_LEAKAGE_CONFIG.clear(); R.ANTI_LEAKAGE_CONFIG.update(keep_r)
+            OC.ANTI_LEAKAGE_CONFIG.clear(); OC.ANTI_LEAKAGE_CONFIG.update(keep_o)
+        print("anti-leakage variants identical:", len(variants))
         for mode in ('full','mixed'):
             for mod in (RC,):
                 mod.NO_PROMPT_TRAINING_CONFIG.update(enabled=True,mode=mode)
